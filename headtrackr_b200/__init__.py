@@ -1,0 +1,15 @@
+"""headtrackr_b200 — B200-native (sm_100a) replacement for headtrackr's detect+track pixel kernels.
+
+Host-side mirror of the reference's L1 interface:
+    headtrackr_b200.ccv.grayscale / ccv.detect_objects      <- /root/reference/src/ccv.js
+    headtrackr_b200.cascade                                  <- /root/reference/src/cascade.js
+    headtrackr_b200.camshift.Tracker / Rectangle / TrackObj  <- /root/reference/src/camshift.js
+    headtrackr_b200.getWhitebalance                          <- /root/reference/src/whitebalance.js
+    headtrackr_b200.facetrackr.Tracker                       <- /root/reference/src/facetrackr.js (host state machine)
+All pixel work runs in libheadtrackr_b200.so (CUDA, C ABI in include/headtrackr_b200.h).
+"""
+from . import _lib  # noqa: F401
+from .context import Context  # noqa: F401
+from .synth import load_cascade_blob  # noqa: F401
+
+__all__ = ["Context", "load_cascade_blob"]

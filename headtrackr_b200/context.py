@@ -1,0 +1,175 @@
+"""Batched context over the C ABI: frames in, rect lists / track objects out.
+
+Accepts numpy uint8 arrays (host memory) or torch CUDA uint8 tensors (device memory, zero copy) of
+shape (n, H, W, 4) or (H, W, 4).  torch is optional and only used for device-resident batches.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import HtError, Rect, TrackObj, Window
+from .synth import load_cascade_blob
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
+
+
+def _frames_ptr(frames):
+    """-> (address, n, H, W, keepalive)"""
+    if _is_torch(frames):
+        t = frames
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        if not t.is_contiguous() or t.element_size() != 1 or t.shape[-1] != 4:
+            raise ValueError("frames tensor must be contiguous uint8 (n,H,W,4)")
+        return t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t
+    a = np.ascontiguousarray(frames, dtype=np.uint8)
+    if a.ndim == 3:
+        a = a[None]
+    if a.ndim != 4 or a.shape[-1] != 4:
+        raise ValueError("frames must be (n,H,W,4) uint8")
+    return a.ctypes.data, a.shape[0], a.shape[1], a.shape[2], a
+
+
+def rect_to_dict(r, raw=False):
+    d = {"x": r.x, "y": r.y, "width": r.width, "height": r.height}
+    d["neighbor" if raw else "neighbors"] = r.neighbors  # src/ccv.js:232 vs :301
+    d["confidence"] = r.confidence
+    return d
+
+
+class Context:
+    def __init__(self, max_width=1280, max_height=720, max_frames=64, device=0, cascade=None, stream=None,
+                 max_raw_per_frame=0, max_rects_per_frame=0):
+        self._h = C.c_void_p()
+        self._L = _lib.lib()
+        blob = cascade if cascade is not None else load_cascade_blob()
+        cfg = _lib.Config(device, max_width, max_height, max_frames, max_raw_per_frame, max_rects_per_frame,
+                          C.c_void_p(stream) if stream else None)
+        rc = self._L.ht_create(C.byref(self._h), C.byref(cfg), blob, len(blob))
+        if rc != 0:
+            raise HtError(rc, (self._L.ht_last_error(None) or b"").decode())
+        self.K = self._L.ht_max_rects(self._h)
+        self.max_frames = max_frames
+        self.last_warning = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.ht_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise HtError(rc, (self._L.ht_last_error(self._h) or b"").decode())
+        self.last_warning = (self._L.ht_last_error(self._h) or b"").decode() if rc > 0 else None
+        return rc
+
+    def sync(self):
+        return self._check(self._L.ht_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._L.ht_launch_count(self._h))
+
+    # ---- ccv.detect_objects ----
+    def detect_raw(self, frames, interval=5, min_neighbors=1, out_rects=None, out_counts=None):
+        """Low-level: returns (rects, counts).  With torch device outputs the call is asynchronous."""
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        if out_rects is None:
+            rects = (Rect * (n * self.K))()
+            counts = (C.c_int32 * n)()
+            self._check(self._L.ht_detect(self._h, ptr, n, W, H, interval, min_neighbors,
+                                          C.addressof(rects), C.addressof(counts)))
+            return rects, counts
+        self._check(self._L.ht_detect(self._h, ptr, n, W, H, interval, min_neighbors,
+                                      out_rects.data_ptr(), out_counts.data_ptr()))
+        return out_rects, out_counts
+
+    def detect(self, frames, interval=5, min_neighbors=1):
+        """-> per frame, the list detect_objects returns: dicts {x,y,width,height,neighbors,confidence}."""
+        rects, counts = self.detect_raw(frames, interval, min_neighbors)
+        raw = not (min_neighbors > 0)
+        return [[rect_to_dict(rects[f * self.K + i], raw) for i in range(counts[f])] for f in range(len(counts))]
+
+    # ---- camshift ----
+    @staticmethod
+    def _slots(slots, n):
+        if slots is None:
+            return None, None
+        a = (C.c_int32 * n)(*slots)
+        return C.addressof(a), a
+
+    def track_init(self, frames, rects, slots=None, calc_angles=True):
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        r = np.ascontiguousarray(rects, dtype=np.int32).reshape(n, 4)
+        sp, skeep = self._slots(slots, n)
+        self._check(self._L.ht_track_init(self._h, sp, n, ptr, W, H, r.ctypes.data, int(bool(calc_angles))))
+
+    def track_init_from_detect(self, frames, det_rects, det_counts, slots=None, calc_angles=True):
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        sp, skeep = self._slots(slots, n)
+        found = (C.c_int32 * n)()
+        dr = det_rects.data_ptr() if _is_torch(det_rects) else C.addressof(det_rects)
+        dc = det_counts.data_ptr() if _is_torch(det_counts) else C.addressof(det_counts)
+        self._check(self._L.ht_track_init_from_detect(self._h, sp, n, ptr, W, H, dr, dc, int(bool(calc_angles)),
+                                                      C.addressof(found)))
+        return list(found)
+
+    def track(self, frames, slots=None, n_calls=1, out_objs=None, out_windows=None):
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        sp, skeep = self._slots(slots, n)
+        if out_objs is not None:
+            self._check(self._L.ht_track(self._h, sp, n, ptr, W, H, n_calls, out_objs.data_ptr(),
+                                         out_windows.data_ptr() if out_windows is not None else None))
+            return out_objs, out_windows
+        objs = (TrackObj * n)()
+        wins = (Window * n)()
+        self._check(self._L.ht_track(self._h, sp, n, ptr, W, H, n_calls, C.addressof(objs), C.addressof(wins)))
+        return ([dict(x=o.x, y=o.y, width=o.width, height=o.height, angle=o.angle) for o in objs],
+                [(w.x, w.y, w.width, w.height) for w in wins])
+
+    def backprojection(self, frame, slot=0):
+        ptr, n, H, W, keep = _frames_ptr(frame)
+        out = np.zeros((H, W, 4), np.uint8)
+        self._check(self._L.ht_backprojection(self._h, slot, ptr, W, H, out.ctypes.data))
+        return out
+
+    def whitebalance(self, frames):
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        out = np.zeros(n, np.float64)
+        self._check(self._L.ht_whitebalance(self._h, ptr, n, W, H, out.ctypes.data))
+        return out
+
+    # ---- introspection (parity tests) ----
+    def plan_info(self, W, H, interval=5):
+        ns, su = C.c_int32(), C.c_int32()
+        sw, sh = (C.c_int32 * 128)(), (C.c_int32 * 128)()
+        self._check(self._L.ht_plan_info(self._h, W, H, interval, C.addressof(ns), C.addressof(su),
+                                         C.addressof(sw), C.addressof(sh), 128))
+        return dict(n_slots=ns.value, scale_upto=su.value, w=list(sw[:ns.value]), h=list(sh[:ns.value]))
+
+    def debug_plane(self, frame, slot, q=0):
+        w, h = C.c_int32(), C.c_int32()
+        buf = np.zeros(2048 * 2048, np.uint8)
+        rc = self._L.ht_debug_plane(self._h, frame, slot, q, buf.ctypes.data, buf.size, C.addressof(w), C.addressof(h))
+        self._check(rc)
+        return buf[: w.value * h.value].reshape(h.value, w.value).copy()
+
+    def debug_raw(self, frame, cap=65536):
+        out = (Rect * cap)()
+        cnt = C.c_int32()
+        self._check(self._L.ht_debug_raw(self._h, frame, C.addressof(out), cap, C.addressof(cnt)))
+        return [(r.x, r.y, r.width, r.height, r.confidence, r.neighbors) for r in out[: min(cnt.value, cap)]], cnt.value
+
+    def debug_model_hist(self, slot):
+        out = np.zeros(4096, np.uint32)
+        self._check(self._L.ht_debug_model_hist(self._h, slot, out.ctypes.data))
+        return out

@@ -1,0 +1,808 @@
+// ht_api.cu — host side of libheadtrackr_b200.so: the C ABI declared in include/headtrackr_b200.h,
+// the pyramid/tile planner, and the kernel launches.  sm_100a only; there is no CPU fallback.
+#include "../../include/headtrackr_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "ht_common.cuh"
+#include "ht_detect.cuh"
+#include "ht_track.cuh"
+
+using namespace ht;
+
+static_assert(sizeof(ht_rect) == sizeof(Rect), "ht_rect layout");
+static_assert(sizeof(ht_rect) == 48, "ht_rect is 48 bytes");
+static_assert(sizeof(ht_trackobj) == 24, "ht_trackobj is 24 bytes");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+inline T align_up(T v, T a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// device buffer that only ever grows (no allocation on the steady-state per-frame path)
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Plan: everything that depends only on (w, h, interval) — src/ccv.js:110-160
+struct Plan {
+  int w = 0, h = 0, interval = 0;
+  int next = 0, scale_upto = 0, n_slots = 0;
+  std::vector<int> slot_w, slot_h;
+  std::vector<int> plane_id;            // [slot*4+q] -> dense plane id or -1
+  std::vector<DevPlane> planes;
+  std::vector<DevJob> jobs;             // sorted by generation
+  std::vector<TapEnt> taps;
+  std::vector<DevPyrTile> pyr_tiles;    // grouped by generation
+  std::vector<int> gen_tile_begin;      // size n_gens+1
+  std::vector<DevScale> scales;
+  std::vector<DevCascTile> casc_tiles;
+  size_t arena_stride = 0;
+  uint32_t windows_per_frame = 0;
+  DevBuf dev;
+  DevPlan dplan{};
+};
+
+int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std::string &err) {
+  P.w = W; P.h = H; P.interval = interval;
+  const double scale = std::pow(2.0, 1.0 / (interval + 1.0));                      // ccv.js:110
+  P.next = interval + 1;                                                            // ccv.js:111
+  P.scale_upto = (int)std::floor(std::log((double)std::min(casc_w, casc_h)) / std::log(scale));  // :112
+  P.n_slots = P.scale_upto + P.next * 2;                                            // :113
+  if (P.n_slots > 120 || P.scale_upto < 1) { err = "unsupported interval"; return HT_ERR_ARG; }
+  P.slot_w.assign(P.n_slots, 0); P.slot_h.assign(P.n_slots, 0);
+  P.slot_w[0] = W; P.slot_h[0] = H;
+  for (int i = 1; i <= interval; ++i) {                                             // :117-120
+    P.slot_w[i] = (int)std::floor((double)W / std::pow(scale, (double)i));
+    P.slot_h[i] = (int)std::floor((double)H / std::pow(scale, (double)i));
+  }
+  for (int i = P.next; i < P.n_slots; ++i) {                                        // :124-127
+    P.slot_w[i] = P.slot_w[i - P.next] / 2;
+    P.slot_h[i] = P.slot_h[i - P.next] / 2;
+  }
+  for (int i = 0; i < P.n_slots; ++i)
+    if (P.slot_w[i] <= 0 || P.slot_h[i] <= 0) {
+      err = "frame too small: pyramid level " + std::to_string(i) + " would be 0-sized (a browser throws here)";
+      return HT_ERR_SIZE;
+    }
+  // ---- planes ----
+  P.plane_id.assign((size_t)P.n_slots * 4, -1);
+  size_t off = 0;
+  auto add_plane = [&](int slot, int q) {
+    DevPlane pl;
+    pl.w = P.slot_w[slot]; pl.h = P.slot_h[slot];
+    pl.pitch = align_up(pl.w, 16);
+    off = align_up(off, (size_t)256);
+    pl.off = (uint32_t)off;
+    off += (size_t)pl.pitch * pl.h;
+    P.plane_id[(size_t)slot * 4 + q] = (int)P.planes.size();
+    P.planes.push_back(pl);
+  };
+  for (int s = 0; s < P.n_slots; ++s) {
+    add_plane(s, 0);
+    if (s >= 2 * P.next) for (int q = 1; q < 4; ++q) add_plane(s, q);
+  }
+  if (off > 0xF0000000ull) { err = "frame too large"; return HT_ERR_SIZE; }
+  P.arena_stride = align_up(off, (size_t)256);
+  // ---- resample jobs, by generation ----
+  std::vector<int> gen(P.n_slots, 0);
+  int n_gens = 1;
+  for (int s = 1; s < P.n_slots; ++s) {
+    gen[s] = (s <= interval) ? 1 : gen[s - P.next] + 1;
+    n_gens = std::max(n_gens, gen[s] + 1);
+  }
+  struct JobSpec { int gen, src_slot, dst_slot, q, sx, sy, sw, sh, dw, dh; };
+  std::vector<JobSpec> specs;
+  for (int s = 1; s < P.n_slots; ++s) {
+    const int src = (s <= interval) ? 0 : s - P.next;
+    const int sw = P.slot_w[src], sh = P.slot_h[src], w = P.slot_w[s], h = P.slot_h[s];
+    specs.push_back({gen[s], src, s, 0, 0, 0, sw, sh, w, h});                       // :121, :128
+    if (s >= 2 * P.next) {
+      specs.push_back({gen[s], src, s, 1, 1, 0, sw - 1, sh, w - 2, h});            // :135
+      specs.push_back({gen[s], src, s, 2, 0, 1, sw, sh - 1, w, h - 2});            // :140
+      specs.push_back({gen[s], src, s, 3, 1, 1, sw - 1, sh - 1, w - 2, h - 2});    // :145
+    }
+  }
+  std::stable_sort(specs.begin(), specs.end(), [](const JobSpec &a, const JobSpec &b) { return a.gen < b.gen; });
+  P.gen_tile_begin.assign(n_gens + 1, 0);
+  int cur_gen = 1;
+  P.gen_tile_begin[0] = 0; P.gen_tile_begin[1] = 0;
+  for (const JobSpec &js : specs) {
+    while (cur_gen < js.gen) { ++cur_gen; P.gen_tile_begin[cur_gen] = (int)P.pyr_tiles.size(); }
+    DevJob j{};
+    j.src = P.plane_id[(size_t)js.src_slot * 4];
+    j.dst = P.plane_id[(size_t)js.dst_slot * 4 + js.q];
+    int dw = js.dw, dh = js.dh;
+    if (dw <= 0 || dh <= 0 || js.sw <= 0 || js.sh <= 0) dw = dh = 0;  // paints nothing
+    j.dw = dw; j.dh = dh;
+    if (dw > 0) {
+      if (dw > 32767 || dh > 32767 || js.sx + js.sw > 65535 || js.sy + js.sh > 65535) { err = "frame too large"; return HT_ERR_SIZE; }
+      auto make_taps = [&](int d, int s, int s0) {
+        const uint32_t first = (uint32_t)P.taps.size();
+        for (int X = 0; X < d; ++X) {
+          const long long un = (2LL * X + 1) * s - d;
+          long long x0 = un / (2LL * d);
+          if (un < 0 && (un % (2LL * d)) != 0) --x0;
+          const long long f = un - x0 * 2LL * d;
+          const long long a = std::min<long long>(std::max<long long>(x0, 0), s - 1);
+          const long long b = std::min<long long>(std::max<long long>(x0 + 1, 0), s - 1);
+          TapEnt t; t.a = (uint16_t)(a + s0); t.b = (uint16_t)(b + s0); t.f = (uint16_t)f; t.pad_ = 0;
+          P.taps.push_back(t);
+        }
+        return first;
+      };
+      j.col_off = make_taps(dw, js.sw, js.sx);
+      j.row_off = make_taps(dh, js.sh, js.sy);
+      const unsigned long long d = 4ull * dw * dh;
+      const unsigned __int128 nmax = (unsigned __int128)d * 255 + d / 2 + 1;
+      if (nmax >= ((unsigned __int128)1 << 32)) { err = "frame too large for 32-bit bilinear numerators"; return HT_ERR_SIZE; }
+      int k = 32;
+      while ((((unsigned __int128)1) << k) <= nmax * d) ++k;
+      const unsigned __int128 M = ((((unsigned __int128)1) << k) / d) + 1;
+      if (k > 63 || M >= ((unsigned __int128)1 << 32) || nmax * M >= ((unsigned __int128)1 << 64)) {
+        err = "frame too large for the exact-division constants"; return HT_ERR_SIZE;
+      }
+      j.magic = (uint32_t)M; j.shift = (uint32_t)k; j.half = (uint32_t)(d / 2);
+    }
+    const int job_id = (int)P.jobs.size();
+    P.jobs.push_back(j);
+    const DevPlane &dp = P.planes[j.dst];
+    for (int ty = 0; ty < (dp.h + 7) / 8; ++ty)
+      for (int tx = 0; tx < (dp.pitch + 127) / 128; ++tx) {
+        DevPyrTile t; t.job = (uint16_t)job_id; t.tx = (uint16_t)tx; t.ty = (uint16_t)ty; t.pad_ = 0;
+        P.pyr_tiles.push_back(t);
+      }
+  }
+  while (cur_gen < n_gens) { ++cur_gen; P.gen_tile_begin[cur_gen] = (int)P.pyr_tiles.size(); }
+  P.gen_tile_begin[n_gens] = (int)P.pyr_tiles.size();
+  // ---- scales and cascade tiles ----
+  double scale_x = 1.0;
+  uint32_t win_base = 0;
+  for (int i = 0; i < P.scale_upto; ++i) {                                          // ccv.js:154
+    DevScale sc{};
+    sc.p0 = P.plane_id[(size_t)i * 4];
+    sc.p1 = P.plane_id[(size_t)(i + P.next) * 4];
+    for (int q = 0; q < 4; ++q) sc.p2[q] = P.plane_id[(size_t)(i + 2 * P.next) * 4 + q];
+    sc.qw = P.slot_w[i + 2 * P.next] - casc_w / 4;                                  // :155
+    sc.qh = P.slot_h[i + 2 * P.next] - casc_h / 4;                                  // :156
+    sc.win_base = win_base;
+    sc.scale_x = scale_x;
+    if (sc.qw > 0 && sc.qh > 0) {
+      win_base += 4u * (uint32_t)sc.qw * (uint32_t)sc.qh;
+      for (int ty = 0; ty < (sc.qh + TH - 1) / TH; ++ty)
+        for (int tx = 0; tx < (sc.qw + TW - 1) / TW; ++tx) {
+          DevCascTile t; t.scale = (uint16_t)i; t.tx = (uint16_t)tx; t.ty = (uint16_t)ty; t.pad_ = 0;
+          P.casc_tiles.push_back(t);
+        }
+    }
+    P.scales.push_back(sc);
+    scale_x *= scale;                                                               // :244
+  }
+  P.windows_per_frame = win_base;
+  // ---- upload ----
+  size_t o_planes = 0, o_jobs = align_up(o_planes + P.planes.size() * sizeof(DevPlane), (size_t)256);
+  size_t o_taps = align_up(o_jobs + P.jobs.size() * sizeof(DevJob), (size_t)256);
+  size_t o_pt = align_up(o_taps + P.taps.size() * sizeof(TapEnt), (size_t)256);
+  size_t o_sc = align_up(o_pt + P.pyr_tiles.size() * sizeof(DevPyrTile), (size_t)256);
+  size_t o_ct = align_up(o_sc + P.scales.size() * sizeof(DevScale), (size_t)256);
+  size_t total = align_up(o_ct + P.casc_tiles.size() * sizeof(DevCascTile), (size_t)256);
+  std::vector<uint8_t> host(total, 0);
+  memcpy(host.data() + o_planes, P.planes.data(), P.planes.size() * sizeof(DevPlane));
+  memcpy(host.data() + o_jobs, P.jobs.data(), P.jobs.size() * sizeof(DevJob));
+  memcpy(host.data() + o_taps, P.taps.data(), P.taps.size() * sizeof(TapEnt));
+  memcpy(host.data() + o_pt, P.pyr_tiles.data(), P.pyr_tiles.size() * sizeof(DevPyrTile));
+  memcpy(host.data() + o_sc, P.scales.data(), P.scales.size() * sizeof(DevScale));
+  memcpy(host.data() + o_ct, P.casc_tiles.data(), P.casc_tiles.size() * sizeof(DevCascTile));
+  if (P.dev.reserve(total) != cudaSuccess) { err = "cudaMalloc(plan) failed"; return HT_ERR_CUDA; }
+  if (cudaMemcpy(P.dev.p, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) { err = "plan upload failed"; return HT_ERR_CUDA; }
+  uint8_t *b = P.dev.as<uint8_t>();
+  P.dplan.planes = reinterpret_cast<const DevPlane *>(b + o_planes);
+  P.dplan.jobs = reinterpret_cast<const DevJob *>(b + o_jobs);
+  P.dplan.taps = reinterpret_cast<const TapEnt *>(b + o_taps);
+  P.dplan.pyr_tiles = reinterpret_cast<const DevPyrTile *>(b + o_pt);
+  P.dplan.scales = reinterpret_cast<const DevScale *>(b + o_sc);
+  P.dplan.casc_tiles = reinterpret_cast<const DevCascTile *>(b + o_ct);
+  P.dplan.n_planes = (int)P.planes.size(); P.dplan.n_jobs = (int)P.jobs.size();
+  P.dplan.n_scales = (int)P.scales.size(); P.dplan.n_casc_tiles = (int)P.casc_tiles.size();
+  return HT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// "HTC1" cascade blob (tools/pack_cascade.py) -> device tables
+struct HostCascade {
+  int n_stages = 0, n_features = 0, width = 0, height = 0;
+  std::vector<DevStage> stages;
+  std::vector<DevFeat> feats;
+  std::vector<double2> alphas;
+};
+
+int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &err) {
+  const uint8_t *b = static_cast<const uint8_t *>(blob);
+  if (!b || len < 24 || memcmp(b, "HTC1", 4) != 0) { err = "cascade blob: bad magic"; return HT_ERR_CASCADE; }
+  uint32_t hdr[5];
+  memcpy(hdr, b + 4, 20);
+  hc.n_stages = (int)hdr[0]; hc.n_features = (int)hdr[1]; hc.width = (int)hdr[2]; hc.height = (int)hdr[3];
+  if (hc.n_stages < 1 || hc.n_stages > MAX_STAGES) { err = "cascade blob: stage count"; return HT_ERR_CASCADE; }
+  if (hc.width != 24 || hc.height != 24) { err = "cascade blob: only 24x24 BBF windows are supported"; return HT_ERR_CASCADE; }
+  const size_t need = 24 + (size_t)hc.n_stages * 16 + (size_t)hc.n_features * 48;
+  if (len < need) { err = "cascade blob: truncated"; return HT_ERR_CASCADE; }
+  const uint8_t *ps = b + 24, *pf = ps + (size_t)hc.n_stages * 16, *pa = pf + (size_t)hc.n_features * 32;
+  int total = 0;
+  for (int j = 0; j < hc.n_stages; ++j) {
+    uint32_t cnt, first; double thr;
+    memcpy(&cnt, ps + 16 * j, 4); memcpy(&first, ps + 16 * j + 4, 4); memcpy(&thr, ps + 16 * j + 8, 8);
+    if ((int)first != total || (int)(first + cnt) > hc.n_features) { err = "cascade blob: stage table"; return HT_ERR_CASCADE; }
+    total += (int)cnt;
+    DevStage st; st.first = (int)first; st.count = (int)cnt; st.threshold = thr;
+    hc.stages.push_back(st);
+  }
+  if (total != hc.n_features) { err = "cascade blob: feature count"; return HT_ERR_CASCADE; }
+  auto point_off = [&](int z, int x, int y, bool &ok) -> uint16_t {
+    const int lim = (24 >> z) - 1;
+    if (z < 0 || z > 2 || x < 0 || y < 0 || x > lim || y > lim) { ok = false; return 0; }
+    if (z == 0) return (uint16_t)(y * TP + x);
+    if (z == 1) return (uint16_t)(REGION + TP + 2 * x + 2 * y * TP);
+    return (uint16_t)(REGION + 4 * x + 4 * y * TP);
+  };
+  for (int k = 0; k < hc.n_features; ++k) {
+    const uint8_t *r = pf + (size_t)k * 32;
+    DevFeat f{};
+    const int size = r[0];
+    if (size < 1 || size > 5) { err = "cascade blob: feature size"; return HT_ERR_CASCADE; }
+    f.size = (uint16_t)size;
+    bool ok = true;
+    for (int side = 0; side < 2; ++side) {
+      const uint8_t *z = r + (side ? 17 : 2), *x = z + 5, *y = z + 10;
+      uint16_t *dst = side ? f.n : f.p;
+      if ((int8_t)z[0] < 0) { err = "cascade blob: slot 0 must be a valid point (src/ccv.js:191-192)"; return HT_ERR_CASCADE; }
+      const uint16_t first = point_off((int8_t)z[0], x[0], y[0], ok);
+      for (int q = 0; q < 5; ++q) {
+        if (q < size && (int8_t)z[q] >= 0) dst[q] = point_off((int8_t)z[q], x[q], y[q], ok);
+        else dst[q] = first;  // min/max are idempotent: unused slots repeat slot 0
+      }
+    }
+    if (!ok) { err = "cascade blob: point out of the 24x24 window"; return HT_ERR_CASCADE; }
+    hc.feats.push_back(f);
+    double a[2];
+    memcpy(a, pa + (size_t)k * 16, 16);
+    hc.alphas.push_back(make_double2(a[0], a[1]));
+  }
+  return HT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct ht_ctx {
+  ht_config cfg{};
+  int K = 64, raw_cap = 1024;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+
+  HostCascade hc;
+  DevBuf d_casc;
+  DevCascade dcasc{};
+
+  std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
+  Plan *last_plan = nullptr;
+  int last_n = 0;
+
+  DevBuf arena, d_frames, raw_keys, raw_conf, raw_count, sorted, labels, seq2, d_out_rects, d_out_counts, d_flags;
+  DevBuf model_hist, cur_hist, track_state, d_slots, d_rects, d_found, d_objs, d_windows, d_wb_sums, d_wb_out, d_scratch;
+
+  int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return ctx->fail(HT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+namespace {
+
+bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int get_plan(ht_ctx *ctx, int w, int h, int interval, Plan **out) {
+  if (w <= 0 || h <= 0 || interval < 0 || interval > 15) return ctx->fail(HT_ERR_ARG, "bad w/h/interval");
+  if (w > ctx->cfg.max_width || h > ctx->cfg.max_height)
+    return ctx->fail(HT_ERR_SIZE, "frame %dx%d exceeds the context maximum %dx%d", w, h, ctx->cfg.max_width, ctx->cfg.max_height);
+  auto key = std::make_tuple(w, h, interval);
+  auto it = ctx->plans.find(key);
+  if (it == ctx->plans.end()) {
+    std::unique_ptr<Plan> p(new Plan());
+    std::string err;
+    int rc = build_plan(*p, w, h, interval, ctx->hc.width, ctx->hc.height, err);
+    if (rc != HT_OK) return ctx->fail(rc, "%s", err.c_str());
+    it = ctx->plans.emplace(key, std::move(p)).first;
+  }
+  *out = it->second.get();
+  return HT_OK;
+}
+
+// stage n frames on the device if the caller passed host memory
+int device_frames(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, const uint8_t **out) {
+  if (!rgba) return ctx->fail(HT_ERR_ARG, "rgba is NULL");
+  if ((reinterpret_cast<uintptr_t>(rgba) & 3u) != 0) return ctx->fail(HT_ERR_ARG, "rgba must be 4-byte aligned");
+  if (is_device_ptr(rgba)) { *out = rgba; return HT_OK; }
+  const size_t bytes = (size_t)n * w * h * 4;
+  CK(ctx->d_frames.reserve(bytes));
+  CK(cudaMemcpyAsync(ctx->d_frames.p, rgba, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *out = ctx->d_frames.as<uint8_t>();
+  return HT_OK;
+}
+
+int check_batch(ht_ctx *ctx, int n) {
+  if (n <= 0 || n > ctx->cfg.max_frames) return ctx->fail(HT_ERR_ARG, "n=%d outside [1,%d]", n, ctx->cfg.max_frames);
+  return HT_OK;
+}
+
+int upload_slots(ht_ctx *ctx, const int32_t *slots, int n, const int32_t **d_slots) {
+  *d_slots = nullptr;
+  if (!slots) return HT_OK;
+  if (is_device_ptr(slots)) { *d_slots = slots; return HT_OK; }
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= ctx->cfg.max_frames) return ctx->fail(HT_ERR_ARG, "slot %d out of range", slots[i]);
+  CK(ctx->d_slots.reserve(sizeof(int32_t) * ctx->cfg.max_frames));
+  CK(cudaMemcpyAsync(ctx->d_slots.p, slots, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  *d_slots = ctx->d_slots.as<int32_t>();
+  return HT_OK;
+}
+
+int ensure_tracker_buffers(ht_ctx *ctx) {
+  const size_t mf = (size_t)ctx->cfg.max_frames;
+  if (!ctx->model_hist.p) {
+    CK(ctx->model_hist.reserve(mf * 4096 * sizeof(uint32_t)));
+    CK(ctx->cur_hist.reserve(mf * 4096 * sizeof(uint32_t)));
+    CK(ctx->track_state.reserve(mf * sizeof(TrackState)));
+    CK(cudaMemsetAsync(ctx->track_state.p, 0, mf * sizeof(TrackState), ctx->stream));
+    CK(ctx->d_rects.reserve(mf * 4 * sizeof(int32_t)));
+    CK(ctx->d_found.reserve(mf * sizeof(int32_t)));
+    CK(ctx->d_objs.reserve(mf * 6 * sizeof(int32_t)));
+    CK(ctx->d_windows.reserve(mf * 4 * sizeof(int32_t)));
+  }
+  return HT_OK;
+}
+
+int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_t *hist) {
+  const int n_px = w * h;
+  int chunks = 1;
+  if (n < 592) chunks = std::min(64, std::max(1, 1184 / n));  // keep ~8 CTAs per SM busy for small batches
+  if (chunks > 1) CK(cudaMemsetAsync(hist, 0, (size_t)n * 4096 * sizeof(uint32_t), ctx->stream));
+  k_hist<<<dim3(chunks, n), 256, 0, ctx->stream>>>(d_rgba, (size_t)n_px * 4, n_px, hist, chunks);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  return HT_OK;
+}
+
+int track_init_common(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *d_rgba, int w, int h,
+                      const int32_t *d_rects, int calc_angles, int32_t *out_found) {
+  const int32_t *d_slots = nullptr;
+  int rc = upload_slots(ctx, slots, n, &d_slots);
+  if (rc != HT_OK) return rc;
+  const bool found_dev = out_found && is_device_ptr(out_found);
+  int32_t *d_found = out_found ? (found_dev ? out_found : ctx->d_found.as<int32_t>()) : nullptr;
+  k_track_init<<<n, 256, 0, ctx->stream>>>(d_rgba, (size_t)w * h * 4, w, h, d_slots, d_rects, calc_angles ? 1 : 0,
+                                           ctx->model_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), d_found);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  if (out_found && !found_dev) {
+    CK(cudaMemcpyAsync(out_found, d_found, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return HT_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+uint32_t ht_version(void) { return (1u << 16) | 0u; }
+
+const char *ht_last_error(const ht_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ht_max_rects(const ht_ctx *ctx) { return ctx ? ctx->K : 0; }
+
+uint64_t ht_launch_count(const ht_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size_t blob_len) {
+  if (!out || !cfg) { g_create_error = "ht_create: NULL argument"; return HT_ERR_ARG; }
+  *out = nullptr;
+  if (cfg->max_width <= 0 || cfg->max_height <= 0 || cfg->max_frames <= 0) { g_create_error = "ht_create: bad maxima"; return HT_ERR_ARG; }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    g_create_error = "ht_create: no CUDA device (this library has no CPU fallback)";
+    return HT_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= n_dev) { g_create_error = "ht_create: bad device ordinal"; return HT_ERR_ARG; }
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { g_create_error = "ht_create: cudaGetDeviceProperties failed"; return HT_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "ht_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) + ", this build is sm_100a only";
+    return HT_ERR_CUDA;
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { g_create_error = "ht_create: cudaSetDevice failed"; return HT_ERR_CUDA; }
+  std::unique_ptr<ht_ctx> c(new ht_ctx());
+  c->cfg = *cfg;
+  c->K = cfg->max_rects_per_frame > 0 ? cfg->max_rects_per_frame : 64;
+  c->raw_cap = cfg->max_raw_per_frame > 0 ? cfg->max_raw_per_frame : 1024;
+  std::string err;
+  int rc = parse_cascade(cascade_blob, blob_len, c->hc, err);
+  if (rc != HT_OK) { g_create_error = "ht_create: " + err; return rc; }
+  if (cfg->cuda_stream) c->stream = static_cast<cudaStream_t>(cfg->cuda_stream);
+  else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "ht_create: stream"; return HT_ERR_CUDA; }
+    c->own_stream = true;
+  }
+  // cascade tables
+  const HostCascade &hc = c->hc;
+  const size_t o_feat = 0, o_alpha = align_up(o_feat + hc.feats.size() * sizeof(DevFeat), (size_t)256);
+  const size_t o_stage = align_up(o_alpha + hc.alphas.size() * sizeof(double2), (size_t)256);
+  const size_t total = o_stage + hc.stages.size() * sizeof(DevStage);
+  std::vector<uint8_t> host(total, 0);
+  memcpy(host.data() + o_feat, hc.feats.data(), hc.feats.size() * sizeof(DevFeat));
+  memcpy(host.data() + o_alpha, hc.alphas.data(), hc.alphas.size() * sizeof(double2));
+  memcpy(host.data() + o_stage, hc.stages.data(), hc.stages.size() * sizeof(DevStage));
+  if (c->d_casc.reserve(total) != cudaSuccess ||
+      cudaMemcpy(c->d_casc.p, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
+    g_create_error = "ht_create: cascade upload failed"; return HT_ERR_CUDA;
+  }
+  uint8_t *b = c->d_casc.as<uint8_t>();
+  c->dcasc.feat = reinterpret_cast<const DevFeat *>(b + o_feat);
+  c->dcasc.alpha = reinterpret_cast<const double2 *>(b + o_alpha);
+  c->dcasc.stage = reinterpret_cast<const DevStage *>(b + o_stage);
+  c->dcasc.n_stages = hc.n_stages;
+  // stage groups for queue compaction: {0,1} {2,3} {4,5} {6,7,8} {9..}
+  {
+    const int cuts[] = {0, 2, 4, 6, 9};
+    int g = 0;
+    for (int cpos : cuts) if (cpos < hc.n_stages) c->dcasc.group_first[g++] = cpos;
+    c->dcasc.group_first[g] = hc.n_stages;
+    c->dcasc.n_groups = g;
+  }
+  // per-frame result buffers
+  const size_t mf = (size_t)cfg->max_frames;
+  bool ok = c->raw_keys.reserve(mf * c->raw_cap * sizeof(uint32_t)) == cudaSuccess &&
+            c->raw_conf.reserve(mf * c->raw_cap * sizeof(double)) == cudaSuccess &&
+            c->raw_count.reserve(mf * sizeof(uint32_t)) == cudaSuccess &&
+            c->sorted.reserve(mf * c->raw_cap * sizeof(Rect)) == cudaSuccess &&
+            c->labels.reserve(mf * c->raw_cap * sizeof(int)) == cudaSuccess &&
+            c->seq2.reserve(mf * c->raw_cap * sizeof(Rect)) == cudaSuccess &&
+            c->d_out_rects.reserve(mf * c->K * sizeof(Rect)) == cudaSuccess &&
+            c->d_out_counts.reserve(mf * sizeof(int32_t)) == cudaSuccess &&
+            c->d_flags.reserve(256) == cudaSuccess;
+  if (!ok) { g_create_error = "ht_create: cudaMalloc failed"; return HT_ERR_CUDA; }
+  cudaMemset(c->d_flags.p, 0, 256);
+  cudaMemset(c->raw_count.p, 0, mf * sizeof(uint32_t));
+  *out = c.release();
+  return HT_OK;
+}
+
+void ht_destroy(ht_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->plans) kv.second->dev.release();
+  DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
+                    &ctx->labels, &ctx->seq2, &ctx->d_out_rects, &ctx->d_out_counts, &ctx->d_flags, &ctx->model_hist,
+                    &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
+                    &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
+  for (DevBuf *b : bufs) b->release();
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int ht_sync(ht_ctx *ctx) {
+  if (!ctx) return HT_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  int32_t flags[2] = {0, 0};
+  CK(cudaMemcpy(flags, ctx->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost));
+  if (flags[0] || flags[1]) {
+    CK(cudaMemset(ctx->d_flags.p, 0, sizeof(flags)));
+    if (flags[1]) return ctx->fail(HT_ERR_STATE, "ht_track on a tracker slot that was never initialised");
+    return ctx->fail(HT_WARN_OVERFLOW, "a per-frame detection list overflowed its capacity (raw %d / K %d) and was truncated",
+                     ctx->raw_cap, ctx->K);
+  }
+  return HT_OK;
+}
+
+int ht_detect(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors,
+              ht_rect *out_rects, int32_t *out_counts) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!out_rects || !out_counts) return ctx->fail(HT_ERR_ARG, "output pointers are NULL");
+  int rc = check_batch(ctx, n);
+  if (rc != HT_OK) return rc;
+  CK(cudaSetDevice(ctx->cfg.device));
+  Plan *P = nullptr;
+  rc = get_plan(ctx, w, h, interval, &P);
+  if (rc != HT_OK) return rc;
+  const uint8_t *d_rgba = nullptr;
+  rc = device_frames(ctx, rgba, n, w, h, &d_rgba);
+  if (rc != HT_OK) return rc;
+  CK(ctx->arena.reserve(P->arena_stride * (size_t)n));
+  uint8_t *arena = ctx->arena.as<uint8_t>();
+  cudaStream_t st = ctx->stream;
+  const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
+  Rect *d_rects = rects_dev ? reinterpret_cast<Rect *>(out_rects) : ctx->d_out_rects.as<Rect>();
+  int32_t *d_counts = counts_dev ? out_counts : ctx->d_out_counts.as<int32_t>();
+
+  CK(cudaMemsetAsync(ctx->raw_count.p, 0, sizeof(uint32_t) * n, st));
+  // K1 grayscale -> plane 0
+  {
+    const int qpr = (w + 3) / 4;
+    const unsigned blocks = (unsigned)(((size_t)qpr * h + 255) / 256);
+    const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgba) & 15u) == 0);
+    if (vec) k_gray<true><<<dim3(blocks, n), 256, 0, st>>>(d_rgba, (size_t)w * h * 4, arena, P->arena_stride, w, h, P->planes[0].pitch, qpr);
+    else k_gray<false><<<dim3(blocks, n), 256, 0, st>>>(d_rgba, (size_t)w * h * 4, arena, P->arena_stride, w, h, P->planes[0].pitch, qpr);
+    ++ctx->launches;
+  }
+  // K2 pyramid generations
+  for (size_t g = 1; g + 1 < P->gen_tile_begin.size(); ++g) {
+    const int t0 = P->gen_tile_begin[g], t1 = P->gen_tile_begin[g + 1];
+    if (t1 > t0) {
+      k_resample<<<dim3(t1 - t0, n), 256, 0, st>>>(P->dplan, t0, arena, P->arena_stride);
+      ++ctx->launches;
+    }
+  }
+  // K3 cascade
+  if (!P->casc_tiles.empty()) {
+    k_cascade<<<dim3((unsigned)P->casc_tiles.size(), n), CASCADE_THREADS, 0, st>>>(
+        P->dplan, ctx->dcasc, arena, P->arena_stride, ctx->raw_keys.as<uint32_t>(), ctx->raw_conf.as<double>(),
+        ctx->raw_count.as<uint32_t>(), ctx->raw_cap);
+    ++ctx->launches;
+  }
+  // K4 sort + group
+  k_group<<<(n + 3) / 4, 128, 0, st>>>(P->dplan, n, ctx->raw_keys.as<uint32_t>(), ctx->raw_conf.as<double>(),
+                                       ctx->raw_count.as<uint32_t>(), ctx->raw_cap, ctx->sorted.as<Rect>(),
+                                       ctx->labels.as<int>(), ctx->seq2.as<Rect>(), min_neighbors, d_rects, d_counts, ctx->K,
+                                       ctx->d_flags.as<int32_t>());
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  ctx->last_plan = P;
+  ctx->last_n = n;
+  if (!rects_dev) CK(cudaMemcpyAsync(out_rects, d_rects, sizeof(Rect) * (size_t)n * ctx->K, cudaMemcpyDeviceToHost, st));
+  if (!counts_dev) CK(cudaMemcpyAsync(out_counts, d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  if (!rects_dev || !counts_dev) return ht_sync(ctx);
+  return HT_OK;
+}
+
+int ht_track_init(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int w, int h, const int32_t *rects,
+                  int calc_angles) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!rects) return ctx->fail(HT_ERR_ARG, "rects is NULL");
+  int rc = check_batch(ctx, n);
+  if (rc != HT_OK) return rc;
+  if (w <= 0 || h <= 0) return ctx->fail(HT_ERR_ARG, "bad frame size");
+  CK(cudaSetDevice(ctx->cfg.device));
+  rc = ensure_tracker_buffers(ctx);
+  if (rc != HT_OK) return rc;
+  const uint8_t *d_rgba = nullptr;
+  rc = device_frames(ctx, rgba, n, w, h, &d_rgba);
+  if (rc != HT_OK) return rc;
+  const int32_t *d_rects = rects;
+  if (!is_device_ptr(rects)) {
+    for (int i = 0; i < n; ++i)
+      if (rects[4 * i + 2] <= 0 || rects[4 * i + 3] <= 0)
+        return ctx->fail(HT_ERR_ARG, "initTracker rectangle %d is empty (canvas getImageData would throw)", i);
+    CK(cudaMemcpyAsync(ctx->d_rects.p, rects, sizeof(int32_t) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    d_rects = ctx->d_rects.as<int32_t>();
+  }
+  return track_init_common(ctx, slots, n, d_rgba, w, h, d_rects, calc_angles, nullptr);
+}
+
+int ht_track_init_from_detect(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int w, int h,
+                              const ht_rect *det_rects, const int32_t *det_counts, int calc_angles, int32_t *out_found) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!det_rects || !det_counts) return ctx->fail(HT_ERR_ARG, "detection outputs are NULL");
+  int rc = check_batch(ctx, n);
+  if (rc != HT_OK) return rc;
+  if (w <= 0 || h <= 0) return ctx->fail(HT_ERR_ARG, "bad frame size");
+  CK(cudaSetDevice(ctx->cfg.device));
+  rc = ensure_tracker_buffers(ctx);
+  if (rc != HT_OK) return rc;
+  const uint8_t *d_rgba = nullptr;
+  rc = device_frames(ctx, rgba, n, w, h, &d_rgba);
+  if (rc != HT_OK) return rc;
+  const Rect *d_det = reinterpret_cast<const Rect *>(det_rects);
+  const int32_t *d_cnt = det_counts;
+  if (!is_device_ptr(det_rects)) {
+    CK(cudaMemcpyAsync(ctx->d_out_rects.p, det_rects, sizeof(Rect) * (size_t)n * ctx->K, cudaMemcpyHostToDevice, ctx->stream));
+    d_det = ctx->d_out_rects.as<Rect>();
+  }
+  if (!is_device_ptr(det_counts)) {
+    CK(cudaMemcpyAsync(ctx->d_out_counts.p, det_counts, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    d_cnt = ctx->d_out_counts.as<int32_t>();
+  }
+  k_pick_face<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_det, d_cnt, ctx->K, n, ctx->d_rects.as<int32_t>());
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  return track_init_common(ctx, slots, n, d_rgba, w, h, ctx->d_rects.as<int32_t>(), calc_angles, out_found);
+}
+
+int ht_track(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int w, int h, int n_calls,
+             ht_trackobj *out_objs, ht_window *out_windows) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!out_objs) return ctx->fail(HT_ERR_ARG, "out_objs is NULL");
+  if (n_calls < 1) return ctx->fail(HT_ERR_ARG, "n_calls must be >= 1");
+  int rc = check_batch(ctx, n);
+  if (rc != HT_OK) return rc;
+  if (w <= 0 || h <= 0) return ctx->fail(HT_ERR_ARG, "bad frame size");
+  CK(cudaSetDevice(ctx->cfg.device));
+  rc = ensure_tracker_buffers(ctx);
+  if (rc != HT_OK) return rc;
+  const uint8_t *d_rgba = nullptr;
+  rc = device_frames(ctx, rgba, n, w, h, &d_rgba);
+  if (rc != HT_OK) return rc;
+  const int32_t *d_slots = nullptr;
+  rc = upload_slots(ctx, slots, n, &d_slots);
+  if (rc != HT_OK) return rc;
+  rc = launch_hist(ctx, d_rgba, n, w, h, ctx->cur_hist.as<uint32_t>());   // camshift.js:268
+  if (rc != HT_OK) return rc;
+  const bool objs_dev = is_device_ptr(out_objs), win_dev = out_windows && is_device_ptr(out_windows);
+  int32_t *d_objs = objs_dev ? reinterpret_cast<int32_t *>(out_objs) : ctx->d_objs.as<int32_t>();
+  int32_t *d_win = out_windows ? (win_dev ? reinterpret_cast<int32_t *>(out_windows) : ctx->d_windows.as<int32_t>()) : nullptr;
+  k_track<<<n, 256, 0, ctx->stream>>>(d_rgba, (size_t)w * h * 4, w, h, d_slots, ctx->model_hist.as<uint32_t>(),
+                                      ctx->cur_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), n_calls, d_objs,
+                                      d_win, ctx->d_flags.as<int32_t>() + 1);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  if (!objs_dev) CK(cudaMemcpyAsync(out_objs, d_objs, sizeof(ht_trackobj) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_windows && !win_dev) CK(cudaMemcpyAsync(out_windows, d_win, sizeof(ht_window) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!objs_dev || (out_windows && !win_dev)) return ht_sync(ctx);
+  return HT_OK;
+}
+
+int ht_backprojection(ht_ctx *ctx, int slot, const uint8_t *rgba, int w, int h, uint8_t *out_rgba) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!out_rgba || slot < 0 || slot >= ctx->cfg.max_frames || w <= 0 || h <= 0) return ctx->fail(HT_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_tracker_buffers(ctx);
+  if (rc != HT_OK) return rc;
+  const uint8_t *d_rgba = nullptr;
+  rc = device_frames(ctx, rgba, 1, w, h, &d_rgba);
+  if (rc != HT_OK) return rc;
+  const size_t bytes = (size_t)w * h * 4;
+  CK(ctx->d_scratch.reserve(bytes + 4096 * sizeof(uint32_t)));
+  uint32_t *hist = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<uint8_t>() + bytes);
+  rc = launch_hist(ctx, d_rgba, 1, w, h, hist);
+  if (rc != HT_OK) return rc;
+  const bool out_dev = is_device_ptr(out_rgba);
+  uint8_t *d_out = out_dev ? out_rgba : ctx->d_scratch.as<uint8_t>();
+  k_backproj<<<(w * h + 255) / 256, 256, 0, ctx->stream>>>(d_rgba, w * h, ctx->model_hist.as<uint32_t>() + (size_t)slot * 4096,
+                                                          hist, d_out);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  if (!out_dev) {
+    CK(cudaMemcpyAsync(out_rgba, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return HT_OK;
+}
+
+int ht_whitebalance(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, double *out) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!out || w <= 0 || h <= 0) return ctx->fail(HT_ERR_ARG, "bad argument");
+  int rc = check_batch(ctx, n);
+  if (rc != HT_OK) return rc;
+  CK(cudaSetDevice(ctx->cfg.device));
+  const uint8_t *d_rgba = nullptr;
+  rc = device_frames(ctx, rgba, n, w, h, &d_rgba);
+  if (rc != HT_OK) return rc;
+  const size_t mf = (size_t)ctx->cfg.max_frames;
+  CK(ctx->d_wb_sums.reserve(mf * 3 * sizeof(unsigned long long)));
+  CK(ctx->d_wb_out.reserve(mf * sizeof(double)));
+  CK(cudaMemsetAsync(ctx->d_wb_sums.p, 0, (size_t)n * 3 * sizeof(unsigned long long), ctx->stream));
+  const int chunks = std::min(64, std::max(1, 1184 / n));
+  k_wb_sums<<<dim3(chunks, n), 256, 0, ctx->stream>>>(d_rgba, (size_t)w * h * 4, w * h, ctx->d_wb_sums.as<unsigned long long>(), chunks);
+  const bool out_dev = is_device_ptr(out);
+  double *d_out = out_dev ? out : ctx->d_wb_out.as<double>();
+  k_wb_final<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_wb_sums.as<unsigned long long>(), n, w * h, d_out);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  if (!out_dev) {
+    CK(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return HT_OK;
+}
+
+// ---- introspection for the parity tests ----
+
+int ht_plan_info(ht_ctx *ctx, int w, int h, int interval, int32_t *n_slots, int32_t *scale_upto, int32_t *slot_w,
+                 int32_t *slot_h, int cap) {
+  if (!ctx) return HT_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  Plan *P = nullptr;
+  int rc = get_plan(ctx, w, h, interval, &P);
+  if (rc != HT_OK) return rc;
+  if (n_slots) *n_slots = P->n_slots;
+  if (scale_upto) *scale_upto = P->scale_upto;
+  for (int i = 0; i < P->n_slots && i < cap; ++i) {
+    if (slot_w) slot_w[i] = P->slot_w[i];
+    if (slot_h) slot_h[i] = P->slot_h[i];
+  }
+  return HT_OK;
+}
+
+int ht_debug_plane(ht_ctx *ctx, int frame, int slot, int q, uint8_t *out, int cap_bytes, int32_t *w, int32_t *h) {
+  if (!ctx) return HT_ERR_ARG;
+  Plan *P = ctx->last_plan;
+  if (!P) return ctx->fail(HT_ERR_STATE, "no ht_detect call yet");
+  if (frame < 0 || frame >= ctx->last_n || slot < 0 || slot >= P->n_slots || q < 0 || q > 3) return ctx->fail(HT_ERR_ARG, "bad frame/slot/q");
+  const int id = P->plane_id[(size_t)slot * 4 + q];
+  if (id < 0) return ctx->fail(HT_ERR_ARG, "plane (%d,%d) does not exist", slot, q);
+  const DevPlane &pl = P->planes[id];
+  if (w) *w = pl.w;
+  if (h) *h = pl.h;
+  if (!out || cap_bytes < pl.w * pl.h) return ctx->fail(HT_ERR_ARG, "output too small");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy2D(out, pl.w, ctx->arena.as<uint8_t>() + (size_t)frame * P->arena_stride + pl.off, pl.pitch, pl.w, pl.h,
+                  cudaMemcpyDeviceToHost));
+  return HT_OK;
+}
+
+int ht_debug_raw(ht_ctx *ctx, int frame, ht_rect *out, int cap, int32_t *count) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!ctx->last_plan || frame < 0 || frame >= ctx->last_n || !count) return ctx->fail(HT_ERR_ARG, "bad frame");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  uint32_t c = 0;
+  CK(cudaMemcpy(&c, ctx->raw_count.as<uint32_t>() + frame, sizeof(c), cudaMemcpyDeviceToHost));
+  *count = (int32_t)c;
+  const int ncopy = std::min<int>(std::min<uint32_t>(c, (uint32_t)ctx->raw_cap), cap);
+  if (out && ncopy > 0)
+    CK(cudaMemcpy(out, ctx->sorted.as<Rect>() + (size_t)frame * ctx->raw_cap, sizeof(Rect) * ncopy, cudaMemcpyDeviceToHost));
+  return HT_OK;
+}
+
+int ht_debug_model_hist(ht_ctx *ctx, int slot, uint32_t *out4096) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!out4096 || slot < 0 || slot >= ctx->cfg.max_frames || !ctx->model_hist.p) return ctx->fail(HT_ERR_ARG, "bad slot");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out4096, ctx->model_hist.as<uint32_t>() + (size_t)slot * 4096, 4096 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return HT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// ht_common.cuh — structures shared by the host planner and the sm_100a kernels.
+//
+// Data layout in HBM:
+//   frames   : caller-owned RGBA8, n contiguous frames of w*h*4 bytes (the "canvas" of the reference).
+//   arena    : per frame, every pyramid plane of src/ccv.js:113-147 as a single-channel u8 plane
+//              (the reference only ever reads channel 0 of its gray canvases, src/ccv.js:171).
+//              Plane pitch is the width rounded up to 16 B so tile staging can use 16 B vector loads;
+//              plane offsets are 256 B aligned.  Planes are indexed densely; plane 0 is the gray image.
+//   plan     : immutable per (w,h,interval): plane table, resample jobs + their column/row tap tables,
+//              per-scale window geometry, tile lists.  Built once on the host (ht_plan.cuh).
+//   cascade  : immutable device copy of the BBF cascade (features as shared-memory byte offsets).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace ht {
+
+// ------------------------------------------------------------------------------------------------
+// Cascade-tile geometry (k_cascade).  A tile is TW x TH quarter-resolution window positions x 4
+// phases.  All three pyramid levels a window reads are staged in shared memory in an "expanded"
+// layout so that EVERY feature point of window (lx,ly,q) sits at  a0 + constant  with the single
+// per-window base  a0 = (4*lx + 2*dx) + (4*ly + 2*dy) * TP :
+//   region A, level 0 (full res)  pixel (X,Y)            at  A + Y*TP + X
+//   region B, level 1 (half res)  pixel (X,Y)            at  B + (2*Y+1)*TP + 2*X
+//   region B, level 2 (quarter res, phase copy q)        at  B + (4*Y + 2*dy)*TP + 4*X + 2*dx
+// A window's level-1 origin is (2lx+dx, 2ly+dy) and its level-2 origin is (lx,ly) in copy q
+// (src/ccv.js:179-180,235-241), which makes the three address forms collapse onto a0.
+// Adjacent lanes (lx, lx+1) are 4 bytes apart in every level -> conflict-free shared-memory reads.
+constexpr int TW = 32;
+constexpr int TH = 16;
+constexpr int TP = 160;                       // tile pitch in bytes (>= 4*TW+22, multiple of 16)
+constexpr int TILE_ROWS = 4 * TH + 22;        // 86 level-0 rows: 4*(TH-1)+2+23+1
+constexpr int REGION = TILE_ROWS * TP;        // bytes per region
+constexpr int L1_ROWS = 2 * TH + 11;          // 43
+constexpr int L1_COLS = 2 * TW + 11;          // 75
+constexpr int L2_ROWS = TH + 5;               // 21
+constexpr int L2_COLS = TW + 5;               // 37
+constexpr int NWIN = TW * TH * 4;             // windows per tile
+constexpr int CASCADE_THREADS = 256;
+
+constexpr int MAX_STAGES = 64;
+constexpr int MAX_GROUPS = 16;
+
+struct DevPlane {
+  uint32_t off;   // byte offset inside the per-frame arena
+  int32_t pitch;  // bytes per row (multiple of 16)
+  int32_t w, h;
+};
+
+// one canvas-shim drawImage(src, sx,sy,sw,sh, 0,0,dw,dh) producing plane `dst` (oracle/ht_oracle.h)
+struct DevJob {
+  int32_t src, dst;
+  int32_t dw, dh;             // painted destination size; the rest of the plane is 0
+  uint32_t col_off, row_off;  // first entry of the tap tables
+  uint32_t magic, shift;      // floor(n / (4 dw dh)) == (uint64(n) * magic) >> shift   for n <= 255.5 * 4 dw dh
+  uint32_t half;              // 2 dw dh (round half up)
+  uint32_t pad_;
+};
+
+// bilinear taps for one destination column (or row): source indices a,b (already clamped and
+// offset by sx/sy) and the numerator f of the fractional weight, 0 <= f < 2*dw (2*dh).
+struct TapEnt {
+  uint16_t a, b, f, pad_;
+};
+
+struct DevPyrTile {  // 8 rows x 128 columns of a destination plane
+  uint16_t job, tx, ty, pad_;
+};
+
+struct DevScale {  // one iteration i of src/ccv.js:154
+  int32_t p0, p1, p2[4];  // plane ids: level 0, level 1, four quarter-res phase copies
+  int32_t qw, qh;         // src/ccv.js:155-156
+  uint32_t win_base;      // index of window (q=0,y=0,x=0) in the reference's (i,q,y,x) visiting order
+  int32_t pad_;
+  double scale_x;         // src/ccv.js:150,244 (repeated multiplication, computed on the host)
+};
+
+struct DevCascTile {
+  uint16_t scale, tx, ty, pad_;
+};
+
+struct DevFeat {   // shared-memory byte offsets relative to a0 (see above)
+  uint16_t p[5];
+  uint16_t n[5];
+  uint16_t size;   // number of point slots used; slots with z==-1 inside `size` repeat slot 0
+  uint16_t pad_;
+};
+
+struct DevStage {
+  int32_t first, count;
+  double threshold;
+};
+
+struct DevCascade {
+  const DevFeat *feat;
+  const double2 *alpha;  // {alpha[2k] (fail), alpha[2k+1] (pass)}  src/ccv.js:194,219
+  const DevStage *stage;
+  int32_t n_stages;
+  int32_t n_groups;
+  int32_t group_first[MAX_GROUPS + 1];  // stage-group boundaries for queue compaction
+};
+
+struct DevPlan {  // pointers into one device allocation
+  const DevPlane *planes;
+  const DevJob *jobs;
+  const TapEnt *taps;
+  const DevPyrTile *pyr_tiles;
+  const DevScale *scales;
+  const DevCascTile *casc_tiles;
+  int32_t n_planes, n_jobs, n_scales, n_casc_tiles;
+};
+
+// result record, identical to ht_rect in include/headtrackr_b200.h
+struct Rect {
+  double x, y, width, height, confidence;
+  int32_t neighbors;
+  int32_t pad_;
+};
+
+// per-slot camshift.Tracker state (src/camshift.js:153-160)
+struct TrackState {
+  int32_t sx, sy, sw, sh;  // _searchWindow
+  int32_t tx, ty, tw, th;  // _trackObj
+  double angle;
+  int32_t calc_angles;
+  int32_t initialised;
+};
+
+}  // namespace ht

@@ -1,0 +1,389 @@
+// ht_detect.cuh — sm_100a kernels for ccv.grayscale + ccv.detect_objects
+// (/root/reference/src/ccv.js:22-32, 109-333).  No tensor cores: byte compares + ordered fp64 adds.
+// The whole library is compiled with -fmad=false so that every a*b+c below is two IEEE roundings,
+// as in JavaScript.
+#pragma once
+#include "ht_common.cuh"
+
+namespace ht {
+
+// ------------------------------------------------------------------------------------------------
+// K1  grayscale — src/ccv.js:28-29:  gray = ToUint8Clamp(r*0.3 + g*0.59 + b*0.11)  (fp64, RN-even)
+// One thread per 4 horizontally adjacent pixels: one 16 B load, one 4 B store into plane 0.
+// HBM-bound: 4 B read + 1 B written per pixel.
+__device__ __forceinline__ uint32_t gray_of(uint32_t px) {
+  const double r = (double)(px & 0xffu), g = (double)((px >> 8) & 0xffu), b = (double)((px >> 16) & 0xffu);
+  const double v = __dadd_rn(__dadd_rn(__dmul_rn(r, 0.3), __dmul_rn(g, 0.59)), __dmul_rn(b, 0.11));
+  int iv = __double2int_rn(v);  // round half to even == Uint8ClampedArray store
+  return (uint32_t)min(iv, 255);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, size_t frame_bytes,
+                                              uint8_t *__restrict__ arena, size_t arena_stride,
+                                              int w, int h, int pitch0, int quads_per_row) {
+  const int frame = blockIdx.y;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t row = t / (uint32_t)quads_per_row;
+  if (row >= (uint32_t)h) return;
+  const int col = (int)(t - row * (uint32_t)quads_per_row) * 4;
+  const uint8_t *src = rgba + (size_t)frame * frame_bytes + ((size_t)row * w + col) * 4;
+  uint32_t px[4] = {0, 0, 0, 0};
+  if (VEC) {  // w % 4 == 0 and 16 B aligned base
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+    px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (col + i < w) px[i] = (uint32_t)src[4 * i] | ((uint32_t)src[4 * i + 1] << 8) | ((uint32_t)src[4 * i + 2] << 16);
+  }
+  uint32_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t gv = (col + i < w) ? gray_of(px[i]) : 0u;  // pad columns are written as 0
+    out |= gv << (8 * i);
+  }
+  *reinterpret_cast<uint32_t *>(arena + (size_t)frame * arena_stride + (size_t)row * pitch0 + col) = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  pyramid level = canvas-shim drawImage (exact integer bilinear, see oracle/ht_oracle.h and
+// src/ccv.js:121,128,135,140,145).  One launch per pyramid "generation" (levels whose sources are
+// complete).  Block = 8 rows x 128 columns of one destination plane; thread = 4 adjacent pixels.
+__global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8_t *__restrict__ arena,
+                                                  size_t arena_stride) {
+  const DevPyrTile tl = plan.pyr_tiles[tile0 + blockIdx.x];
+  const DevJob job = plan.jobs[tl.job];
+  const DevPlane dp = plan.planes[job.dst];
+  const DevPlane sp = plan.planes[job.src];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Y = tl.ty * 8 + warp;
+  const int X = tl.tx * 128 + lane * 4;
+  if (Y >= dp.h || X >= dp.pitch) return;
+  uint8_t *frame = arena + (size_t)blockIdx.y * arena_stride;
+  uint32_t out = 0;
+  if (Y < job.dh && X < job.dw) {
+    const TapEnt ry = plan.taps[job.row_off + Y];
+    const uint8_t *ra = frame + sp.off + (size_t)ry.a * sp.pitch;
+    const uint8_t *rb = frame + sp.off + (size_t)ry.b * sp.pitch;
+    const uint32_t Dx = 2u * (uint32_t)job.dw, Dy = 2u * (uint32_t)job.dh;
+    const uint32_t wy1 = ry.f, wy0 = Dy - ry.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (X + i < job.dw) {
+        const TapEnt cx = plan.taps[job.col_off + X + i];
+        const uint32_t wx1 = cx.f, wx0 = Dx - cx.f;
+        const uint32_t top = wx0 * ra[cx.a] + wx1 * ra[cx.b];   // <= 255 * 2dw
+        const uint32_t bot = wx0 * rb[cx.a] + wx1 * rb[cx.b];
+        const uint32_t num = top * wy0 + bot * wy1 + job.half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
+        const uint32_t q = (uint32_t)(((uint64_t)num * job.magic) >> job.shift);
+        out |= q << (8 * i);
+      }
+    }
+  }
+  *reinterpret_cast<uint32_t *>(frame + dp.off + (size_t)Y * dp.pitch + X) = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  BBF cascade over all windows of one (frame, scale, tile) — src/ccv.js:178-243.
+//
+// Feature test: min over the p-points > max over the n-points.  The reference's early-outs
+// (src/ccv.js:193-218) break exactly when a running min(p) <= running max(n); since min is
+// non-increasing and max non-decreasing this is equivalent to the final comparison.
+// Stage sum: sequential fp64 adds of alpha in feature order (bit-exact with the JS).
+//
+// Windows are evaluated in stage groups; survivors of a group are compacted (ballot + prefix) into
+// a shared-memory queue so that later, longer stages run on dense warps.
+
+__device__ __forceinline__ bool stage_pass(const uint8_t *__restrict__ win, const DevCascade &c, int j,
+                                           bool alive, double &sum_out) {
+  const DevStage st = c.stage[j];
+  double sum = 0.0;
+  for (int k = st.first; k < st.first + st.count; ++k) {
+    const DevFeat f = c.feat[k];   // warp-uniform address -> one broadcast load
+    const double2 al = c.alpha[k];
+    unsigned pmin = win[f.p[0]], nmax = win[f.n[0]];
+    for (int s = 1; s < f.size; ++s) {
+      pmin = min(pmin, (unsigned)win[f.p[s]]);
+      nmax = max(nmax, (unsigned)win[f.n[s]]);
+    }
+    sum += (pmin > nmax) ? al.y : al.x;
+  }
+  sum_out = sum;
+  return alive && !(sum < st.threshold);  // src/ccv.js:222
+}
+
+__global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan, DevCascade casc,
+                                                              const uint8_t *__restrict__ arena, size_t arena_stride,
+                                                              uint32_t *__restrict__ raw_keys,
+                                                              double *__restrict__ raw_conf,
+                                                              uint32_t *__restrict__ raw_count, int raw_cap) {
+  __shared__ __align__(16) uint8_t tile[2 * REGION];
+  __shared__ uint16_t queue[2][NWIN];
+  __shared__ int qcount[2];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int frame = blockIdx.y;
+  const DevCascTile tl = plan.casc_tiles[blockIdx.x];
+  const DevScale sc = plan.scales[tl.scale];
+  const uint8_t *fr = arena + (size_t)frame * arena_stride;
+  const int x0 = tl.tx * TW, y0 = tl.ty * TH;  // quarter-res origin of the tile
+
+  // ---- stage the three levels in shared memory (layout in ht_common.cuh) ----
+  {
+    const DevPlane pl = plan.planes[sc.p0];
+    const uint8_t *src = fr + pl.off;
+    const int X0 = 4 * x0, Y0 = 4 * y0;
+    for (int i = tid; i < TILE_ROWS * (TP / 16); i += CASCADE_THREADS) {
+      const int r = i / (TP / 16), c = (i % (TP / 16)) * 16;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (Y0 + r < pl.h && X0 + c < pl.pitch)
+        v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(Y0 + r) * pl.pitch + X0 + c));
+      *reinterpret_cast<uint4 *>(tile + r * TP + c) = v;
+    }
+  }
+  {
+    const DevPlane pl = plan.planes[sc.p1];
+    const uint8_t *src = fr + pl.off;
+    const int X0 = 2 * x0, Y0 = 2 * y0;
+    constexpr int QC = (L1_COLS + 3) / 4;
+    for (int i = tid; i < L1_ROWS * QC; i += CASCADE_THREADS) {
+      const int r = i / QC, c = (i % QC) * 4;
+      uint32_t v = 0;
+      if (Y0 + r < pl.h && X0 + c < pl.pitch)
+        v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(Y0 + r) * pl.pitch + X0 + c));
+      uint8_t *d = tile + REGION + (2 * r + 1) * TP + 2 * c;
+      d[0] = (uint8_t)v; d[2] = (uint8_t)(v >> 8); d[4] = (uint8_t)(v >> 16); d[6] = (uint8_t)(v >> 24);
+    }
+  }
+  {
+    constexpr int QC = (L2_COLS + 3) / 4;
+    for (int i = tid; i < 4 * L2_ROWS * QC; i += CASCADE_THREADS) {
+      const int q = i / (L2_ROWS * QC), rem = i % (L2_ROWS * QC);
+      const int r = rem / QC, c = (rem % QC) * 4;
+      const DevPlane pl = plan.planes[sc.p2[q]];
+      uint32_t v = 0;
+      if (y0 + r < pl.h && x0 + c < pl.pitch)
+        v = __ldg(reinterpret_cast<const uint32_t *>(fr + pl.off + (size_t)(y0 + r) * pl.pitch + x0 + c));
+      uint8_t *d = tile + REGION + (4 * r + 2 * (q >> 1)) * TP + 4 * c + 2 * (q & 1);
+      d[0] = (uint8_t)v; d[4] = (uint8_t)(v >> 8); d[8] = (uint8_t)(v >> 16); d[12] = (uint8_t)(v >> 24);
+    }
+  }
+  if (tid < 2) qcount[tid] = 0;
+  __syncthreads();
+
+  // ---- stage groups ----
+  int cur = 0;  // queue written by the current group
+  for (int g = 0; g < casc.n_groups; ++g) {
+    const int jb = casc.group_first[g], je = casc.group_first[g + 1];
+    const bool last = (g == casc.n_groups - 1);
+    const int n_in = (g == 0) ? NWIN : qcount[cur ^ 1];
+    const int n_iter = (n_in + CASCADE_THREADS - 1) / CASCADE_THREADS;
+    for (int it = 0; it < n_iter; ++it) {
+      const int i = it * CASCADE_THREADS + tid;
+      int wid = 0;
+      bool alive = i < n_in;
+      if (g > 0 && alive) wid = queue[cur ^ 1][i];
+      if (g == 0) wid = i;
+      const int lx = wid & (TW - 1), ly = (wid / TW) & (TH - 1), q = wid / (TW * TH);
+      const int dx = q & 1, dy = q >> 1;
+      if (g == 0) alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh);
+      const uint8_t *win = tile + (4 * lx + 2 * dx) + (4 * ly + 2 * dy) * TP;
+      double sum = 0.0;
+      for (int j = jb; j < je; ++j) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        alive = stage_pass(win, casc, j, alive, sum);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, alive);
+      if (m) {
+        if (!last) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&qcount[cur], __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (alive) queue[cur][base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
+        } else if (alive) {  // src/ccv.js:227-234: emit (window id in reference order, last stage sum)
+          const uint32_t key = sc.win_base + (uint32_t)((q * sc.qh + (y0 + ly)) * sc.qw + (x0 + lx));
+          const uint32_t pos = atomicAdd(&raw_count[frame], 1u);
+          if (pos < (uint32_t)raw_cap) {
+            raw_keys[(size_t)frame * raw_cap + pos] = key;
+            raw_conf[(size_t)frame * raw_cap + pos] = sum;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+    if (tid == 0) qcount[cur] = 0;  // the queue two groups back is free again
+    __syncthreads();
+    if (!last && qcount[cur ^ 1] == 0) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  sort raw detections into the reference's (i,q,y,x) order and group them —
+// src/ccv.js:34-107 (array_group), 249-332.  One warp per frame.
+//
+// array_group's union-find yields the connected components of the symmetric closure of the
+// predicate, numbered by smallest member index (src/ccv.js:90-105); any components algorithm
+// gives the same partition, so min-label propagation is used.  Sums run in list order per class
+// (fp64, order-sensitive) exactly as src/ccv.js:274-289.
+
+__device__ __forceinline__ bool group_pred(const Rect &r1, const Rect &r2) {  // src/ccv.js:252-261
+  const double distance = floor(r1.width * 0.25 + 0.5);
+  return r2.x <= r1.x + distance && r2.x >= r1.x - distance && r2.y <= r1.y + distance &&
+         r2.y >= r1.y - distance && r2.width <= floor(r1.width * 1.5 + 0.5) &&
+         floor(r2.width * 1.5 + 0.5) >= r1.width;
+}
+
+__global__ void __launch_bounds__(128) k_group(DevPlan plan, int n_frames, const uint32_t *__restrict__ raw_keys,
+                                               const double *__restrict__ raw_conf,
+                                               const uint32_t *__restrict__ raw_count, int raw_cap,
+                                               Rect *__restrict__ sorted, int *__restrict__ labels,
+                                               Rect *__restrict__ seq2, int min_neighbors,
+                                               Rect *__restrict__ out_rects, int32_t *__restrict__ out_counts, int K,
+                                               int32_t *__restrict__ overflow_flag) {
+  const int lane = threadIdx.x & 31;
+  const int frame = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (frame >= n_frames) return;
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t n_true = raw_count[frame];
+  const int n = (int)min(n_true, (uint32_t)raw_cap);
+  if (n_true > (uint32_t)raw_cap && lane == 0) atomicOr(overflow_flag, 1);
+  const uint32_t *keys = raw_keys + (size_t)frame * raw_cap;
+  const double *conf = raw_conf + (size_t)frame * raw_cap;
+  Rect *S = sorted + (size_t)frame * raw_cap;
+  int *L = labels + (size_t)frame * raw_cap;
+  Rect *S2 = seq2 + (size_t)frame * raw_cap;
+  Rect *O = out_rects + (size_t)frame * K;
+
+  // 1. rank sort by window id (ids are unique) and decode to rectangles, src/ccv.js:228-233
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t key = keys[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (keys[j] < key) ? 1 : 0;
+    int s = 0;
+    for (int t = 1; t < plan.n_scales; ++t)
+      if (plan.scales[t].win_base <= key && plan.scales[t].qw > 0 && plan.scales[t].qh > 0) s = t;
+    const DevScale sc = plan.scales[s];
+    uint32_t rem = key - sc.win_base;
+    const uint32_t per_q = (uint32_t)(sc.qw * sc.qh);
+    const uint32_t q = rem / per_q;
+    rem -= q * per_q;
+    const uint32_t y = rem / (uint32_t)sc.qw, x = rem - y * (uint32_t)sc.qw;
+    Rect r;
+    r.x = (double)(x * 4 + (q & 1) * 2) * sc.scale_x;
+    r.y = (double)(y * 4 + (q >> 1) * 2) * sc.scale_x;  // scale_y == scale_x, src/ccv.js:244-245
+    r.width = 24.0 * sc.scale_x;
+    r.height = 24.0 * sc.scale_x;
+    r.confidence = conf[i];
+    r.neighbors = 1;
+    r.pad_ = 0;
+    S[rank] = r;
+  }
+  __syncwarp();
+
+  if (!(min_neighbors > 0)) {  // src/ccv.js:249-250: raw list
+    for (int i = lane; i < n && i < K; i += 32) O[i] = S[i];
+    if (lane == 0) {
+      out_counts[frame] = min(n, K);
+      if (n > K) atomicOr(overflow_flag, 1);
+    }
+    return;
+  }
+
+  // 2. connected components by min-label propagation + pointer jumping
+  for (int i = lane; i < n; i += 32) L[i] = i;
+  __syncwarp();
+  for (;;) {
+    bool changed = false;
+    for (int i = lane; i < n; i += 32) {
+      const Rect ri = S[i];
+      int li = L[i];
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const Rect rj = S[j];
+        if (group_pred(ri, rj) || group_pred(rj, ri)) li = min(li, L[j]);
+      }
+      li = min(li, L[li]);
+      if (li < L[i]) { L[i] = li; changed = true; }
+    }
+    __syncwarp();
+    if (!__any_sync(FULL, changed)) break;
+  }
+  // flatten: every label points at the component's smallest index
+  for (int i = lane; i < n; i += 32) {
+    int li = L[i];
+    while (L[li] != li) li = L[li];
+    L[i] = li;
+  }
+  __syncwarp();
+
+  // 3. per class (in order of smallest member): ordered sums, src/ccv.js:274-303
+  int n2 = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool is_root = (i < n) && (L[i] == i);
+    Rect c;
+    c.x = c.y = c.width = c.height = c.confidence = 0.0;
+    c.neighbors = 0; c.pad_ = 0;
+    if (is_root) {
+      for (int j = i; j < n; ++j) {
+        if (L[j] != i) continue;
+        const Rect r1 = S[j];
+        if (c.neighbors == 0) c.confidence = r1.confidence;
+        ++c.neighbors;
+        c.x += r1.x; c.y += r1.y; c.width += r1.width; c.height += r1.height;
+        c.confidence = fmax(c.confidence, r1.confidence);
+      }
+    }
+    const bool keep = is_root && c.neighbors >= min_neighbors;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) {
+      const double nn = (double)c.neighbors;
+      Rect r;
+      r.x = (c.x * 2 + nn) / (2 * nn);
+      r.y = (c.y * 2 + nn) / (2 * nn);
+      r.width = (c.width * 2 + nn) / (2 * nn);
+      r.height = (c.height * 2 + nn) / (2 * nn);
+      r.neighbors = c.neighbors;
+      r.confidence = c.confidence;
+      r.pad_ = 0;
+      S2[n2 + __popc(m & ((1u << lane) - 1u))] = r;
+    }
+    n2 += __popc(m);
+  }
+  __syncwarp();
+
+  // 4. drop rectangles contained in a better one, src/ccv.js:307-330
+  int n_out = 0;
+  for (int base = 0; base < n2; base += 32) {
+    const int i = base + lane;
+    bool flag = i < n2;
+    Rect r1;
+    if (flag) {
+      r1 = S2[i];
+      for (int j = 0; j < n2; ++j) {
+        const Rect r2 = S2[j];
+        const double distance = floor(r2.width * 0.25 + 0.5);
+        if (i != j && r1.x >= r2.x - distance && r1.y >= r2.y - distance &&
+            r1.x + r1.width <= r2.x + r2.width + distance && r1.y + r1.height <= r2.y + r2.height + distance &&
+            (r2.neighbors > max(3, r1.neighbors) || r1.neighbors < 3)) {
+          flag = false;
+          break;
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(FULL, flag);
+    if (flag) {
+      const int pos = n_out + __popc(m & ((1u << lane) - 1u));
+      if (pos < K) O[pos] = r1;
+    }
+    n_out += __popc(m);
+  }
+  if (lane == 0) {
+    out_counts[frame] = min(n_out, K);
+    if (n_out > K) atomicOr(overflow_flag, 1);
+  }
+}
+
+}  // namespace ht

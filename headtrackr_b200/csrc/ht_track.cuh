@@ -1,0 +1,345 @@
+// ht_track.cuh — sm_100a kernels for camshift.Tracker (/root/reference/src/camshift.js) and
+// getWhitebalance (/root/reference/src/whitebalance.js).
+//
+// The reference materialises a whole-frame back-projection (307,200 doubles in nested arrays,
+// src/camshift.js:332-353) on every track(); here the weight of a pixel is looked up on the fly
+// inside the search window, so a track() costs one streaming histogram pass over the frame plus a
+// few window passes that stay in L2.
+#pragma once
+#include "ht_common.cuh"
+
+namespace ht {
+
+__device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:63-66, 345-348
+  return ((px & 0xf0u) << 4) | ((px >> 8) & 0xf0u) | ((px >> 20) & 0xfu);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1'  4096-bin RGB histogram of whole frames — src/camshift.js:49-72 via :268.
+// grid = (chunks, n_frames).  Shared-memory histogram per CTA, flushed to hist[frame][4096].
+__global__ void __launch_bounds__(256) k_hist(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_px,
+                                              uint32_t *__restrict__ hist, int chunks) {
+  __shared__ uint32_t sh[4096];
+  for (int i = threadIdx.x; i < 4096; i += 256) sh[i] = 0;
+  __syncthreads();
+  const uint32_t *px = reinterpret_cast<const uint32_t *>(rgba + (size_t)blockIdx.y * frame_bytes);
+  const int per = (n_px + chunks - 1) / chunks;
+  const int beg = blockIdx.x * per, end = min(n_px, beg + per);
+  for (int i = beg + threadIdx.x; i < end; i += 256) atomicAdd(&sh[rgb_bin(__ldg(px + i))], 1u);
+  __syncthreads();
+  uint32_t *out = hist + (size_t)blockIdx.y * 4096;
+  if (chunks == 1) {
+    for (int i = threadIdx.x; i < 4096; i += 256) out[i] = sh[i];
+  } else {
+    for (int i = threadIdx.x; i < 4096; i += 256)
+      if (sh[i]) atomicAdd(&out[i], sh[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// initTracker — src/camshift.js:198-211.  One CTA per slot: model histogram of the rectangle
+// (pixels outside the canvas read as 0,0,0,0 -> bin 0, like getImageData), _searchWindow := rect,
+// _trackObj := new TrackObj().  rects == NULL -> take the rectangle from det_pick (device pick).
+__global__ void __launch_bounds__(256) k_track_init(const uint8_t *__restrict__ rgba, size_t frame_bytes, int W, int H,
+                                                    const int32_t *__restrict__ slots,
+                                                    const int32_t *__restrict__ rects, int calc_angles,
+                                                    uint32_t *__restrict__ model_hist, TrackState *__restrict__ state,
+                                                    int32_t *__restrict__ found) {
+  __shared__ uint32_t sh[4096];
+  const int k = blockIdx.x;
+  const int slot = slots ? slots[k] : k;
+  const int rx = rects[4 * k + 0], ry = rects[4 * k + 1], rw = rects[4 * k + 2], rh = rects[4 * k + 3];
+  if (rw <= 0 || rh <= 0) {  // no candidate (device pick) — slot left untouched
+    if (threadIdx.x == 0 && found) found[k] = 0;
+    return;
+  }
+  for (int i = threadIdx.x; i < 4096; i += 256) sh[i] = 0;
+  __syncthreads();
+  const uint32_t *px = reinterpret_cast<const uint32_t *>(rgba + (size_t)k * frame_bytes);
+  for (int yy = threadIdx.x >> 5; yy < rh; yy += 8) {
+    const int cy = ry + yy;
+    for (int xx = threadIdx.x & 31; xx < rw; xx += 32) {
+      const int cx = rx + xx;
+      uint32_t bin = 0;
+      if (cx >= 0 && cx < W && cy >= 0 && cy < H) bin = rgb_bin(__ldg(px + (size_t)cy * W + cx));
+      atomicAdd(&sh[bin], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t *out = model_hist + (size_t)slot * 4096;
+  for (int i = threadIdx.x; i < 4096; i += 256) out[i] = sh[i];
+  if (threadIdx.x == 0) {
+    TrackState s;
+    s.sx = rx; s.sy = ry; s.sw = rw; s.sh = rh;
+    s.tx = s.ty = s.tw = s.th = 0;
+    s.angle = 0.0;
+    s.calc_angles = calc_angles;
+    s.initialised = 1;
+    state[slot] = s;
+    if (found) found[k] = 1;
+  }
+}
+
+// facetrackr's VJ->CS hand-off on the device — src/facetrackr.js:157-165 (first max-confidence
+// candidate), :97 (confidence > -10), :101-106 (Math.floor of x,y,width,height).
+__global__ void k_pick_face(const Rect *__restrict__ det, const int32_t *__restrict__ counts, int K, int n,
+                            int32_t *__restrict__ rects) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int c = counts[k];
+  int32_t r[4] = {0, 0, 0, 0};
+  if (c > 0) {
+    const Rect *d = det + (size_t)k * K;
+    int best = 0;
+    for (int i = 1; i < c; ++i)
+      if (d[i].confidence > d[best].confidence) best = i;
+    if (d[best].confidence > -10.0) {
+      r[0] = (int32_t)floor(d[best].x); r[1] = (int32_t)floor(d[best].y);
+      r[2] = (int32_t)floor(d[best].width); r[3] = (int32_t)floor(d[best].height);
+    }
+  }
+  rects[4 * k + 0] = r[0]; rects[4 * k + 1] = r[1]; rects[4 * k + 2] = r[2]; rects[4 * k + 3] = r[3];
+}
+
+// ------------------------------------------------------------------------------------------------
+// track() — src/camshift.js:213-312.  One CTA per slot runs getWeights, the <=10 mean-shift
+// iterations and the camShift epilogue for n_calls successive track() calls on the same frame.
+
+struct Mom {
+  double m00, m10, m01, m11, m20, m02;
+};
+
+__device__ __forceinline__ int32_t js_to_int32(double v) {  // ES ToInt32 for |v| < 2^31; NaN/Inf -> 0
+  if (!isfinite(v)) return 0;
+  return (int32_t)v;  // cvt.rzi: truncation toward zero
+}
+
+// true when truncating v could flip under the (tiny) summation-order error of a parallel reduction
+__device__ __forceinline__ bool trunc_ambiguous(double v) {
+  return isfinite(v) && fabs(v - rint(v)) < 1e-7;
+}
+
+// Moments in the reference's exact order (x outer, y inner, one accumulator each) —
+// src/camshift.js:90-107.  Used by one thread only when a truncation decision is ambiguous.
+__device__ __noinline__ Mom moments_serial(const uint32_t *__restrict__ px, int W, int x, int y, int w, int h,
+                                           const double *__restrict__ wsm) {
+  Mom m = {0, 0, 0, 0, 0, 0};
+  for (int i = x; i < w; ++i) {
+    const double vx = (double)(i - x);
+    for (int j = y; j < h; ++j) {
+      const double val = wsm[rgb_bin(px[(size_t)j * W + i])];
+      const double vy = (double)(j - y);
+      m.m00 += val;
+      m.m01 += vy * val;
+      m.m10 += vx * val;
+      m.m11 += vx * vy * val;
+      m.m02 += vy * vy * val;
+      m.m20 += vx * vx * val;
+    }
+  }
+  return m;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba, size_t frame_bytes, int W, int H,
+                                               const int32_t *__restrict__ slots,
+                                               const uint32_t *__restrict__ model_hist,
+                                               const uint32_t *__restrict__ cur_hist, TrackState *__restrict__ state,
+                                               int n_calls, int32_t *__restrict__ out_objs /* 6 x i32 per frame */,
+                                               int32_t *__restrict__ out_windows, int32_t *__restrict__ err_flag) {
+  __shared__ double wsm[4096];
+  __shared__ double red[8][6];
+  __shared__ int win[4];   // wadx, wady, wadw, wadh
+  __shared__ int ctrl;     // 0 = next iteration, 1 = call finished
+  const int k = blockIdx.x;
+  const int slot = slots ? slots[k] : k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  TrackState s = state[slot];
+  if (!s.initialised) {
+    if (tid == 0) atomicOr(err_flag, 1);
+    return;
+  }
+  // getWeights — src/camshift.js:314-330
+  {
+    const uint32_t *mh = model_hist + (size_t)slot * 4096, *ch = cur_hist + (size_t)k * 4096;
+    for (int i = tid; i < 4096; i += 256) {
+      const uint32_t c = ch[i];
+      double p = 0.0;
+      if (c != 0) p = fmin((double)mh[i] / (double)c, 1.0);
+      wsm[i] = p;
+    }
+  }
+  const uint32_t *px = reinterpret_cast<const uint32_t *>(rgba + (size_t)k * frame_bytes);
+  __syncthreads();
+
+  for (int call = 0; call < n_calls; ++call) {
+    int prevx = s.sx, prevy = s.sy;                                  // :280-281
+    Mom m = {0, 0, 0, 0, 0, 0};
+    for (int it = 0; it < 10; ++it) {                                // :284
+      if (tid == 0) {
+        win[0] = max(s.sx, 0);                                       // :286-289
+        win[1] = max(s.sy, 0);
+        win[2] = min(win[0] + s.sw, W);
+        win[3] = min(win[1] + s.sh, H);
+        ctrl = 0;
+      }
+      __syncthreads();
+      const int wx = win[0], wy = win[1], ww = win[2] - win[0], wh = win[3] - win[1];
+      double a00 = 0, a10 = 0, a01 = 0, a11 = 0, a20 = 0, a02 = 0;
+      for (int yy = warp; yy < wh; yy += 8) {
+        const uint32_t *row = px + (size_t)(wy + yy) * W + wx;
+        const double vy = (double)yy;
+        for (int xx = lane; xx < ww; xx += 32) {
+          const double val = wsm[rgb_bin(__ldg(row + xx))];
+          const double vx = (double)xx;
+          a00 += val;
+          a01 += vy * val;
+          a10 += vx * val;
+          a11 += vx * vy * val;
+          a02 += vy * vy * val;
+          a20 += vx * vx * val;
+        }
+      }
+      a00 = warp_sum(a00); a10 = warp_sum(a10); a01 = warp_sum(a01);
+      a11 = warp_sum(a11); a20 = warp_sum(a20); a02 = warp_sum(a02);
+      if (lane == 0) {
+        red[warp][0] = a00; red[warp][1] = a10; red[warp][2] = a01;
+        red[warp][3] = a11; red[warp][4] = a20; red[warp][5] = a02;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        m = Mom{0, 0, 0, 0, 0, 0};
+        for (int w8 = 0; w8 < 8; ++w8) {
+          m.m00 += red[w8][0]; m.m10 += red[w8][1]; m.m01 += red[w8][2];
+          m.m11 += red[w8][3]; m.m20 += red[w8][4]; m.m02 += red[w8][5];
+        }
+        bool exact = false;
+        double inv = 1.0 / m.m00;                                    // :109-111
+        double vxf = m.m10 * inv - s.sw / 2.0, vyf = m.m01 * inv - s.sh / 2.0;
+        if (trunc_ambiguous(vxf) || trunc_ambiguous(vyf)) {
+          m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm);
+          exact = true;
+          inv = 1.0 / m.m00;
+          vxf = m.m10 * inv - s.sw / 2.0;
+          vyf = m.m01 * inv - s.sh / 2.0;
+        }
+        s.sx += js_to_int32(vxf);                                    // :295-296
+        s.sy += js_to_int32(vyf);
+        const bool conv = (s.sx == prevx && s.sy == prevy);         // :299
+        if (conv || it == 9) {
+          // final moments (second == true) are those of this window; make the <<2 truncations safe
+          if (!exact) {
+            const double xc = m.m10 * inv, yc = m.m01 * inv;
+            const double a = (m.m20 - m.m10 * xc) * inv, c = (m.m02 - m.m01 * yc) * inv;
+            bool amb;
+            if (s.calc_angles) {
+              const double b = (m.m11 - m.m01 * xc) * inv, d = a + c;
+              const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
+              amb = trunc_ambiguous(sqrt((d - e) * 0.5)) || trunc_ambiguous(sqrt((d + e) * 0.5));
+            } else {
+              amb = trunc_ambiguous(sqrt(a)) || trunc_ambiguous(sqrt(c));
+            }
+            if (amb) m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm);
+          }
+          ctrl = 1;
+        } else {
+          prevx = s.sx;
+          prevy = s.sy;
+        }
+      }
+      __syncthreads();
+      if (ctrl) break;
+    }
+    if (tid == 0) {
+      s.sx = max(0, min(s.sx, W));                                   // :308-309
+      s.sy = max(0, min(s.sy, H));
+      // camShift epilogue — src/camshift.js:230-258
+      const double invM00 = 1.0 / m.m00;
+      const double xc = m.m10 * invM00, yc = m.m01 * invM00;
+      const double mu20 = m.m20 - m.m10 * xc, mu02 = m.m02 - m.m01 * yc, mu11 = m.m11 - m.m01 * xc;
+      const double a = mu20 * invM00, c = mu02 * invM00;
+      if (s.calc_angles) {
+        const double b = mu11 * invM00;
+        const double d = a + c;
+        const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
+        s.tw = (int32_t)((uint32_t)js_to_int32(sqrt((d - e) * 0.5)) << 2);
+        s.th = (int32_t)((uint32_t)js_to_int32(sqrt((d + e) * 0.5)) << 2);
+        double ang = atan2(2 * b, a - c + e);
+        if (ang < 0) ang = ang + 3.141592653589793;
+        s.angle = ang;
+      } else {
+        s.tw = (int32_t)((uint32_t)js_to_int32(sqrt(a)) << 2);
+        s.th = (int32_t)((uint32_t)js_to_int32(sqrt(c)) << 2);
+        s.angle = 3.141592653589793 / 2;
+      }
+      s.tx = (int32_t)floor(fmax(0.0, fmin(s.sx + s.sw / 2.0, (double)W)));   // :253-254
+      s.ty = (int32_t)floor(fmax(0.0, fmin(s.sy + s.sh / 2.0, (double)H)));
+      s.sw = (int32_t)floor(1.1 * s.tw);                             // :257-258
+      s.sh = (int32_t)floor(1.1 * s.th);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    state[slot] = s;
+    int32_t *o = out_objs + 6 * (size_t)k;
+    o[0] = s.tx; o[1] = s.ty; o[2] = s.tw; o[3] = s.th;
+    *reinterpret_cast<double *>(o + 4) = s.angle;
+    if (out_windows) {
+      int32_t *w4 = out_windows + 4 * (size_t)k;
+      w4[0] = s.sx; w4[1] = s.sy; w4[2] = s.sw; w4[3] = s.sh;
+    }
+  }
+}
+
+// getBackProjectionImg — src/camshift.js:177-196 (debug path)
+__global__ void k_backproj(const uint8_t *__restrict__ rgba, int n_px, const uint32_t *__restrict__ mh,
+                           const uint32_t *__restrict__ ch, uint8_t *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const uint32_t bin = rgb_bin(reinterpret_cast<const uint32_t *>(rgba)[i]);
+  const uint32_t c = ch[bin];
+  double p = 0.0;
+  if (c != 0) p = fmin((double)mh[bin] / (double)c, 1.0);
+  const uint32_t v = (uint32_t)floor(255 * p);
+  reinterpret_cast<uint32_t *>(out)[i] = v | (v << 8) | (v << 16) | 0xff000000u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// getWhitebalance — src/whitebalance.js:17-26.  The reference sums bytes in fp64; the sums are
+// exact integers, so integer accumulation in any order is bit-identical.
+__global__ void __launch_bounds__(256) k_wb_sums(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_px,
+                                                 unsigned long long *__restrict__ sums, int chunks) {
+  const uint32_t *px = reinterpret_cast<const uint32_t *>(rgba + (size_t)blockIdx.y * frame_bytes);
+  const int per = (n_px + chunks - 1) / chunks;
+  const int beg = blockIdx.x * per, end = min(n_px, beg + per);
+  unsigned long long r = 0, g = 0, b = 0;
+  for (int i = beg + threadIdx.x; i < end; i += 256) {
+    const uint32_t p = __ldg(px + i);
+    r += p & 0xffu; g += (p >> 8) & 0xffu; b += (p >> 16) & 0xffu;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r += __shfl_down_sync(0xffffffffu, r, o);
+    g += __shfl_down_sync(0xffffffffu, g, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long *s = sums + 3 * (size_t)blockIdx.y;
+    atomicAdd(&s[0], r); atomicAdd(&s[1], g); atomicAdd(&s[2], b);
+  }
+}
+
+__global__ void k_wb_final(const unsigned long long *__restrict__ sums, int n, int n_px, double *__restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double sz = (double)n_px;
+  const double avgr = (double)sums[3 * k] / sz, avgg = (double)sums[3 * k + 1] / sz, avgb = (double)sums[3 * k + 2] / sz;
+  out[k] = (avgr + avgg + avgb) / 3;  // src/whitebalance.js:23-26
+}
+
+}  // namespace ht

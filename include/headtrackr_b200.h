@@ -1,0 +1,149 @@
+/*
+ * headtrackr_b200.h — C ABI of libheadtrackr_b200.so: the B200-native (sm_100a) replacement for
+ * headtrackr's per-frame detect-then-track pixel kernels.
+ *
+ * This is the drop-in boundary.  Every entry point replaces a call that
+ * headtrackr's facetrackr.js makes into ccv.js / camshift.js / whitebalance.js; a Node N-API addon
+ * (js/addon.cc) or any FFI (ctypes: headtrackr_b200/_lib.py) binds these 1:1.  Plain pointers and
+ * sizes only; no C++/torch types.  All citations are into /root/reference/.
+ *
+ *   reference call (file:line)                                       ->  C ABI
+ *   ---------------------------------------------------------------      ---------------------------
+ *   headtrackr.ccv.detect_objects(headtrackr.ccv.grayscale(canvas),
+ *       headtrackr.cascade, 5, 1)          src/facetrackr.js:147-149 ->  ht_detect
+ *       (= src/ccv.js:22-32 grayscale + src/ccv.js:109-333 detect_objects)
+ *   headtrackr.cascade                     src/cascade.js:19         ->  cascade blob given to ht_create
+ *   new headtrackr.camshift.Tracker({calcAngles})
+ *                                          src/facetrackr.js:64      ->  tracker slots inside ht_ctx
+ *   cstracker.initTracker(canvas, Rectangle)
+ *                                          src/facetrackr.js:101-107 ->  ht_track_init / ht_track_init_from_detect
+ *       (= src/camshift.js:198-211)
+ *   cstracker.track(canvas); getTrackObj() src/facetrackr.js:190-191 ->  ht_track
+ *       (= src/camshift.js:213-312, 167-170)
+ *   cstracker.getSearchWindow()            src/camshift.js:162-165   ->  ht_track (out_windows)
+ *   cstracker.getBackProjectionImg()       src/facetrackr.js:195     ->  ht_backprojection
+ *   headtrackr.getWhitebalance(canvas)     src/facetrackr.js:223     ->  ht_whitebalance
+ *       (= src/whitebalance.js:5-29)
+ *
+ * Conventions
+ *   - A "canvas" is a tightly packed RGBA8 frame: w*h*4 bytes, row-major (what getImageData returns).
+ *     Frame batches are n contiguous frames.  `rgba` and all out pointers may be HOST or DEVICE
+ *     pointers (resolved with cudaPointerGetAttributes).  With device outputs the call only enqueues
+ *     work on the context's stream (use ht_sync); with host outputs it returns after the results
+ *     have landed.
+ *   - Return value: 0 = ok; >0 = completed with a warning (HT_WARN_*); <0 = error (HT_ERR_*).
+ *     ht_last_error(ctx) describes the last non-zero return.  Nothing throws across the ABI.
+ *   - One context per host thread / GPU; calls on one context must be serialised by the caller
+ *     (the reference is single-threaded, src/main.js:303).
+ *   - There is NO CPU fallback: every entry point fails with HT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef HEADTRACKR_B200_H
+#define HEADTRACKR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HT_OK 0
+#define HT_WARN_OVERFLOW 1      /* a per-frame raw or result list hit its capacity; lists were truncated */
+#define HT_ERR_ARG (-1)
+#define HT_ERR_CUDA (-2)
+#define HT_ERR_SIZE (-3)        /* frame too small/large for the pyramid (a browser would throw on a 0-sized level) */
+#define HT_ERR_CASCADE (-4)
+#define HT_ERR_STATE (-5)       /* e.g. ht_track on a slot that was never initialised */
+
+typedef struct ht_ctx ht_ctx;
+
+/* One element of the array detect_objects returns (src/ccv.js:228-233 raw, :297-302 grouped):
+ * x,y = top-left, all Numbers (fp64).  For raw lists (min_neighbors <= 0) neighbors == 1. */
+typedef struct {
+  double x, y, width, height, confidence;
+  int32_t neighbors;
+  int32_t pad_;
+} ht_rect;
+
+/* camshift TrackObj (src/camshift.js:362-377): x,y = centre. */
+typedef struct {
+  int32_t x, y, width, height;
+  double angle;
+} ht_trackobj;
+
+/* camshift _searchWindow (src/camshift.js:156) */
+typedef struct {
+  int32_t x, y, width, height;
+} ht_window;
+
+typedef struct {
+  int32_t device;             /* CUDA device ordinal */
+  int32_t max_width;          /* largest frame the context must handle */
+  int32_t max_height;
+  int32_t max_frames;         /* largest batch per call == number of tracker slots */
+  int32_t max_raw_per_frame;  /* capacity of the pre-grouping list per frame (0 -> 1024) */
+  int32_t max_rects_per_frame;/* K: capacity of the result list per frame (0 -> 64) */
+  void *cuda_stream;          /* cudaStream_t to run on; NULL -> the context creates its own */
+} ht_config;
+
+/* Library/ABI version (major<<16 | minor). */
+uint32_t ht_version(void);
+
+/* cascade_blob: "HTC1" blob (tools/pack_cascade.py) of headtrackr.cascade (src/cascade.js:19). */
+int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size_t blob_len);
+void ht_destroy(ht_ctx *ctx);
+const char *ht_last_error(const ht_ctx *ctx);   /* ctx may be NULL: error of the last failed ht_create */
+int ht_sync(ht_ctx *ctx);
+int ht_max_rects(const ht_ctx *ctx);            /* K */
+
+/* ccv.detect_objects(ccv.grayscale(frame), cascade, interval, min_neighbors) for n frames.
+ *   out_rects : [n][K] ht_rect, reference order (src/ccv.js:293-330; raw order (scale,q,y,x) if min_neighbors<=0)
+ *   out_counts: [n]    number of rects written for each frame
+ * The input frames are not modified (the reference works on a copy, src/facetrackr.js:140-145). */
+int ht_detect(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors,
+              ht_rect *out_rects, int32_t *out_counts);
+
+/* camshift.Tracker.initTracker(frame, Rectangle(x,y,w,h)) for n tracker slots (src/camshift.js:198-211).
+ *   slots : [n] slot ids in [0,max_frames) (NULL -> 0..n-1); rgba: n frames; rects: [n][4] = x,y,w,h
+ * Pixels of the rectangle outside the frame count as (0,0,0) like canvas getImageData. */
+int ht_track_init(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int w, int h,
+                  const int32_t *rects, int calc_angles);
+
+/* The VJ->CS hand-off of facetrackr (src/facetrackr.js:157-165 first-max-confidence pick, :97-108
+ * confidence > -10 gate and Math.floor of x,y,w,h) done on the device from ht_detect's outputs:
+ *   det_rects [n][K], det_counts [n] (host or device).  out_found [n] (optional): 1 if the slot was seeded. */
+int ht_track_init_from_detect(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int w, int h,
+                              const ht_rect *det_rects, const int32_t *det_counts, int calc_angles,
+                              int32_t *out_found);
+
+/* n_calls successive camshift.Tracker.track(frame) calls on each slot's frame, state carried
+ * (src/camshift.js:213-312).  out_objs [n] = getTrackObj() after the last call; out_windows [n]
+ * (optional) = getSearchWindow().  Slots that were never initialised yield HT_ERR_STATE. */
+int ht_track(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int w, int h, int n_calls,
+             ht_trackobj *out_objs, ht_window *out_windows);
+
+/* getBackProjectionImg() of the last track() state for one slot: RGBA w*h*4, floor(255*weight) gray
+ * (src/camshift.js:177-196).  Debug path of the reference (src/facetrackr.js:194-196). */
+int ht_backprojection(ht_ctx *ctx, int slot, const uint8_t *rgba, int w, int h, uint8_t *out_rgba);
+
+/* headtrackr.getWhitebalance(frame) for n frames: out[n] doubles (src/whitebalance.js:5-29). */
+int ht_whitebalance(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, double *out);
+
+/* ---- introspection used by the parity tests (not needed by a caller of the reference API) ---- */
+
+/* pyramid geometry for (w,h,interval): n_slots, scale_upto and the per-slot sizes (src/ccv.js:110-127) */
+int ht_plan_info(ht_ctx *ctx, int w, int h, int interval, int32_t *n_slots, int32_t *scale_upto,
+                 int32_t *slot_w, int32_t *slot_h, int cap);
+/* copy one pyramid plane (slot, q) of frame `frame` of the LAST ht_detect call to host memory (w*h bytes) */
+int ht_debug_plane(ht_ctx *ctx, int frame, int slot, int q, uint8_t *out, int cap_bytes, int32_t *w, int32_t *h);
+/* raw (pre-grouping) list of frame `frame` of the LAST ht_detect call, reference order */
+int ht_debug_raw(ht_ctx *ctx, int frame, ht_rect *out, int cap, int32_t *count);
+/* tracker slot state: model histogram (4096 u32, optional) */
+int ht_debug_model_hist(ht_ctx *ctx, int slot, uint32_t *out4096);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t ht_launch_count(const ht_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

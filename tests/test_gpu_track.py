@@ -1,0 +1,134 @@
+"""GPU parity: camshift.Tracker + getWhitebalance through the C ABI vs the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from headtrackr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def face_rect(blob, f):
+    res = oracle.detect(f, blob)
+    best = max(res, key=lambda r: r[4])          # no confidence ties in these frames
+    return [int(math.floor(v)) for v in best[:4]]
+
+
+@pytest.mark.parametrize("W,H,idx,calc", [(320, 240, 0, True), (320, 240, 1, False), (640, 480, 3, False),
+                                          (640, 480, 2, True)])
+def test_track_matches_oracle(ctx, blob, W, H, idx, calc):
+    f = synth.frame(idx, W, H)
+    rect = face_rect(blob, f)
+    ot = oracle.CamshiftTracker(calc_angles=calc)
+    ot.init_tracker(f, *rect)
+    ctx.track_init(f, [rect], calc_angles=calc)
+    assert np.array_equal(ctx.debug_model_hist(0), np.frombuffer(bytes(ot.t.model_hist), np.uint32))
+    for call in range(5):
+        ot.track(f)
+        objs, wins = ctx.track(f)
+        want = ot.track_obj()
+        got = objs[0]
+        assert (got["x"], got["y"], got["width"], got["height"]) == (want["x"], want["y"], want["width"], want["height"]), call
+        assert abs(got["angle"] - want["angle"]) <= 1e-4          # north_star tolerance for the angle
+        assert wins[0] == ot.search_window()
+    assert want["width"] > 0 and want["height"] > 0
+
+
+def test_n_calls_equals_repeated_calls(ctx, blob):
+    f = synth.frame(3, 640, 480)
+    rect = face_rect(blob, f)
+    ot = oracle.CamshiftTracker(calc_angles=False)
+    ot.init_tracker(f, *rect)
+    for _ in range(30):
+        ot.track(f)
+    ctx.track_init(f, [rect], calc_angles=False)
+    objs, wins = ctx.track(f, n_calls=30)
+    want = ot.track_obj()
+    assert (objs[0]["x"], objs[0]["y"], objs[0]["width"], objs[0]["height"]) == (want["x"], want["y"], want["width"], want["height"])
+    assert wins[0] == ot.search_window()
+
+
+def test_lost_face_degenerates_like_reference(ctx, blob):
+    """Model colours absent from the frame -> all weights 0 -> NaN moments -> width == height == 0 (src/main.js:230)."""
+    f = synth.frame(0, 320, 240)
+    rect = face_rect(blob, f)
+    g = synth.frame(0, 320, 240, kind="constant")
+    ot = oracle.CamshiftTracker(calc_angles=False)
+    ot.init_tracker(f, *rect)
+    ot.track(g)
+    ctx.track_init(f, [rect], calc_angles=False)
+    objs, wins = ctx.track(g)
+    want = ot.track_obj()
+    assert (objs[0]["x"], objs[0]["y"], objs[0]["width"], objs[0]["height"]) == (want["x"], want["y"], want["width"], want["height"])
+    assert wins[0] == ot.search_window()
+
+
+def test_rect_outside_canvas(ctx, blob):
+    f = synth.frame(1, 320, 240)
+    rect = [300, 220, 60, 50]
+    ot = oracle.CamshiftTracker(calc_angles=True)
+    ot.init_tracker(f, *rect)
+    ctx.track_init(f, [rect], calc_angles=True)
+    assert np.array_equal(ctx.debug_model_hist(0), np.frombuffer(bytes(ot.t.model_hist), np.uint32))
+    ot.track(f)
+    objs, wins = ctx.track(f)
+    want = ot.track_obj()
+    assert (objs[0]["x"], objs[0]["y"], objs[0]["width"], objs[0]["height"]) == (want["x"], want["y"], want["width"], want["height"])
+
+
+def test_batched_streams_and_slots(ctx, blob):
+    frames = synth.batch(4, 320, 240, start=0)
+    rects = [face_rect(blob, frames[i]) for i in range(4)]
+    slots = [7, 2, 5, 0]
+    ctx.track_init(frames, rects, slots=slots, calc_angles=False)
+    objs, wins = ctx.track(frames, slots=slots, n_calls=3)
+    for i in range(4):
+        ot = oracle.CamshiftTracker(calc_angles=False)
+        ot.init_tracker(frames[i], *rects[i])
+        for _ in range(3):
+            ot.track(frames[i])
+        want = ot.track_obj()
+        assert (objs[i]["x"], objs[i]["y"], objs[i]["width"], objs[i]["height"]) == (want["x"], want["y"], want["width"], want["height"])
+        assert wins[i] == ot.search_window()
+
+
+def test_track_init_from_detect(ctx, blob):
+    frames = synth.batch(3, 640, 480, start=0)
+    rects, counts = ctx.detect_raw(frames, 5, 1)
+    found = ctx.track_init_from_detect(frames, rects, counts, calc_angles=False)
+    objs, wins = ctx.track(frames, n_calls=2)
+    for i in range(3):
+        res = oracle.detect(frames[i], blob)
+        cand = None
+        for r in res:                                  # src/facetrackr.js:157-165
+            if cand is None or r[4] > cand[4]:
+                cand = r
+        assert found[i] == int(cand is not None and cand[4] > -10)
+        ot = oracle.CamshiftTracker(calc_angles=False)
+        ot.init_tracker(frames[i], *[int(math.floor(v)) for v in cand[:4]])
+        ot.track(frames[i]); ot.track(frames[i])
+        want = ot.track_obj()
+        assert (objs[i]["x"], objs[i]["y"], objs[i]["width"], objs[i]["height"]) == (want["x"], want["y"], want["width"], want["height"])
+
+
+def test_uninitialised_slot_is_an_error(ctx):
+    from headtrackr_b200._lib import HtError, HT_ERR_STATE
+    f = synth.frame(0, 320, 240)
+    with pytest.raises(HtError) as e:
+        ctx.track(f, slots=[15])
+    assert e.value.code == HT_ERR_STATE
+
+
+def test_backprojection_and_whitebalance(ctx, blob):
+    f = synth.frame(2, 320, 240)
+    rect = face_rect(blob, f)
+    ot = oracle.CamshiftTracker(calc_angles=False)
+    ot.init_tracker(f, *rect)
+    ctx.track_init(f, [rect], calc_angles=False)
+    assert np.array_equal(ctx.backprojection(f, 0), ot.backprojection_img(f))
+    frames = synth.batch(3, 320, 240, start=5)
+    wb = ctx.whitebalance(frames)
+    for i in range(3):
+        assert wb[i] == oracle.whitebalance(frames[i])
