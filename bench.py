@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the detect+track hot path (contract: see the task prompt / DESIGN.md §6).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle restatement)
+
+A "step" is one pass of the hot path over one batch of synthetic 640x480 RGBA frames:
+ccv.grayscale + ccv.detect_objects(interval=5, min_neighbors=1), facetrackr's VJ->CS hand-off, then
+30 camshift track() calls on the frame (BASELINE.json configs[2]; configs[1] = --workload detect).
+`value` is whole-job frames/s with the batch resident in HBM; `e2e` is the same work through
+Context.detect_track() on pinned HOST frames (H2D + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from headtrackr_b200 import synth  # noqa: E402
+
+N_UNIQUE = 64          # distinct synthetic frames generated on the CPU; the batch tiles them with x-rolls
+HBM_PEAK_FALLBACK = 6650.0
+
+
+def make_base_frames(W, H, start, n=N_UNIQUE):
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        frames = list(ex.map(lambda i: synth.frame(start + i, W, H), range(n)))
+    return np.stack(frames)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_PEAK_FALLBACK, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle (C restatement of src/ccv.js + src/camshift.js)
+
+def cpu_step(frames, blob, track_calls, threads):
+    import oracle
+
+    def one(i):
+        f = frames[i]
+        res = oracle.detect(f, blob, 5, 1)
+        if track_calls > 0 and res:
+            cand = res[0]
+            for r in res[1:]:
+                if r[4] > cand[4]:
+                    cand = r
+            if cand[4] > -10:
+                t = oracle.CamshiftTracker(calc_angles=False)
+                t.init_tracker(f, *[int(np.floor(v)) for v in cand[:4]])
+                for _ in range(track_calls):
+                    t.track(f)
+        return len(res)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:   # ctypes releases the GIL inside the C oracle
+        list(ex.map(one, range(len(frames))))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(frames, blob, track_calls, steps=1, warmup=0):
+    import oracle
+    oracle.lib()
+    threads = os.cpu_count() or 1
+    for _ in range(warmup):
+        cpu_step(frames, blob, track_calls, threads)
+    times = [cpu_step(frames, blob, track_calls, threads) for _ in range(steps)]
+    total = sum(times)
+    return {"value": len(frames) * steps / total, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{len(frames)} of the bench's synthetic frames per step, C restatement of the reference JS "
+                      f"(oracle/ht_oracle.c, -O2, one thread per host core; not V8)"}, total / steps
+
+
+def run_reference(args, W, H, track_calls, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    blob = synth.load_cascade_blob()
+    n_sample = args.cpu_sample
+    frames = make_base_frames(W, H, 0, n_sample)
+    cb, sec_per_step = cpu_baseline(frames, blob, track_calls, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "frames/sec @640x480 (detect+CAMShift)", "value": cb["value"],
+            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8+f64", "data": "synthetic",
+            "config": {"workload": workload, "frame": f"{W}x{H}", "frames_per_step": n_sample, "interval": 5,
+                       "min_neighbors": 1, "track_calls_per_frame": track_calls},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args, W, H, track_calls, workload):
+    import torch
+    import torch.distributed as dist
+    from headtrackr_b200 import Context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    # per-rank data: independent frames per GPU (weak scaling, frames are the shard unit)
+    base = make_base_frames(W, H, rank * 100000, N_UNIQUE)
+    host = torch.empty((B, H, W, 4), dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    for j in range(B):
+        hv[j] = np.roll(base[j % N_UNIQUE], (j // N_UNIQUE) * 16, axis=1)
+    dev = host.cuda(non_blocking=False)
+    stream = torch.cuda.Stream()          # a real (non-NULL) stream: the context launches on it, the events time it
+    torch.cuda.set_stream(stream)
+    ctx = Context(max_width=W, max_height=H, max_frames=B, device=local, stream=stream.cuda_stream)
+    K = ctx.K
+    d_rects = torch.zeros((B, K, 6), dtype=torch.float64, device="cuda")      # ht_rect = 48 B
+    d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    d_found = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    d_objs = torch.zeros((B, 6), dtype=torch.int32, device="cuda")            # ht_trackobj = 24 B
+    d_wins = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+    gathered = torch.zeros((world, B, 6), dtype=torch.int32, device="cuda") if world > 1 else None
+
+    def step():
+        if workload == "detect":
+            ctx.detect_raw(dev, 5, 1, out_rects=d_rects, out_counts=d_counts)
+        else:
+            ctx.detect_track(dev, 5, 1, calc_angles=False, n_calls=track_calls,
+                             outputs=(d_rects, d_counts, d_found, d_objs, d_wins))
+        if world > 1:   # the only collective: fixed-size result records gathered over NCCL/NVLink
+            dist.all_gather_into_tensor(gathered, d_objs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count
+    ctx.profile(True)
+    ctx.profile_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read(reset=True)
+    ctx.profile(False)
+    track_stats = ctx.debug_track_stats(reset=True)
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- e2e: same work through the public API on pinned HOST frames ----
+    h_rects = torch.empty((B, K, 6), dtype=torch.float64, pin_memory=True)
+    h_counts = torch.empty((B,), dtype=torch.int32, pin_memory=True)
+    h_found = torch.empty((B,), dtype=torch.int32, pin_memory=True)
+    h_objs = torch.empty((B, 6), dtype=torch.int32, pin_memory=True)
+    h_wins = torch.empty((B, 4), dtype=torch.int32, pin_memory=True)
+    L = ctx._L
+
+    def e2e_step():
+        if workload == "detect":
+            rc = L.ht_detect(ctx._h, host.data_ptr(), B, W, H, 5, 1, h_rects.data_ptr(), h_counts.data_ptr())
+        else:
+            rc = L.ht_detect_track(ctx._h, host.data_ptr(), B, W, H, 5, 1, 0, track_calls, h_rects.data_ptr(),
+                                   h_counts.data_ptr(), h_found.data_ptr(), h_objs.data_ptr(), h_wins.data_ptr())
+        ctx._check(rc)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()          # returns after the D2H of the results has completed
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * e2e_steps / e2e_s
+    h2d = B * H * W * 4
+    d2h = h_rects.numel() * 8 + h_counts.numel() * 4 + (0 if workload == "detect" else (h_found.numel() + h_objs.numel() + h_wins.numel()) * 4)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        casc_ms, casc_n = prof["cascade"]
+        alg_bytes = B * W * H * 4                      # one read of the RGBA frame, x frames per launch
+        achieved = (alg_bytes / 1e9) / (casc_ms / casc_n / 1e3) if casc_n else None
+        kernel_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
+        line = {"metric": "frames/sec @640x480 (detect+CAMShift)", "value": value, "unit": "frames/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64",
+                "data": "synthetic",
+                "config": {"workload": workload, "frame": f"{W}x{H}", "frames_per_gpu_per_step": B, "interval": 5,
+                           "min_neighbors": 1, "track_calls_per_frame": track_calls, "sharding": f"frames dp{world}",
+                           "l2": f"inputs larger than L2 ({B * W * H * 4 / 1e6:.0f} MB of frames per GPU per step)",
+                           "unique_frames": N_UNIQUE},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "k_cascade", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": (achieved / peak) if achieved else None, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                             "kernel_ms_per_launch": casc_ms / casc_n if casc_n else None,
+                             "note": "BBF cascade is issue/shared-memory bound, not HBM bound (DESIGN.md §5)"},
+                "kernel_ms_per_step": kernel_ms,
+                "track_stats": track_stats,
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            blob = synth.load_cascade_blob()
+            sample = base if args.cpu_sample <= N_UNIQUE else make_base_frames(W, H, 0, args.cpu_sample)
+            cb, _ = cpu_baseline(sample[: args.cpu_sample], blob, track_calls)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="detect_track30", choices=["detect_track30", "detect"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--cpu-sample", type=int, default=max(64, 2 * (os.cpu_count() or 1)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    track_calls = 30 if args.workload == "detect_track30" else 0
+    if args.impl == "reference":
+        run_reference(args, args.width, args.height, track_calls, args.workload)
+    else:
+        run_ours(args, args.width, args.height, track_calls, args.workload)
+
+
+if __name__ == "__main__":
+    main()

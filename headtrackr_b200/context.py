@@ -79,6 +79,17 @@ class Context:
     def launch_count(self):
         return int(self._L.ht_launch_count(self._h))
 
+    def profile(self, enable=True):
+        self._check(self._L.ht_profile(self._h, int(bool(enable))))
+
+    def profile_read(self, reset=True):
+        """-> {class: (milliseconds, launches)} accumulated while profiling was enabled."""
+        n = len(_lib.PROF_CLASSES)
+        ms = (C.c_double * n)()
+        ln = (C.c_uint64 * n)()
+        self._check(self._L.ht_profile_read(self._h, C.addressof(ms), C.addressof(ln), int(bool(reset))))
+        return {name: (ms[i], int(ln[i])) for i, name in enumerate(_lib.PROF_CLASSES)}
+
     # ---- ccv.detect_objects ----
     def detect_raw(self, frames, interval=5, min_neighbors=1, out_rects=None, out_counts=None):
         """Low-level: returns (rects, counts).  With torch device outputs the call is asynchronous."""
@@ -136,6 +147,33 @@ class Context:
         return ([dict(x=o.x, y=o.y, width=o.width, height=o.height, angle=o.angle) for o in objs],
                 [(w.x, w.y, w.width, w.height) for w in wins])
 
+    def detect_track(self, frames, interval=5, min_neighbors=1, calc_angles=False, n_calls=1, outputs=None):
+        """Batched facetrackr VJ->CS flow (ht_detect_track).
+
+        outputs=None: host results -> (rect lists, found, track objects, windows).
+        outputs=(rects, counts, found, objs, windows) torch CUDA tensors: asynchronous, nothing returned to the host.
+        """
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        if outputs is not None:
+            r, cnt, fnd, ob, wn = outputs
+            self._check(self._L.ht_detect_track(self._h, ptr, n, W, H, interval, min_neighbors, int(bool(calc_angles)),
+                                                n_calls, r.data_ptr(), cnt.data_ptr(),
+                                                fnd.data_ptr() if fnd is not None else None, ob.data_ptr(),
+                                                wn.data_ptr() if wn is not None else None))
+            return None
+        rects = (Rect * (n * self.K))()
+        counts = (C.c_int32 * n)()
+        found = (C.c_int32 * n)()
+        objs = (TrackObj * n)()
+        wins = (Window * n)()
+        self._check(self._L.ht_detect_track(self._h, ptr, n, W, H, interval, min_neighbors, int(bool(calc_angles)),
+                                            n_calls, C.addressof(rects), C.addressof(counts), C.addressof(found),
+                                            C.addressof(objs), C.addressof(wins)))
+        dets = [[rect_to_dict(rects[f * self.K + i]) for i in range(counts[f])] for f in range(n)]
+        return (dets, list(found),
+                [dict(x=o.x, y=o.y, width=o.width, height=o.height, angle=o.angle) for o in objs],
+                [(w.x, w.y, w.width, w.height) for w in wins])
+
     def backprojection(self, frame, slot=0):
         ptr, n, H, W, keep = _frames_ptr(frame)
         out = np.zeros((H, W, 4), np.uint8)
@@ -168,6 +206,11 @@ class Context:
         cnt = C.c_int32()
         self._check(self._L.ht_debug_raw(self._h, frame, C.addressof(out), cap, C.addressof(cnt)))
         return [(r.x, r.y, r.width, r.height, r.confidence, r.neighbors) for r in out[: min(cnt.value, cap)]], cnt.value
+
+    def debug_track_stats(self, reset=True):
+        out = (C.c_uint64 * 4)()
+        self._check(self._L.ht_debug_track_stats(self._h, C.addressof(out), int(bool(reset))))
+        return dict(passes=int(out[0]), serial_passes=int(out[1]), pixels=int(out[2]), calls=int(out[3]))
 
     def debug_model_hist(self, slot):
         out = np.zeros(4096, np.uint32)

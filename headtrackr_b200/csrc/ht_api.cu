@@ -318,6 +318,36 @@ struct ht_ctx {
   DevBuf arena, d_frames, raw_keys, raw_conf, raw_count, sorted, labels, seq2, d_out_rects, d_out_counts, d_flags;
   DevBuf model_hist, cur_hist, track_state, d_slots, d_rects, d_found, d_objs, d_windows, d_wb_sums, d_wb_out, d_scratch;
 
+  // optional per-kernel-class device timing (CUDA events on the launching stream) for bench.py's roofline
+  bool prof_on = false;
+  struct ProfSpan { int cls; cudaEvent_t a, b; };
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_free;
+  double prof_ms[HT_PROF_N] = {0};
+  uint64_t prof_launches[HT_PROF_N] = {0};
+
+  cudaEvent_t prof_event() {
+    cudaEvent_t e = nullptr;
+    if (!prof_free.empty()) { e = prof_free.back(); prof_free.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+  void prof_begin(int cls) {
+    if (!prof_on) return;
+    ProfSpan s{cls, prof_event(), prof_event()};
+    cudaEventRecord(s.a, stream);
+    prof_spans.push_back(s);
+  }
+  void prof_end() {
+    if (!prof_on) return;
+    cudaEventRecord(prof_spans.back().b, stream);
+  }
+
+  cudaStream_t copy_stream = nullptr;       // H2D staging stream of ht_detect_track
+  cudaEvent_t compute_done = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+  int h2d_chunk = 64;                       // frames per pipelined upload chunk
+
   int fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
@@ -407,7 +437,9 @@ int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_
   int chunks = 1;
   if (n < 592) chunks = std::min(64, std::max(1, 1184 / n));  // keep ~8 CTAs per SM busy for small batches
   if (chunks > 1) CK(cudaMemsetAsync(hist, 0, (size_t)n * 4096 * sizeof(uint32_t), ctx->stream));
+  ctx->prof_begin(HT_PROF_HIST);
   k_hist<<<dim3(chunks, n), 256, 0, ctx->stream>>>(d_rgba, (size_t)n_px * 4, n_px, hist, chunks);
+  ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
   return HT_OK;
@@ -420,14 +452,100 @@ int track_init_common(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *d
   if (rc != HT_OK) return rc;
   const bool found_dev = out_found && is_device_ptr(out_found);
   int32_t *d_found = out_found ? (found_dev ? out_found : ctx->d_found.as<int32_t>()) : nullptr;
+  ctx->prof_begin(HT_PROF_TRACK_INIT);
   k_track_init<<<n, 256, 0, ctx->stream>>>(d_rgba, (size_t)w * h * 4, w, h, d_slots, d_rects, calc_angles ? 1 : 0,
                                            ctx->model_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), d_found);
+  ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
   if (out_found && !found_dev) {
     CK(cudaMemcpyAsync(out_found, d_found, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
+  return HT_OK;
+}
+
+// gray -> pyramid -> cascade -> sort+group for frames [f0, f0+n) of a device-resident batch.
+// Every per-frame buffer is indexed by absolute frame number so that chunks can be pipelined.
+int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n, int min_neighbors, Rect *d_rects_batch,
+               int32_t *d_counts_batch) {
+  cudaStream_t st = ctx->stream;
+  const int w = P->w, h = P->h;
+  const uint8_t *d_rgba = d_rgba_batch + (size_t)f0 * w * h * 4;
+  uint8_t *arena = ctx->arena.as<uint8_t>() + (size_t)f0 * P->arena_stride;
+  uint32_t *raw_keys = ctx->raw_keys.as<uint32_t>() + (size_t)f0 * ctx->raw_cap;
+  double *raw_conf = ctx->raw_conf.as<double>() + (size_t)f0 * ctx->raw_cap;
+  uint32_t *raw_count = ctx->raw_count.as<uint32_t>() + f0;
+  CK(cudaMemsetAsync(raw_count, 0, sizeof(uint32_t) * n, st));
+  // K1 grayscale -> plane 0
+  {
+    const int qpr = (w + 3) / 4;
+    const unsigned blocks = (unsigned)(((size_t)qpr * h + 255) / 256);
+    const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgba) & 15u) == 0);
+    ctx->prof_begin(HT_PROF_GRAY);
+    if (vec) k_gray<true><<<dim3(blocks, n), 256, 0, st>>>(d_rgba, (size_t)w * h * 4, arena, P->arena_stride, w, h, P->planes[0].pitch, qpr);
+    else k_gray<false><<<dim3(blocks, n), 256, 0, st>>>(d_rgba, (size_t)w * h * 4, arena, P->arena_stride, w, h, P->planes[0].pitch, qpr);
+    ctx->prof_end();
+    ++ctx->launches;
+  }
+  // K2 pyramid generations
+  for (size_t g = 1; g + 1 < P->gen_tile_begin.size(); ++g) {
+    const int t0 = P->gen_tile_begin[g], t1 = P->gen_tile_begin[g + 1];
+    if (t1 > t0) {
+      ctx->prof_begin(HT_PROF_PYRAMID);
+      k_resample<<<dim3(t1 - t0, n), 256, 0, st>>>(P->dplan, t0, arena, P->arena_stride);
+      ctx->prof_end();
+      ++ctx->launches;
+    }
+  }
+  // K3 cascade
+  if (!P->casc_tiles.empty()) {
+    ctx->prof_begin(HT_PROF_CASCADE);
+    k_cascade<<<dim3((unsigned)P->casc_tiles.size(), n), CASCADE_THREADS, 0, st>>>(
+        P->dplan, ctx->dcasc, arena, P->arena_stride, raw_keys, raw_conf, raw_count, ctx->raw_cap);
+    ctx->prof_end();
+    ++ctx->launches;
+  }
+  // K4 sort + group
+  ctx->prof_begin(HT_PROF_GROUP);
+  k_group<<<(n + 3) / 4, 128, 0, st>>>(P->dplan, n, raw_keys, raw_conf, raw_count, ctx->raw_cap,
+                                       ctx->sorted.as<Rect>() + (size_t)f0 * ctx->raw_cap,
+                                       ctx->labels.as<int>() + (size_t)f0 * ctx->raw_cap,
+                                       ctx->seq2.as<Rect>() + (size_t)f0 * ctx->raw_cap, min_neighbors,
+                                       d_rects_batch + (size_t)f0 * ctx->K, d_counts_batch + f0, ctx->K,
+                                       ctx->d_flags.as<int32_t>());
+  ctx->prof_end();
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  return HT_OK;
+}
+
+// pick (optional) + initTracker + n_calls x track() for frames [f0, f0+n); slot of frame k is k (slots == NULL)
+int run_track_from_detect(ht_ctx *ctx, const uint8_t *d_rgba_batch, int w, int h, int f0, int n, const Rect *d_det,
+                          const int32_t *d_cnt, int calc_angles, int n_calls, int32_t *d_found, int32_t *d_objs,
+                          int32_t *d_win) {
+  cudaStream_t st = ctx->stream;
+  const uint8_t *d_rgba = d_rgba_batch + (size_t)f0 * w * h * 4;
+  int32_t *d_rects4 = ctx->d_rects.as<int32_t>() + 4 * (size_t)f0;
+  ctx->prof_begin(HT_PROF_TRACK_INIT);
+  k_pick_face<<<(n + 127) / 128, 128, 0, st>>>(d_det + (size_t)f0 * ctx->K, d_cnt + f0, ctx->K, n, d_rects4);
+  k_track_init<<<n, 256, 0, st>>>(d_rgba, (size_t)w * h * 4, w, h, nullptr, d_rects4, calc_angles ? 1 : 0,
+                                  ctx->model_hist.as<uint32_t>() + (size_t)f0 * 4096,
+                                  ctx->track_state.as<TrackState>() + f0, d_found ? d_found + f0 : nullptr);
+  ctx->prof_end();
+  ctx->launches += 2;
+  if (n_calls > 0) {
+    int rc = launch_hist(ctx, d_rgba, n, w, h, ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096);
+    if (rc != HT_OK) return rc;
+    ctx->prof_begin(HT_PROF_TRACK);
+    k_track<<<n, 256, 0, st>>>(d_rgba, (size_t)w * h * 4, w, h, nullptr, ctx->model_hist.as<uint32_t>() + (size_t)f0 * 4096,
+                               ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096, ctx->track_state.as<TrackState>() + f0,
+                               n_calls, d_objs + 6 * (size_t)f0, d_win ? d_win + 4 * (size_t)f0 : nullptr,
+                               ctx->d_flags.as<int32_t>() + 2, ctx->d_flags.as<unsigned long long>() + 8);
+    ctx->prof_end();
+    ++ctx->launches;
+  }
+  CK(cudaGetLastError());
   return HT_OK;
 }
 
@@ -474,6 +592,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "ht_create: stream"; return HT_ERR_CUDA; }
     c->own_stream = true;
   }
+  if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
   // cascade tables
   const HostCascade &hc = c->hc;
   const size_t o_feat = 0, o_alpha = align_up(o_feat + hc.feats.size() * sizeof(DevFeat), (size_t)256);
@@ -528,6 +647,11 @@ void ht_destroy(ht_ctx *ctx) {
                     &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
                     &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
   for (DevBuf *b : bufs) b->release();
+  for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (cudaEvent_t e : ctx->prof_free) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
+  if (ctx->compute_done) cudaEventDestroy(ctx->compute_done);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -560,44 +684,12 @@ int ht_detect(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interva
   rc = device_frames(ctx, rgba, n, w, h, &d_rgba);
   if (rc != HT_OK) return rc;
   CK(ctx->arena.reserve(P->arena_stride * (size_t)n));
-  uint8_t *arena = ctx->arena.as<uint8_t>();
   cudaStream_t st = ctx->stream;
   const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
   Rect *d_rects = rects_dev ? reinterpret_cast<Rect *>(out_rects) : ctx->d_out_rects.as<Rect>();
   int32_t *d_counts = counts_dev ? out_counts : ctx->d_out_counts.as<int32_t>();
-
-  CK(cudaMemsetAsync(ctx->raw_count.p, 0, sizeof(uint32_t) * n, st));
-  // K1 grayscale -> plane 0
-  {
-    const int qpr = (w + 3) / 4;
-    const unsigned blocks = (unsigned)(((size_t)qpr * h + 255) / 256);
-    const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgba) & 15u) == 0);
-    if (vec) k_gray<true><<<dim3(blocks, n), 256, 0, st>>>(d_rgba, (size_t)w * h * 4, arena, P->arena_stride, w, h, P->planes[0].pitch, qpr);
-    else k_gray<false><<<dim3(blocks, n), 256, 0, st>>>(d_rgba, (size_t)w * h * 4, arena, P->arena_stride, w, h, P->planes[0].pitch, qpr);
-    ++ctx->launches;
-  }
-  // K2 pyramid generations
-  for (size_t g = 1; g + 1 < P->gen_tile_begin.size(); ++g) {
-    const int t0 = P->gen_tile_begin[g], t1 = P->gen_tile_begin[g + 1];
-    if (t1 > t0) {
-      k_resample<<<dim3(t1 - t0, n), 256, 0, st>>>(P->dplan, t0, arena, P->arena_stride);
-      ++ctx->launches;
-    }
-  }
-  // K3 cascade
-  if (!P->casc_tiles.empty()) {
-    k_cascade<<<dim3((unsigned)P->casc_tiles.size(), n), CASCADE_THREADS, 0, st>>>(
-        P->dplan, ctx->dcasc, arena, P->arena_stride, ctx->raw_keys.as<uint32_t>(), ctx->raw_conf.as<double>(),
-        ctx->raw_count.as<uint32_t>(), ctx->raw_cap);
-    ++ctx->launches;
-  }
-  // K4 sort + group
-  k_group<<<(n + 3) / 4, 128, 0, st>>>(P->dplan, n, ctx->raw_keys.as<uint32_t>(), ctx->raw_conf.as<double>(),
-                                       ctx->raw_count.as<uint32_t>(), ctx->raw_cap, ctx->sorted.as<Rect>(),
-                                       ctx->labels.as<int>(), ctx->seq2.as<Rect>(), min_neighbors, d_rects, d_counts, ctx->K,
-                                       ctx->d_flags.as<int32_t>());
-  ++ctx->launches;
-  CK(cudaGetLastError());
+  rc = run_detect(ctx, P, d_rgba, 0, n, min_neighbors, d_rects, d_counts);
+  if (rc != HT_OK) return rc;
   ctx->last_plan = P;
   ctx->last_n = n;
   if (!rects_dev) CK(cudaMemcpyAsync(out_rects, d_rects, sizeof(Rect) * (size_t)n * ctx->K, cudaMemcpyDeviceToHost, st));
@@ -653,7 +745,9 @@ int ht_track_init_from_detect(ht_ctx *ctx, const int32_t *slots, int n, const ui
     CK(cudaMemcpyAsync(ctx->d_out_counts.p, det_counts, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     d_cnt = ctx->d_out_counts.as<int32_t>();
   }
+  ctx->prof_begin(HT_PROF_TRACK_INIT);
   k_pick_face<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_det, d_cnt, ctx->K, n, ctx->d_rects.as<int32_t>());
+  ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
   return track_init_common(ctx, slots, n, d_rgba, w, h, ctx->d_rects.as<int32_t>(), calc_angles, out_found);
@@ -681,14 +775,93 @@ int ht_track(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int 
   const bool objs_dev = is_device_ptr(out_objs), win_dev = out_windows && is_device_ptr(out_windows);
   int32_t *d_objs = objs_dev ? reinterpret_cast<int32_t *>(out_objs) : ctx->d_objs.as<int32_t>();
   int32_t *d_win = out_windows ? (win_dev ? reinterpret_cast<int32_t *>(out_windows) : ctx->d_windows.as<int32_t>()) : nullptr;
+  ctx->prof_begin(HT_PROF_TRACK);
   k_track<<<n, 256, 0, ctx->stream>>>(d_rgba, (size_t)w * h * 4, w, h, d_slots, ctx->model_hist.as<uint32_t>(),
                                       ctx->cur_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), n_calls, d_objs,
-                                      d_win, ctx->d_flags.as<int32_t>() + 1);
+                                      d_win, ctx->d_flags.as<int32_t>() + 1, ctx->d_flags.as<unsigned long long>() + 8);
+  ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
   if (!objs_dev) CK(cudaMemcpyAsync(out_objs, d_objs, sizeof(ht_trackobj) * n, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_windows && !win_dev) CK(cudaMemcpyAsync(out_windows, d_win, sizeof(ht_window) * n, cudaMemcpyDeviceToHost, ctx->stream));
   if (!objs_dev || (out_windows && !win_dev)) return ht_sync(ctx);
+  return HT_OK;
+}
+
+int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors,
+                    int calc_angles, int n_calls, ht_rect *out_rects, int32_t *out_counts, int32_t *out_found,
+                    ht_trackobj *out_objs, ht_window *out_windows) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!out_rects || !out_counts || !out_objs) return ctx->fail(HT_ERR_ARG, "output pointers are NULL");
+  if (n_calls < 0) return ctx->fail(HT_ERR_ARG, "n_calls must be >= 0");
+  int rc = check_batch(ctx, n);
+  if (rc != HT_OK) return rc;
+  CK(cudaSetDevice(ctx->cfg.device));
+  Plan *P = nullptr;
+  rc = get_plan(ctx, w, h, interval, &P);
+  if (rc != HT_OK) return rc;
+  rc = ensure_tracker_buffers(ctx);
+  if (rc != HT_OK) return rc;
+  CK(ctx->arena.reserve(P->arena_stride * (size_t)n));
+  cudaStream_t st = ctx->stream;
+  const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
+  const bool found_dev = out_found && is_device_ptr(out_found), objs_dev = is_device_ptr(out_objs);
+  const bool win_dev = out_windows && is_device_ptr(out_windows);
+  Rect *d_rects = rects_dev ? reinterpret_cast<Rect *>(out_rects) : ctx->d_out_rects.as<Rect>();
+  int32_t *d_counts = counts_dev ? out_counts : ctx->d_out_counts.as<int32_t>();
+  int32_t *d_found = out_found ? (found_dev ? out_found : ctx->d_found.as<int32_t>()) : nullptr;
+  int32_t *d_objs = objs_dev ? reinterpret_cast<int32_t *>(out_objs) : ctx->d_objs.as<int32_t>();
+  int32_t *d_win = out_windows ? (win_dev ? reinterpret_cast<int32_t *>(out_windows) : ctx->d_windows.as<int32_t>()) : nullptr;
+  if (n_calls == 0) CK(cudaMemsetAsync(d_objs, 0, sizeof(ht_trackobj) * n, st));
+  if (!rgba) return ctx->fail(HT_ERR_ARG, "rgba is NULL");
+  if ((reinterpret_cast<uintptr_t>(rgba) & 3u) != 0) return ctx->fail(HT_ERR_ARG, "rgba must be 4-byte aligned");
+  const size_t frame_bytes = (size_t)w * h * 4;
+  if (is_device_ptr(rgba)) {
+    rc = run_detect(ctx, P, rgba, 0, n, min_neighbors, d_rects, d_counts);
+    if (rc != HT_OK) return rc;
+    rc = run_track_from_detect(ctx, rgba, w, h, 0, n, d_rects, d_counts, calc_angles, n_calls, d_found, d_objs, d_win);
+    if (rc != HT_OK) return rc;
+  } else {
+    // host frames: upload in chunks on a copy stream so the H2D of chunk c+1 overlaps the kernels of chunk c
+    CK(ctx->d_frames.reserve(frame_bytes * (size_t)n));
+    if (!ctx->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    }
+    const int chunk = std::max(1, std::min(n, ctx->h2d_chunk));
+    const int n_chunks = (n + chunk - 1) / chunk;
+    while ((int)ctx->chunk_events.size() < n_chunks) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->chunk_events.push_back(e);
+    }
+    // the staging buffer may still be read by work enqueued earlier on the compute stream
+    CK(cudaEventRecord(ctx->compute_done, st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done, 0));
+    uint8_t *d_frames = ctx->d_frames.as<uint8_t>();
+    for (int c = 0; c < n_chunks; ++c) {
+      const int f0 = c * chunk, nf = std::min(chunk, n - f0);
+      CK(cudaMemcpyAsync(d_frames + frame_bytes * f0, rgba + frame_bytes * f0, frame_bytes * nf, cudaMemcpyHostToDevice,
+                         ctx->copy_stream));
+      CK(cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      const int f0 = c * chunk, nf = std::min(chunk, n - f0);
+      CK(cudaStreamWaitEvent(st, ctx->chunk_events[c], 0));
+      rc = run_detect(ctx, P, d_frames, f0, nf, min_neighbors, d_rects, d_counts);
+      if (rc != HT_OK) return rc;
+      rc = run_track_from_detect(ctx, d_frames, w, h, f0, nf, d_rects, d_counts, calc_angles, n_calls, d_found, d_objs, d_win);
+      if (rc != HT_OK) return rc;
+    }
+  }
+  ctx->last_plan = P;
+  ctx->last_n = n;
+  bool any_host = false;
+  if (!rects_dev) { CK(cudaMemcpyAsync(out_rects, d_rects, sizeof(Rect) * (size_t)n * ctx->K, cudaMemcpyDeviceToHost, st)); any_host = true; }
+  if (!counts_dev) { CK(cudaMemcpyAsync(out_counts, d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st)); any_host = true; }
+  if (out_found && !found_dev) { CK(cudaMemcpyAsync(out_found, d_found, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st)); any_host = true; }
+  if (!objs_dev) { CK(cudaMemcpyAsync(out_objs, d_objs, sizeof(ht_trackobj) * n, cudaMemcpyDeviceToHost, st)); any_host = true; }
+  if (out_windows && !win_dev) { CK(cudaMemcpyAsync(out_windows, d_win, sizeof(ht_window) * n, cudaMemcpyDeviceToHost, st)); any_host = true; }
+  if (any_host) return ht_sync(ctx);
   return HT_OK;
 }
 
@@ -746,6 +919,34 @@ int ht_whitebalance(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, doubl
   return HT_OK;
 }
 
+int ht_profile(ht_ctx *ctx, int enable) {
+  if (!ctx) return HT_ERR_ARG;
+  ctx->prof_on = enable != 0;
+  return HT_OK;
+}
+
+int ht_profile_read(ht_ctx *ctx, double *ms, uint64_t *launches, int reset) {
+  if (!ctx) return HT_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (auto &sp : ctx->prof_spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+      ctx->prof_ms[sp.cls] += t;
+      ctx->prof_launches[sp.cls] += 1;
+    } else cudaGetLastError();
+    ctx->prof_free.push_back(sp.a);
+    ctx->prof_free.push_back(sp.b);
+  }
+  ctx->prof_spans.clear();
+  for (int i = 0; i < HT_PROF_N; ++i) {
+    if (ms) ms[i] = ctx->prof_ms[i];
+    if (launches) launches[i] = ctx->prof_launches[i];
+    if (reset) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
+  }
+  return HT_OK;
+}
+
 // ---- introspection for the parity tests ----
 
 int ht_plan_info(ht_ctx *ctx, int w, int h, int interval, int32_t *n_slots, int32_t *scale_upto, int32_t *slot_w,
@@ -793,6 +994,15 @@ int ht_debug_raw(ht_ctx *ctx, int frame, ht_rect *out, int cap, int32_t *count) 
   const int ncopy = std::min<int>(std::min<uint32_t>(c, (uint32_t)ctx->raw_cap), cap);
   if (out && ncopy > 0)
     CK(cudaMemcpy(out, ctx->sorted.as<Rect>() + (size_t)frame * ctx->raw_cap, sizeof(Rect) * ncopy, cudaMemcpyDeviceToHost));
+  return HT_OK;
+}
+
+int ht_debug_track_stats(ht_ctx *ctx, uint64_t *out4, int reset) {
+  if (!ctx || !out4) return HT_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out4, ctx->d_flags.as<unsigned long long>() + 8, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(ctx->d_flags.as<unsigned long long>() + 8, 0, 4 * sizeof(uint64_t)));
   return HT_OK;
 }
 

@@ -49,8 +49,11 @@ __global__ void __launch_bounds__(256) k_track_init(const uint8_t *__restrict__ 
   const int k = blockIdx.x;
   const int slot = slots ? slots[k] : k;
   const int rx = rects[4 * k + 0], ry = rects[4 * k + 1], rw = rects[4 * k + 2], rh = rects[4 * k + 3];
-  if (rw <= 0 || rh <= 0) {  // no candidate (device pick) — slot left untouched
-    if (threadIdx.x == 0 && found) found[k] = 0;
+  if (rw <= 0 || rh <= 0) {  // no candidate (device pick): the slot becomes uninitialised
+    if (threadIdx.x == 0) {
+      state[slot].initialised = 0;
+      if (found) found[k] = 0;
+    }
     return;
   }
   for (int i = threadIdx.x; i < 4096; i += 256) sh[i] = 0;
@@ -151,7 +154,8 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
                                                const uint32_t *__restrict__ model_hist,
                                                const uint32_t *__restrict__ cur_hist, TrackState *__restrict__ state,
                                                int n_calls, int32_t *__restrict__ out_objs /* 6 x i32 per frame */,
-                                               int32_t *__restrict__ out_windows, int32_t *__restrict__ err_flag) {
+                                               int32_t *__restrict__ out_windows, int32_t *__restrict__ err_flag,
+                                               unsigned long long *__restrict__ stats) {
   __shared__ double wsm[4096];
   __shared__ double red[8][6];
   __shared__ int win[4];   // wadx, wady, wadw, wadh
@@ -161,7 +165,12 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   TrackState s = state[slot];
   if (!s.initialised) {
-    if (tid == 0) atomicOr(err_flag, 1);
+    if (tid == 0) {
+      atomicOr(err_flag, 1);
+      int32_t *o = out_objs + 6 * (size_t)k;
+      o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0;  // TrackObj() defaults
+      if (out_windows) { int32_t *w4 = out_windows + 4 * (size_t)k; w4[0] = w4[1] = w4[2] = w4[3] = 0; }
+    }
     return;
   }
   // getWeights — src/camshift.js:314-330
@@ -177,6 +186,7 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
   const uint32_t *px = reinterpret_cast<const uint32_t *>(rgba + (size_t)k * frame_bytes);
   __syncthreads();
 
+  unsigned long long st_pass = 0, st_serial = 0, st_px = 0;  // thread 0 only
   for (int call = 0; call < n_calls; ++call) {
     int prevx = s.sx, prevy = s.sy;                                  // :280-281
     Mom m = {0, 0, 0, 0, 0, 0};
@@ -219,11 +229,14 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
           m.m11 += red[w8][3]; m.m20 += red[w8][4]; m.m02 += red[w8][5];
         }
         bool exact = false;
+        ++st_pass;
+        st_px += (unsigned long long)(max(ww, 0)) * (unsigned long long)(max(wh, 0));
         double inv = 1.0 / m.m00;                                    // :109-111
         double vxf = m.m10 * inv - s.sw / 2.0, vyf = m.m01 * inv - s.sh / 2.0;
         if (trunc_ambiguous(vxf) || trunc_ambiguous(vyf)) {
           m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm);
           exact = true;
+          ++st_serial;
           inv = 1.0 / m.m00;
           vxf = m.m10 * inv - s.sw / 2.0;
           vyf = m.m01 * inv - s.sh / 2.0;
@@ -244,7 +257,7 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
             } else {
               amb = trunc_ambiguous(sqrt(a)) || trunc_ambiguous(sqrt(c));
             }
-            if (amb) m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm);
+            if (amb) { m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm); ++st_serial; }
           }
           ctrl = 1;
         } else {
@@ -285,6 +298,10 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
     __syncthreads();
   }
   if (tid == 0) {
+    if (stats) {
+      atomicAdd(&stats[0], st_pass); atomicAdd(&stats[1], st_serial);
+      atomicAdd(&stats[2], st_px); atomicAdd(&stats[3], (unsigned long long)n_calls);
+    }
     state[slot] = s;
     int32_t *o = out_objs + 6 * (size_t)k;
     o[0] = s.tx; o[1] = s.ty; o[2] = s.tw; o[3] = s.th;

@@ -122,6 +122,15 @@ int ht_track_init_from_detect(ht_ctx *ctx, const int32_t *slots, int n, const ui
 int ht_track(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int w, int h, int n_calls,
              ht_trackobj *out_objs, ht_window *out_windows);
 
+/* One facetrackr VJ frame followed by its CS frames, for a batch (src/facetrackr.js:67-126):
+ *   ht_detect -> first-max-confidence pick, confidence > -10 gate, floor -> initTracker on slot k for frame k
+ *   -> n_calls x track().  Frames with no usable face leave out_found[k] = 0 and a zero TrackObj.
+ * With HOST frames the upload is pipelined in chunks against the kernels of the previous chunk.
+ * out_found and out_windows are optional. */
+int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors,
+                    int calc_angles, int n_calls, ht_rect *out_rects, int32_t *out_counts, int32_t *out_found,
+                    ht_trackobj *out_objs, ht_window *out_windows);
+
 /* getBackProjectionImg() of the last track() state for one slot: RGBA w*h*4, floor(255*weight) gray
  * (src/camshift.js:177-196).  Debug path of the reference (src/facetrackr.js:194-196). */
 int ht_backprojection(ht_ctx *ctx, int slot, const uint8_t *rgba, int w, int h, uint8_t *out_rgba);
@@ -140,8 +149,19 @@ int ht_debug_plane(ht_ctx *ctx, int frame, int slot, int q, uint8_t *out, int ca
 int ht_debug_raw(ht_ctx *ctx, int frame, ht_rect *out, int cap, int32_t *count);
 /* tracker slot state: model histogram (4096 u32, optional) */
 int ht_debug_model_hist(ht_ctx *ctx, int slot, uint32_t *out4096);
+/* mean-shift counters since the last reset: {moment passes, passes redone in strict reference order,
+ * window pixels visited, track() calls} */
+int ht_debug_track_stats(ht_ctx *ctx, uint64_t *out4, int reset);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ht_launch_count(const ht_ctx *ctx);
+
+/* Per-kernel-class device time, measured with CUDA events recorded on the context's stream around
+ * every launch while enabled (bench.py's roofline uses the cascade class).  ht_profile_read syncs the
+ * stream and returns the accumulated milliseconds and launch counts per class. */
+enum { HT_PROF_GRAY = 0, HT_PROF_PYRAMID, HT_PROF_CASCADE, HT_PROF_GROUP, HT_PROF_HIST, HT_PROF_TRACK_INIT,
+       HT_PROF_TRACK, HT_PROF_N };
+int ht_profile(ht_ctx *ctx, int enable);
+int ht_profile_read(ht_ctx *ctx, double *ms_out, uint64_t *launches_out, int reset);
 
 #ifdef __cplusplus
 }

@@ -132,3 +132,36 @@ def test_backprojection_and_whitebalance(ctx, blob):
     wb = ctx.whitebalance(frames)
     for i in range(3):
         assert wb[i] == oracle.whitebalance(frames[i])
+
+
+def test_detect_track_host_and_device(ctx, blob):
+    """ht_detect_track (chunk-pipelined host path and device path) == detect -> pick -> init -> n x track."""
+    import torch
+    frames = synth.batch(5, 640, 480, start=60)
+    frames[4] = synth.frame(0, 640, 480, kind="constant")        # a frame without any face
+    ref_objs = []
+    for i in range(5):
+        res = oracle.detect(frames[i], blob)
+        cand = None
+        for r in res:
+            if cand is None or r[4] > cand[4]:
+                cand = r
+        if cand is None or not cand[4] > -10:
+            ref_objs.append(None)
+            continue
+        ot = oracle.CamshiftTracker(calc_angles=False)
+        ot.init_tracker(frames[i], *[int(math.floor(v)) for v in cand[:4]])
+        for _ in range(4):
+            ot.track(frames[i])
+        ref_objs.append((ot.track_obj(), ot.search_window(), res))
+    for src in (frames, torch.from_numpy(frames).cuda()):
+        dets, found, objs, wins = ctx.detect_track(src, 5, 1, calc_angles=False, n_calls=4)
+        for i in range(5):
+            if ref_objs[i] is None:
+                assert found[i] == 0 and dets[i] == [] and objs[i]["width"] == 0
+                continue
+            want, win, res = ref_objs[i]
+            assert found[i] == 1
+            assert [(d["x"], d["y"], d["width"], d["height"], d["confidence"], d["neighbors"]) for d in dets[i]] == res
+            assert (objs[i]["x"], objs[i]["y"], objs[i]["width"], objs[i]["height"]) == (want["x"], want["y"], want["width"], want["height"])
+            assert wins[i] == win
