@@ -237,10 +237,12 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
 // "HTC1" cascade blob (tools/pack_cascade.py) -> device tables
 struct HostCascade {
   int n_stages = 0, n_features = 0, width = 0, height = 0;
-  std::vector<DevStage> stages;
-  std::vector<DevFeat> feats;
-  std::vector<double2> alphas;
+  ConstCascade cc;      // image of the __constant__ table
+  uint64_t id = 0;      // FNV-1a of cc: identical cascades share the loaded constants
 };
+
+// which cascade image is currently in c_casc, per device
+uint64_t g_loaded_cascade[64] = {0};
 
 int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &err) {
   const uint8_t *b = static_cast<const uint8_t *>(blob);
@@ -252,16 +254,19 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   if (hc.width != 24 || hc.height != 24) { err = "cascade blob: only 24x24 BBF windows are supported"; return HT_ERR_CASCADE; }
   const size_t need = 24 + (size_t)hc.n_stages * 16 + (size_t)hc.n_features * 48;
   if (len < need) { err = "cascade blob: truncated"; return HT_ERR_CASCADE; }
+  if (hc.n_features > MAX_FEATS) { err = "cascade blob: more features than the constant table holds"; return HT_ERR_CASCADE; }
   const uint8_t *ps = b + 24, *pf = ps + (size_t)hc.n_stages * 16, *pa = pf + (size_t)hc.n_features * 32;
+  ConstCascade &cc = hc.cc;
+  memset(&cc, 0, sizeof(cc));
   int total = 0;
   for (int j = 0; j < hc.n_stages; ++j) {
     uint32_t cnt, first; double thr;
     memcpy(&cnt, ps + 16 * j, 4); memcpy(&first, ps + 16 * j + 4, 4); memcpy(&thr, ps + 16 * j + 8, 8);
     if ((int)first != total || (int)(first + cnt) > hc.n_features) { err = "cascade blob: stage table"; return HT_ERR_CASCADE; }
     total += (int)cnt;
-    DevStage st; st.first = (int)first; st.count = (int)cnt; st.threshold = thr;
-    hc.stages.push_back(st);
+    cc.stage[j].first = (int)first; cc.stage[j].count = (int)cnt; cc.stage[j].threshold = thr;
   }
+  cc.n_stages = hc.n_stages;
   if (total != hc.n_features) { err = "cascade blob: feature count"; return HT_ERR_CASCADE; }
   auto point_off = [&](int z, int x, int y, bool &ok) -> uint16_t {
     const int lim = (24 >> z) - 1;
@@ -272,27 +277,40 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   };
   for (int k = 0; k < hc.n_features; ++k) {
     const uint8_t *r = pf + (size_t)k * 32;
-    DevFeat f{};
     const int size = r[0];
     if (size < 1 || size > 5) { err = "cascade blob: feature size"; return HT_ERR_CASCADE; }
-    f.size = (uint16_t)size;
     bool ok = true;
+    int cnt[2] = {0, 0};
     for (int side = 0; side < 2; ++side) {
       const uint8_t *z = r + (side ? 17 : 2), *x = z + 5, *y = z + 10;
-      uint16_t *dst = side ? f.n : f.p;
+      uint16_t *dst = &cc.off[k][side ? 5 : 0];
       if ((int8_t)z[0] < 0) { err = "cascade blob: slot 0 must be a valid point (src/ccv.js:191-192)"; return HT_ERR_CASCADE; }
       const uint16_t first = point_off((int8_t)z[0], x[0], y[0], ok);
-      for (int q = 0; q < 5; ++q) {
-        if (q < size && (int8_t)z[q] >= 0) dst[q] = point_off((int8_t)z[q], x[q], y[q], ok);
-        else dst[q] = first;  // min/max are idempotent: unused slots repeat slot 0
-      }
+      int m = 0;  // min/max are order independent: valid points are compacted to the front
+      for (int q = 0; q < size; ++q)
+        if ((int8_t)z[q] >= 0) dst[m++] = point_off((int8_t)z[q], x[q], y[q], ok);
+      cnt[side] = m;
+      for (; m < 5; ++m) dst[m] = first;
     }
     if (!ok) { err = "cascade blob: point out of the 24x24 window"; return HT_ERR_CASCADE; }
-    hc.feats.push_back(f);
+    cc.np_nn[k] = (uint8_t)(cnt[0] | (cnt[1] << 4));
     double a[2];
     memcpy(a, pa + (size_t)k * 16, 16);
-    hc.alphas.push_back(make_double2(a[0], a[1]));
+    if (!(a[0] == -a[1])) { err = "cascade blob: alpha[2k] != -alpha[2k+1] (unsupported)"; return HT_ERR_CASCADE; }
+    cc.alpha[k] = a[1];
   }
+  // stage groups for queue compaction: {0,1} {2,3} {4,5} {6,7,8} {9..}
+  {
+    const int cuts[] = {0, 2, 4, 6, 9};
+    int g = 0;
+    for (int cpos : cuts) if (cpos < hc.n_stages) cc.group_first[g++] = cpos;
+    cc.group_first[g] = hc.n_stages;
+    cc.n_groups = g;
+  }
+  uint64_t hsh = 1469598103934665603ull;
+  const uint8_t *cb = reinterpret_cast<const uint8_t *>(&cc);
+  for (size_t i = 0; i < sizeof(cc); ++i) { hsh ^= cb[i]; hsh *= 1099511628211ull; }
+  hc.id = hsh ? hsh : 1;
   return HT_OK;
 }
 
@@ -308,8 +326,7 @@ struct ht_ctx {
   uint64_t launches = 0;
 
   HostCascade hc;
-  DevBuf d_casc;
-  DevCascade dcasc{};
+  DevBuf d_casc;  // unused placeholder kept for the release list
 
   std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
   Plan *last_plan = nullptr;
@@ -500,9 +517,15 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
   }
   // K3 cascade
   if (!P->casc_tiles.empty()) {
+    // make this context's cascade the active __constant__ table (contexts with the same blob share it;
+    // contexts with DIFFERENT cascades must not run concurrently on one device)
+    if (g_loaded_cascade[ctx->cfg.device & 63] != ctx->hc.id) {
+      CK(cudaMemcpyToSymbolAsync(c_casc, &ctx->hc.cc, sizeof(ConstCascade), 0, cudaMemcpyHostToDevice, st));
+      g_loaded_cascade[ctx->cfg.device & 63] = ctx->hc.id;
+    }
     ctx->prof_begin(HT_PROF_CASCADE);
     k_cascade<<<dim3((unsigned)P->casc_tiles.size(), n), CASCADE_THREADS, 0, st>>>(
-        P->dplan, ctx->dcasc, arena, P->arena_stride, raw_keys, raw_conf, raw_count, ctx->raw_cap);
+        P->dplan, arena, P->arena_stride, raw_keys, raw_conf, raw_count, ctx->raw_cap);
     ctx->prof_end();
     ++ctx->launches;
   }
@@ -593,32 +616,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
     c->own_stream = true;
   }
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
-  // cascade tables
-  const HostCascade &hc = c->hc;
-  const size_t o_feat = 0, o_alpha = align_up(o_feat + hc.feats.size() * sizeof(DevFeat), (size_t)256);
-  const size_t o_stage = align_up(o_alpha + hc.alphas.size() * sizeof(double2), (size_t)256);
-  const size_t total = o_stage + hc.stages.size() * sizeof(DevStage);
-  std::vector<uint8_t> host(total, 0);
-  memcpy(host.data() + o_feat, hc.feats.data(), hc.feats.size() * sizeof(DevFeat));
-  memcpy(host.data() + o_alpha, hc.alphas.data(), hc.alphas.size() * sizeof(double2));
-  memcpy(host.data() + o_stage, hc.stages.data(), hc.stages.size() * sizeof(DevStage));
-  if (c->d_casc.reserve(total) != cudaSuccess ||
-      cudaMemcpy(c->d_casc.p, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
-    g_create_error = "ht_create: cascade upload failed"; return HT_ERR_CUDA;
-  }
-  uint8_t *b = c->d_casc.as<uint8_t>();
-  c->dcasc.feat = reinterpret_cast<const DevFeat *>(b + o_feat);
-  c->dcasc.alpha = reinterpret_cast<const double2 *>(b + o_alpha);
-  c->dcasc.stage = reinterpret_cast<const DevStage *>(b + o_stage);
-  c->dcasc.n_stages = hc.n_stages;
-  // stage groups for queue compaction: {0,1} {2,3} {4,5} {6,7,8} {9..}
-  {
-    const int cuts[] = {0, 2, 4, 6, 9};
-    int g = 0;
-    for (int cpos : cuts) if (cpos < hc.n_stages) c->dcasc.group_first[g++] = cpos;
-    c->dcasc.group_first[g] = hc.n_stages;
-    c->dcasc.n_groups = g;
-  }
+  // the cascade image is copied into __constant__ memory lazily by run_detect (load_cascade)
   // per-frame result buffers
   const size_t mf = (size_t)cfg->max_frames;
   bool ok = c->raw_keys.reserve(mf * c->raw_cap * sizeof(uint32_t)) == cudaSuccess &&

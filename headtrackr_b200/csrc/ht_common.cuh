@@ -79,26 +79,28 @@ struct DevCascTile {
   uint16_t scale, tx, ty, pad_;
 };
 
-struct DevFeat {   // shared-memory byte offsets relative to a0 (see above)
-  uint16_t p[5];
-  uint16_t n[5];
-  uint16_t size;   // number of point slots used; slots with z==-1 inside `size` repeat slot 0
-  uint16_t pad_;
-};
+// The active cascade lives in __constant__ memory (ht_detect.cuh: c_casc): every lane of a warp
+// evaluates the same feature at the same time, so all table reads are uniform and go through the
+// constant cache / uniform datapath instead of the LSU pipe that the pixel loads saturate.
+constexpr int MAX_FEATS = 2176;
 
 struct DevStage {
   int32_t first, count;
   double threshold;
 };
 
-struct DevCascade {
-  const DevFeat *feat;
-  const double2 *alpha;  // {alpha[2k] (fail), alpha[2k+1] (pass)}  src/ccv.js:194,219
-  const DevStage *stage;
+struct ConstCascade {
+  // shared-memory byte offsets relative to a0; valid p points first (np of them), then repeats of
+  // slot 0; same for n.  Layout [feature][p0..p4, n0..n4].
+  uint16_t off[MAX_FEATS][10];
+  double alpha[MAX_FEATS];     // alpha[2k+1] (pass); alpha[2k] == -alpha[2k+1] is checked on the host
+  uint8_t np_nn[MAX_FEATS];    // np | nn << 4   (1..5 each)
+  DevStage stage[MAX_STAGES];
   int32_t n_stages;
   int32_t n_groups;
   int32_t group_first[MAX_GROUPS + 1];  // stage-group boundaries for queue compaction
 };
+static_assert(sizeof(ConstCascade) <= 65536 - 1024, "cascade must fit the constant bank");
 
 struct DevPlan {  // pointers into one device allocation
   const DevPlane *planes;

@@ -95,25 +95,47 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
 // Windows are evaluated in stage groups; survivors of a group are compacted (ballot + prefix) into
 // a shared-memory queue so that later, longer stages run on dense warps.
 
-__device__ __forceinline__ bool stage_pass(const uint8_t *__restrict__ win, const DevCascade &c, int j,
-                                           bool alive, double &sum_out) {
-  const DevStage st = c.stage[j];
+__constant__ ConstCascade c_casc;
+
+__device__ __forceinline__ unsigned ldpx(const uint8_t *__restrict__ win, unsigned off) { return win[off]; }
+
+// one stage for one window per lane; all control flow is warp-uniform (table reads are uniform)
+__device__ __forceinline__ bool stage_pass(const uint8_t *__restrict__ win, int j, bool alive, double &sum_out) {
+  const int first = c_casc.stage[j].first, last = first + c_casc.stage[j].count;
   double sum = 0.0;
-  for (int k = st.first; k < st.first + st.count; ++k) {
-    const DevFeat f = c.feat[k];   // warp-uniform address -> one broadcast load
-    const double2 al = c.alpha[k];
-    unsigned pmin = win[f.p[0]], nmax = win[f.n[0]];
-    for (int s = 1; s < f.size; ++s) {
-      pmin = min(pmin, (unsigned)win[f.p[s]]);
-      nmax = max(nmax, (unsigned)win[f.n[s]]);
+  for (int k = first; k < last; ++k) {
+    const unsigned kind = c_casc.np_nn[k];
+    const unsigned np = kind & 15u, nn = kind >> 4;
+    unsigned pmin = ldpx(win, c_casc.off[k][0]);
+    unsigned nmax = ldpx(win, c_casc.off[k][5]);
+    if (np > 1) {
+      pmin = min(pmin, ldpx(win, c_casc.off[k][1]));
+      if (np > 2) {
+        pmin = min(pmin, ldpx(win, c_casc.off[k][2]));
+        if (np > 3) {
+          pmin = min(pmin, ldpx(win, c_casc.off[k][3]));
+          if (np > 4) pmin = min(pmin, ldpx(win, c_casc.off[k][4]));
+        }
+      }
     }
-    sum += (pmin > nmax) ? al.y : al.x;
+    if (nn > 1) {
+      nmax = max(nmax, ldpx(win, c_casc.off[k][6]));
+      if (nn > 2) {
+        nmax = max(nmax, ldpx(win, c_casc.off[k][7]));
+        if (nn > 3) {
+          nmax = max(nmax, ldpx(win, c_casc.off[k][8]));
+          if (nn > 4) nmax = max(nmax, ldpx(win, c_casc.off[k][9]));
+        }
+      }
+    }
+    const double a = c_casc.alpha[k];
+    sum += (pmin > nmax) ? a : -a;   // src/ccv.js:194,219 (alpha[2k] == -alpha[2k+1])
   }
   sum_out = sum;
-  return alive && !(sum < st.threshold);  // src/ccv.js:222
+  return alive && !(sum < c_casc.stage[j].threshold);  // src/ccv.js:222
 }
 
-__global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan, DevCascade casc,
+__global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan,
                                                               const uint8_t *__restrict__ arena, size_t arena_stride,
                                                               uint32_t *__restrict__ raw_keys,
                                                               double *__restrict__ raw_conf,
@@ -161,7 +183,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan, DevCa
     for (int i = tid; i < 4 * L2_ROWS * QC; i += CASCADE_THREADS) {
       const int q = i / (L2_ROWS * QC), rem = i % (L2_ROWS * QC);
       const int r = rem / QC, c = (rem % QC) * 4;
-      const DevPlane pl = plan.planes[sc.p2[q]];
+      const DevPlane pl = plan.planes[plan.scales[tl.scale].p2[q]];  // (indexing the register copy `sc` would spill it)
       uint32_t v = 0;
       if (y0 + r < pl.h && x0 + c < pl.pitch)
         v = __ldg(reinterpret_cast<const uint32_t *>(fr + pl.off + (size_t)(y0 + r) * pl.pitch + x0 + c));
@@ -174,9 +196,9 @@ __global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan, DevCa
 
   // ---- stage groups ----
   int cur = 0;  // queue written by the current group
-  for (int g = 0; g < casc.n_groups; ++g) {
-    const int jb = casc.group_first[g], je = casc.group_first[g + 1];
-    const bool last = (g == casc.n_groups - 1);
+  for (int g = 0; g < c_casc.n_groups; ++g) {
+    const int jb = c_casc.group_first[g], je = c_casc.group_first[g + 1];
+    const bool last = (g == c_casc.n_groups - 1);
     const int n_in = (g == 0) ? NWIN : qcount[cur ^ 1];
     const int n_iter = (n_in + CASCADE_THREADS - 1) / CASCADE_THREADS;
     for (int it = 0; it < n_iter; ++it) {
@@ -192,7 +214,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan, DevCa
       double sum = 0.0;
       for (int j = jb; j < je; ++j) {
         if (!__any_sync(0xffffffffu, alive)) break;
-        alive = stage_pass(win, casc, j, alive, sum);
+        alive = stage_pass(win, j, alive, sum);
       }
       const unsigned m = __ballot_sync(0xffffffffu, alive);
       if (m) {
