@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -239,6 +240,8 @@ struct HostCascade {
   int n_stages = 0, n_features = 0, width = 0, height = 0;
   ConstCascade cc;      // image of the __constant__ table
   uint64_t id = 0;      // FNV-1a of cc: identical cascades share the loaded constants
+  bool fast = false;    // blob == the cascade the generated stages were specialised for
+  std::vector<LateFeat> late;  // per-feature records for the warp-per-window late stages
 };
 
 // which cascade image is currently in c_casc, per device
@@ -299,18 +302,53 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
     if (!(a[0] == -a[1])) { err = "cascade blob: alpha[2k] != -alpha[2k+1] (unsupported)"; return HT_ERR_CASCADE; }
     cc.alpha[k] = a[1];
   }
-  // stage groups for queue compaction: {0,1} {2,3} {4,5} {6,7,8} {9..}
+  // exact integer images of alpha / threshold (see LateFeat in ht_common.cuh)
+  bool ints_ok = true;
+  hc.late.assign((size_t)hc.n_features, LateFeat{});
+  auto to_int = [&](double v, long long &out) {
+    const double scaled = v * 1e8;
+    const long long r = llround(scaled);
+    out = r;
+    return std::fabs(scaled - (double)r) < 1e-3 && ((double)r / 1e8) == v && std::llabs(r) < (1ll << 40);
+  };
+  for (int k = 0; k < hc.n_features; ++k) {
+    long long ai = 0;
+    if (!to_int(cc.alpha[k], ai) || std::llabs(ai) > 0x7fffffffll) ints_ok = false;
+    LateFeat &lf = hc.late[k];
+    for (int q = 0; q < 10; ++q) lf.off[q] = cc.off[k][q];
+    lf.a_int = (int32_t)ai;
+    lf.np = cc.np_nn[k] & 15; lf.nn = cc.np_nn[k] >> 4;
+  }
+  for (int j = 0; j < hc.n_stages; ++j) {
+    long long ti = 0;
+    if (!to_int(cc.stage[j].threshold, ti)) ints_ok = false;
+    cc.thr_int[j] = ti;
+  }
+  // lane-per-window groups {0,1} {2,3} {4,5}; then either warp-per-window late stages (exact integers)
+  // or, when the cascade's numbers are not 8-digit decimals, two more lane-per-window groups.
   {
-    const int cuts[] = {0, 2, 4, 6, 9};
     int g = 0;
-    for (int cpos : cuts) if (cpos < hc.n_stages) cc.group_first[g++] = cpos;
-    cc.group_first[g] = hc.n_stages;
+    const int cuts_int[] = {0, 2, 4}, cuts_fp[] = {0, 2, 4, 6, 9};
+    if (ints_ok && !getenv("HT_NO_LATE")) {
+      for (int cpos : cuts_int) if (cpos < hc.n_stages) cc.group_first[g++] = cpos;
+      cc.group_first[g] = std::min(6, hc.n_stages);
+      cc.late_int = 1;
+    } else {
+      for (int cpos : cuts_fp) if (cpos < hc.n_stages) cc.group_first[g++] = cpos;
+      cc.group_first[g] = hc.n_stages;
+      cc.late_int = 0;
+    }
     cc.n_groups = g;
   }
   uint64_t hsh = 1469598103934665603ull;
   const uint8_t *cb = reinterpret_cast<const uint8_t *>(&cc);
   for (size_t i = 0; i < sizeof(cc); ++i) { hsh ^= cb[i]; hsh *= 1099511628211ull; }
   hc.id = hsh ? hsh : 1;
+  uint64_t bh = 1469598103934665603ull;
+  for (size_t i = 0; i < len; ++i) { bh ^= b[i]; bh *= 1099511628211ull; }
+  hc.fast = (bh == HT_GEN_BLOB_ID) && (len == need) && cc.n_groups >= 3 && cc.group_first[1] == 2 &&
+            cc.group_first[2] == 4 && cc.group_first[3] == 6;
+  if (getenv("HT_NO_FAST")) hc.fast = false;  // A/B switch for profiling: table-driven stages only
   return HT_OK;
 }
 
@@ -326,7 +364,7 @@ struct ht_ctx {
   uint64_t launches = 0;
 
   HostCascade hc;
-  DevBuf d_casc;  // unused placeholder kept for the release list
+  DevBuf d_casc;  // LateFeat table
 
   std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
   Plan *last_plan = nullptr;
@@ -524,8 +562,9 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       g_loaded_cascade[ctx->cfg.device & 63] = ctx->hc.id;
     }
     ctx->prof_begin(HT_PROF_CASCADE);
-    k_cascade<<<dim3((unsigned)P->casc_tiles.size(), n), CASCADE_THREADS, 0, st>>>(
-        P->dplan, arena, P->arena_stride, raw_keys, raw_conf, raw_count, ctx->raw_cap);
+    auto kern = ctx->hc.fast ? k_cascade<true> : k_cascade<false>;
+    kern<<<dim3((unsigned)P->casc_tiles.size(), n), CASCADE_THREADS, 0, st>>>(
+        P->dplan, ctx->d_casc.as<LateFeat>(), arena, P->arena_stride, raw_keys, raw_conf, raw_count, ctx->raw_cap);
     ctx->prof_end();
     ++ctx->launches;
   }
@@ -616,7 +655,11 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
     c->own_stream = true;
   }
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
-  // the cascade image is copied into __constant__ memory lazily by run_detect (load_cascade)
+  // the cascade image is copied into __constant__ memory lazily by run_detect; the late-stage table lives in HBM
+  if (c->d_casc.reserve(c->hc.late.size() * sizeof(LateFeat)) != cudaSuccess ||
+      cudaMemcpy(c->d_casc.p, c->hc.late.data(), c->hc.late.size() * sizeof(LateFeat), cudaMemcpyHostToDevice) != cudaSuccess) {
+    g_create_error = "ht_create: cascade upload failed"; return HT_ERR_CUDA;
+  }
   // per-frame result buffers
   const size_t mf = (size_t)cfg->max_frames;
   bool ok = c->raw_keys.reserve(mf * c->raw_cap * sizeof(uint32_t)) == cudaSuccess &&

@@ -82,7 +82,7 @@ struct DevCascTile {
 // The active cascade lives in __constant__ memory (ht_detect.cuh: c_casc): every lane of a warp
 // evaluates the same feature at the same time, so all table reads are uniform and go through the
 // constant cache / uniform datapath instead of the LSU pipe that the pixel loads saturate.
-constexpr int MAX_FEATS = 2176;
+constexpr int MAX_FEATS = 2112;
 
 struct DevStage {
   int32_t first, count;
@@ -97,9 +97,26 @@ struct ConstCascade {
   uint8_t np_nn[MAX_FEATS];    // np | nn << 4   (1..5 each)
   DevStage stage[MAX_STAGES];
   int32_t n_stages;
-  int32_t n_groups;
-  int32_t group_first[MAX_GROUPS + 1];  // stage-group boundaries for queue compaction
+  int32_t n_groups;                     // lane-per-window stage groups (queue compaction between them)
+  int32_t group_first[MAX_GROUPS + 1];  // their stage boundaries; stages >= group_first[n_groups] are "late"
+  int32_t late_int;                     // 1: late stages run warp-per-window with exact integer sums
+  int64_t thr_int[MAX_STAGES];          // stage thresholds x 1e8 (exact, see LateFeat)
 };
+
+// Late stages (few windows, hundreds of features): one WARP per window, one feature per lane.
+// Stage sums are accumulated as exact integers: every alpha / threshold of the cascade is a decimal
+// literal with <= 8 fractional digits, so alpha * 1e8 is an integer (checked on the host).  The
+// fp64 sequential sum of the reference differs from the exact decimal sum by < 1e-11, while two
+// distinct decimal sums differ by >= 1e-8: `sum < threshold` (src/ccv.js:222) is therefore decided
+// exactly by the integers unless they are EQUAL, in which case the stage is re-evaluated with the
+// reference's ordered fp64 adds.  The confidence of a surviving window is always the ordered fp64 sum.
+struct alignas(16) LateFeat {
+  uint16_t off[10];  // p0..p4, n0..n4 (compacted, as ConstCascade::off)
+  int32_t a_int;     // alpha[2k+1] * 1e8
+  uint8_t np, nn;
+  uint8_t pad_[6];
+};
+static_assert(sizeof(LateFeat) == 32, "LateFeat is two 16-byte loads");
 static_assert(sizeof(ConstCascade) <= 65536 - 1024, "cascade must fit the constant bank");
 
 struct DevPlan {  // pointers into one device allocation

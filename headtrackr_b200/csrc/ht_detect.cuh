@@ -97,6 +97,26 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
 
 __constant__ ConstCascade c_casc;
 
+// ---- stages specialised at build time (tools/gen_cascade_code.py) ----
+__host__ __device__ constexpr unsigned gen_off(int z, int x, int y) {
+  return z == 0 ? (unsigned)(y * TP + x) : z == 1 ? (unsigned)(REGION + TP + 2 * x + 2 * y * TP) : (unsigned)(REGION + 4 * x + 4 * y * TP);
+}
+#define HT_W(z, x, y) ((unsigned)win[gen_off(z, x, y)])
+#define HT_MIN2(a, b) min(a, b)
+#define HT_MIN3(a, b, c) min(min(a, b), c)
+#define HT_MAX2(a, b) max(a, b)
+#define HT_MAX3(a, b, c) max(max(a, b), c)
+#define HT_ALPHA(k) (c_casc.alpha[k])
+#define HT_THRESHOLD(j) (c_casc.stage[j].threshold)
+#include "cascade_face_gen.inc"
+#undef HT_W
+#undef HT_MIN2
+#undef HT_MIN3
+#undef HT_MAX2
+#undef HT_MAX3
+#undef HT_ALPHA
+#undef HT_THRESHOLD
+
 __device__ __forceinline__ unsigned ldpx(const uint8_t *__restrict__ win, unsigned off) { return win[off]; }
 
 // one stage for one window per lane; all control flow is warp-uniform (table reads are uniform)
@@ -135,7 +155,8 @@ __device__ __forceinline__ bool stage_pass(const uint8_t *__restrict__ win, int 
   return alive && !(sum < c_casc.stage[j].threshold);  // src/ccv.js:222
 }
 
-__global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan,
+template <bool FAST>
+__global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
                                                               const uint8_t *__restrict__ arena, size_t arena_stride,
                                                               uint32_t *__restrict__ raw_keys,
                                                               double *__restrict__ raw_conf,
@@ -195,10 +216,9 @@ __global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan,
   __syncthreads();
 
   // ---- stage groups ----
+  // eval(win, alive, sum) runs the stages of one group for one window per lane (warp-uniform control flow)
   int cur = 0;  // queue written by the current group
-  for (int g = 0; g < c_casc.n_groups; ++g) {
-    const int jb = c_casc.group_first[g], je = c_casc.group_first[g + 1];
-    const bool last = (g == c_casc.n_groups - 1);
+  auto run_group = [&](const int g, const bool last, auto eval) {
     const int n_in = (g == 0) ? NWIN : qcount[cur ^ 1];
     const int n_iter = (n_in + CASCADE_THREADS - 1) / CASCADE_THREADS;
     for (int it = 0; it < n_iter; ++it) {
@@ -212,10 +232,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan,
       if (g == 0) alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh);
       const uint8_t *win = tile + (4 * lx + 2 * dx) + (4 * ly + 2 * dy) * TP;
       double sum = 0.0;
-      for (int j = jb; j < je; ++j) {
-        if (!__any_sync(0xffffffffu, alive)) break;
-        alive = stage_pass(win, j, alive, sum);
-      }
+      alive = eval(win, alive, sum);
       const unsigned m = __ballot_sync(0xffffffffu, alive);
       if (m) {
         if (!last) {
@@ -237,7 +254,94 @@ __global__ void __launch_bounds__(CASCADE_THREADS) k_cascade(DevPlan plan,
     cur ^= 1;
     if (tid == 0) qcount[cur] = 0;  // the queue two groups back is free again
     __syncthreads();
-    if (!last && qcount[cur ^ 1] == 0) break;
+    return last || qcount[cur ^ 1] == 0;  // true: nothing left to do
+  };
+  auto table_stages = [&](const int jb, const int je) {
+    return [=](const uint8_t *win, bool alive, double &sum) {
+      for (int j = jb; j < je; ++j) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        alive = stage_pass(win, j, alive, sum);
+      }
+      return alive;
+    };
+  };
+  const int late_first = c_casc.group_first[c_casc.n_groups];
+  const bool has_late = late_first < c_casc.n_stages;
+  int g = 0;
+  if (FAST) {
+    // specialised groups {0,1} {2,3} {4,5}: straight-line code generated from the cascade (cascade_face_gen.inc)
+    static_assert(HT_GEN_STAGES == 6, "the FAST path hard-codes three groups of two generated stages");
+#define HT_GEN_PAIR(A, B)                                                   \
+  [&](const uint8_t *win, bool alive, double &sum) {                        \
+    alive = alive && gen_stage##A(win, sum);                                \
+    if (__any_sync(0xffffffffu, alive)) alive = gen_stage##B(win, sum) && alive; \
+    return alive;                                                           \
+  }
+    if (run_group(0, false, HT_GEN_PAIR(0, 1))) return;
+    if (run_group(1, false, HT_GEN_PAIR(2, 3))) return;
+    if (run_group(2, false, HT_GEN_PAIR(4, 5))) return;
+#undef HT_GEN_PAIR
+    g = 3;
+  }
+  for (; g < c_casc.n_groups; ++g)
+    if (run_group(g, g == c_casc.n_groups - 1 && !has_late,
+                  table_stages(c_casc.group_first[g], c_casc.group_first[g + 1]))) return;
+  if (!has_late) return;
+
+  // ---- late stages: one warp per surviving window, one feature per lane, exact integer sums ----
+  {
+    const int n_in = qcount[cur ^ 1];
+    const uint16_t *qin = queue[cur ^ 1];
+    for (int w = tid >> 5; w < n_in; w += CASCADE_THREADS / 32) {
+      const int wid = qin[w];
+      const int lx = wid & (TW - 1), ly = (wid / TW) & (TH - 1), q = wid / (TW * TH);
+      const uint8_t *win = tile + (4 * lx + 2 * (q & 1)) + (4 * ly + 2 * (q >> 1)) * TP;
+      bool pass = true;
+      for (int j = late_first; j < c_casc.n_stages && pass; ++j) {
+        const int first = c_casc.stage[j].first, count = c_casc.stage[j].count;
+        long long acc = 0;
+        for (int base = 0; base < count; base += 32) {
+          const int kk = base + lane;
+          if (kk < count) {
+            const uint4 *f = reinterpret_cast<const uint4 *>(late + first + kk);
+            const uint4 a = __ldg(f), b = __ldg(f + 1);
+            const unsigned np = b.z & 0xffu, nn = (b.z >> 8) & 0xffu;
+            unsigned pm = win[a.x & 0xffffu], nm = win[a.z >> 16];
+            if (np > 1) pm = min(pm, (unsigned)win[a.x >> 16]);
+            if (np > 2) pm = min(pm, (unsigned)win[a.y & 0xffffu]);
+            if (np > 3) pm = min(pm, (unsigned)win[a.y >> 16]);
+            if (np > 4) pm = min(pm, (unsigned)win[a.z & 0xffffu]);
+            if (nn > 1) nm = max(nm, (unsigned)win[a.w & 0xffffu]);
+            if (nn > 2) nm = max(nm, (unsigned)win[a.w >> 16]);
+            if (nn > 3) nm = max(nm, (unsigned)win[b.x & 0xffffu]);
+            if (nn > 4) nm = max(nm, (unsigned)win[b.x >> 16]);
+            const int ai = (int)b.y;
+            acc += (pm > nm) ? (long long)ai : -(long long)ai;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const long long thr = c_casc.thr_int[j];
+        if (acc == thr) {  // exact tie of the decimal sums: decide with the reference's ordered fp64 adds
+          double s;
+          pass = stage_pass(win, j, true, s);
+        } else {
+          pass = acc > thr;
+        }
+      }
+      if (pass) {  // src/ccv.js:227-234; confidence = ordered fp64 sum of the last stage
+        double s;
+        stage_pass(win, c_casc.n_stages - 1, true, s);
+        if (lane == 0) {
+          const uint32_t key = sc.win_base + (uint32_t)((q * sc.qh + (y0 + ly)) * sc.qw + (x0 + lx));
+          const uint32_t pos = atomicAdd(&raw_count[frame], 1u);
+          if (pos < (uint32_t)raw_cap) {
+            raw_keys[(size_t)frame * raw_cap + pos] = key;
+            raw_conf[(size_t)frame * raw_cap + pos] = s;
+          }
+        }
+      }
+    }
   }
 }
 
