@@ -158,7 +158,9 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
         }
         return first;
       };
+      while (P.taps.size() & 3) P.taps.push_back(TapEnt{0, 0, 0, 0}); // column tables start 32 B aligned
       j.col_off = make_taps(dw, js.sw, js.sx);
+      while (P.taps.size() & 3) P.taps.push_back(TapEnt{0, 0, 0, 0}); // k_resample reads column taps four at a time
       j.row_off = make_taps(dh, js.sh, js.sy);
       const unsigned long long d = 4ull * dw * dh;
       const unsigned __int128 nmax = (unsigned __int128)d * 255 + d / 2 + 1;
@@ -174,6 +176,9 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
     const int job_id = (int)P.jobs.size();
     P.jobs.push_back(j);
     const DevPlane &dp = P.planes[j.dst];
+    const DevPlane &spl = P.planes[j.src];
+    j.src_off = spl.off; j.dst_off = dp.off; j.src_pitch = spl.pitch; j.dst_pitch = dp.pitch; j.dst_h = dp.h;
+    P.jobs.back() = j;
     for (int ty = 0; ty < (dp.h + 7) / 8; ++ty)
       for (int tx = 0; tx < (dp.pitch + 127) / 128; ++tx) {
         DevPyrTile t; t.job = (uint16_t)job_id; t.tx = (uint16_t)tx; t.ty = (uint16_t)ty; t.pad_ = 0;
@@ -371,6 +376,7 @@ struct ht_ctx {
   int last_n = 0;
 
   DevBuf arena, d_frames, raw_keys, raw_conf, raw_count, sorted, labels, seq2, d_out_rects, d_out_counts, d_flags;
+  DevBuf bins;  // [frames][h][w] u16 colour-bin planes written by k_hist, read by k_track
   DevBuf model_hist, cur_hist, track_state, d_slots, d_rects, d_found, d_objs, d_windows, d_wb_sums, d_wb_out, d_scratch;
 
   // optional per-kernel-class device timing (CUDA events on the launching stream) for bench.py's roofline
@@ -487,13 +493,13 @@ int ensure_tracker_buffers(ht_ctx *ctx) {
   return HT_OK;
 }
 
-int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_t *hist) {
+int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_t *hist, uint16_t *bins) {
   const int n_px = w * h;
   int chunks = 1;
   if (n < 592) chunks = std::min(64, std::max(1, 1184 / n));  // keep ~8 CTAs per SM busy for small batches
   if (chunks > 1) CK(cudaMemsetAsync(hist, 0, (size_t)n * 4096 * sizeof(uint32_t), ctx->stream));
   ctx->prof_begin(HT_PROF_HIST);
-  k_hist<<<dim3(chunks, n), 256, 0, ctx->stream>>>(d_rgba, (size_t)n_px * 4, n_px, hist, chunks);
+  k_hist<<<dim3(chunks, n), 256, 0, ctx->stream>>>(d_rgba, (size_t)n_px * 4, n_px, hist, bins, chunks);
   ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
@@ -597,10 +603,11 @@ int run_track_from_detect(ht_ctx *ctx, const uint8_t *d_rgba_batch, int w, int h
   ctx->prof_end();
   ctx->launches += 2;
   if (n_calls > 0) {
-    int rc = launch_hist(ctx, d_rgba, n, w, h, ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096);
+    uint16_t *bins = ctx->bins.as<uint16_t>() + (size_t)f0 * w * h;
+    int rc = launch_hist(ctx, d_rgba, n, w, h, ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096, bins);
     if (rc != HT_OK) return rc;
     ctx->prof_begin(HT_PROF_TRACK);
-    k_track<<<n, 256, 0, st>>>(d_rgba, (size_t)w * h * 4, w, h, nullptr, ctx->model_hist.as<uint32_t>() + (size_t)f0 * 4096,
+    k_track<<<n * TRACK_CLUSTER, 256, 0, st>>>(bins, w, h, nullptr, ctx->model_hist.as<uint32_t>() + (size_t)f0 * 4096,
                                ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096, ctx->track_state.as<TrackState>() + f0,
                                n_calls, d_objs + 6 * (size_t)f0, d_win ? d_win + 4 * (size_t)f0 : nullptr,
                                ctx->d_flags.as<int32_t>() + 2, ctx->d_flags.as<unsigned long long>() + 8);
@@ -685,7 +692,7 @@ void ht_destroy(ht_ctx *ctx) {
   for (auto &kv : ctx->plans) kv.second->dev.release();
   DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
                     &ctx->labels, &ctx->seq2, &ctx->d_out_rects, &ctx->d_out_counts, &ctx->d_flags, &ctx->model_hist,
-                    &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
+                    &ctx->bins, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
                     &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
   for (DevBuf *b : bufs) b->release();
   for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -811,13 +818,14 @@ int ht_track(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int 
   const int32_t *d_slots = nullptr;
   rc = upload_slots(ctx, slots, n, &d_slots);
   if (rc != HT_OK) return rc;
-  rc = launch_hist(ctx, d_rgba, n, w, h, ctx->cur_hist.as<uint32_t>());   // camshift.js:268
+  CK(ctx->bins.reserve((size_t)n * w * h * sizeof(uint16_t)));
+  rc = launch_hist(ctx, d_rgba, n, w, h, ctx->cur_hist.as<uint32_t>(), ctx->bins.as<uint16_t>());   // camshift.js:268
   if (rc != HT_OK) return rc;
   const bool objs_dev = is_device_ptr(out_objs), win_dev = out_windows && is_device_ptr(out_windows);
   int32_t *d_objs = objs_dev ? reinterpret_cast<int32_t *>(out_objs) : ctx->d_objs.as<int32_t>();
   int32_t *d_win = out_windows ? (win_dev ? reinterpret_cast<int32_t *>(out_windows) : ctx->d_windows.as<int32_t>()) : nullptr;
   ctx->prof_begin(HT_PROF_TRACK);
-  k_track<<<n, 256, 0, ctx->stream>>>(d_rgba, (size_t)w * h * 4, w, h, d_slots, ctx->model_hist.as<uint32_t>(),
+  k_track<<<n * TRACK_CLUSTER, 256, 0, ctx->stream>>>(ctx->bins.as<uint16_t>(), w, h, d_slots, ctx->model_hist.as<uint32_t>(),
                                       ctx->cur_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), n_calls, d_objs,
                                       d_win, ctx->d_flags.as<int32_t>() + 1, ctx->d_flags.as<unsigned long long>() + 8);
   ctx->prof_end();
@@ -844,6 +852,7 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   rc = ensure_tracker_buffers(ctx);
   if (rc != HT_OK) return rc;
   CK(ctx->arena.reserve(P->arena_stride * (size_t)n));
+  if (n_calls > 0) CK(ctx->bins.reserve((size_t)n * w * h * sizeof(uint16_t)));
   cudaStream_t st = ctx->stream;
   const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
   const bool found_dev = out_found && is_device_ptr(out_found), objs_dev = is_device_ptr(out_objs);
@@ -918,7 +927,7 @@ int ht_backprojection(ht_ctx *ctx, int slot, const uint8_t *rgba, int w, int h, 
   const size_t bytes = (size_t)w * h * 4;
   CK(ctx->d_scratch.reserve(bytes + 4096 * sizeof(uint32_t)));
   uint32_t *hist = reinterpret_cast<uint32_t *>(ctx->d_scratch.as<uint8_t>() + bytes);
-  rc = launch_hist(ctx, d_rgba, 1, w, h, hist);
+  rc = launch_hist(ctx, d_rgba, 1, w, h, hist, nullptr);
   if (rc != HT_OK) return rc;
   const bool out_dev = is_device_ptr(out_rgba);
   uint8_t *d_out = out_dev ? out_rgba : ctx->d_scratch.as<uint8_t>();

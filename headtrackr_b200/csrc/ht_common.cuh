@@ -48,22 +48,27 @@ struct DevPlane {
 };
 
 // one canvas-shim drawImage(src, sx,sy,sw,sh, 0,0,dw,dh) producing plane `dst` (oracle/ht_oracle.h)
-struct DevJob {
-  int32_t src, dst;
+struct alignas(16) DevJob {   // 64 B, read by k_resample as four 16 B vectors (field order matters)
+  uint32_t src_off, dst_off;  // plane byte offsets inside the per-frame arena
+  int32_t src_pitch, dst_pitch;
+  int32_t dst_h;
   int32_t dw, dh;             // painted destination size; the rest of the plane is 0
-  uint32_t col_off, row_off;  // first entry of the tap tables
+  uint32_t col_off;           // first entry of the column tap table (even)
+  uint32_t row_off;           // first entry of the row tap table
   uint32_t magic, shift;      // floor(n / (4 dw dh)) == (uint64(n) * magic) >> shift   for n <= 255.5 * 4 dw dh
   uint32_t half;              // 2 dw dh (round half up)
-  uint32_t pad_;
+  int32_t src, dst;           // plane ids (host bookkeeping)
+  uint32_t pad_[2];
 };
+static_assert(sizeof(DevJob) == 64, "DevJob is four 16-byte loads");
 
 // bilinear taps for one destination column (or row): source indices a,b (already clamped and
 // offset by sx/sy) and the numerator f of the fractional weight, 0 <= f < 2*dw (2*dh).
-struct TapEnt {
+struct alignas(8) TapEnt {
   uint16_t a, b, f, pad_;
 };
 
-struct DevPyrTile {  // 8 rows x 128 columns of a destination plane
+struct alignas(8) DevPyrTile {  // 8 rows x 128 columns of a destination plane
   uint16_t job, tx, ty, pad_;
 };
 

@@ -52,36 +52,48 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
 // complete).  Block = 8 rows x 128 columns of one destination plane; thread = 4 adjacent pixels.
 __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8_t *__restrict__ arena,
                                                   size_t arena_stride) {
-  const DevPyrTile tl = plan.pyr_tiles[tile0 + blockIdx.x];
-  const DevJob job = plan.jobs[tl.job];
-  const DevPlane dp = plan.planes[job.dst];
-  const DevPlane sp = plan.planes[job.src];
+  // per-block metadata: one 8 B tile record and one 64 B job record, fetched with vector loads
+  const uint2 tl = __ldg(reinterpret_cast<const uint2 *>(plan.pyr_tiles + tile0 + blockIdx.x));
+  const int job_id = (int)(tl.x & 0xffffu), tx = (int)(tl.x >> 16), ty = (int)(tl.y & 0xffffu);
+  const uint4 *jp = reinterpret_cast<const uint4 *>(plan.jobs + job_id);
+  const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1), j2 = __ldg(jp + 2), j3 = __ldg(jp + 3);
+  // DevJob: {src_off, dst_off, src_pitch, dst_pitch} {dst_h, dw, dh, col_off} {row_off, magic, shift, half} {..}
+  const uint32_t src_off = j0.x, dst_off = j0.y;
+  const int src_pitch = (int)j0.z, dst_pitch = (int)j0.w;
+  const int dst_h = (int)j1.x, dw = (int)j1.y, dh = (int)j1.z;
+  const uint32_t col_off = j1.w, row_off = j2.x, magic = j2.y, shift = j2.z, half = j2.w;
+  (void)j3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Y = tl.ty * 8 + warp;
-  const int X = tl.tx * 128 + lane * 4;
-  if (Y >= dp.h || X >= dp.pitch) return;
+  const int Y = ty * 8 + warp;
+  const int X = tx * 128 + lane * 4;
+  if (Y >= dst_h || X >= dst_pitch) return;
   uint8_t *frame = arena + (size_t)blockIdx.y * arena_stride;
   uint32_t out = 0;
-  if (Y < job.dh && X < job.dw) {
-    const TapEnt ry = plan.taps[job.row_off + Y];
-    const uint8_t *ra = frame + sp.off + (size_t)ry.a * sp.pitch;
-    const uint8_t *rb = frame + sp.off + (size_t)ry.b * sp.pitch;
-    const uint32_t Dx = 2u * (uint32_t)job.dw, Dy = 2u * (uint32_t)job.dh;
-    const uint32_t wy1 = ry.f, wy0 = Dy - ry.f;
+  if (Y < dh && X < dw) {
+    const uint2 ry = __ldg(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // {a | b<<16, f}
+    const uint8_t *ra = frame + src_off + (size_t)(ry.x & 0xffffu) * src_pitch;
+    const uint8_t *rb = frame + src_off + (size_t)(ry.x >> 16) * src_pitch;
+    const uint32_t Dx = 2u * (uint32_t)dw, Dy = 2u * (uint32_t)dh;
+    const uint32_t wy1 = ry.y & 0xffffu, wy0 = Dy - wy1;
+    // 4 column taps = 32 B, 16 B aligned (col_off is even, X % 4 == 0); entries past dw are padding
+    const uint4 *cp = reinterpret_cast<const uint4 *>(plan.taps + col_off + X);
+    const uint4 c01 = __ldg(cp), c23 = __ldg(cp + 1);
+    const uint32_t cab[4] = {c01.x, c01.z, c23.x, c23.z};
+    const uint32_t cf[4] = {c01.y & 0xffffu, c01.w & 0xffffu, c23.y & 0xffffu, c23.w & 0xffffu};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (X + i < job.dw) {
-        const TapEnt cx = plan.taps[job.col_off + X + i];
-        const uint32_t wx1 = cx.f, wx0 = Dx - cx.f;
-        const uint32_t top = wx0 * ra[cx.a] + wx1 * ra[cx.b];   // <= 255 * 2dw
-        const uint32_t bot = wx0 * rb[cx.a] + wx1 * rb[cx.b];
-        const uint32_t num = top * wy0 + bot * wy1 + job.half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
-        const uint32_t q = (uint32_t)(((uint64_t)num * job.magic) >> job.shift);
+      if (X + i < dw) {
+        const uint32_t xa = cab[i] & 0xffffu, xb = cab[i] >> 16;
+        const uint32_t wx1 = cf[i], wx0 = Dx - wx1;
+        const uint32_t top = wx0 * ra[xa] + wx1 * ra[xb];   // <= 255 * 2dw
+        const uint32_t bot = wx0 * rb[xa] + wx1 * rb[xb];
+        const uint32_t num = top * wy0 + bot * wy1 + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
+        const uint32_t q = (uint32_t)(((uint64_t)num * magic) >> shift);
         out |= q << (8 * i);
       }
     }
   }
-  *reinterpret_cast<uint32_t *>(frame + dp.off + (size_t)Y * dp.pitch + X) = out;
+  *reinterpret_cast<uint32_t *>(frame + dst_off + (size_t)Y * dst_pitch + X) = out;
 }
 
 // ------------------------------------------------------------------------------------------------

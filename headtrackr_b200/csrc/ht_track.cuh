@@ -6,6 +6,8 @@
 // inside the search window, so a track() costs one streaming histogram pass over the frame plus a
 // few window passes that stay in L2.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ht_common.cuh"
 
 namespace ht {
@@ -15,17 +17,33 @@ __device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:6
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1'  4096-bin RGB histogram of whole frames — src/camshift.js:49-72 via :268.
+// K1'  4096-bin RGB histogram of whole frames — src/camshift.js:49-72 via :268 — plus the per-pixel
+// 12-bit bin plane (u16) that k_track's window passes read instead of re-decoding RGBA (half the bytes).
 // grid = (chunks, n_frames).  Shared-memory histogram per CTA, flushed to hist[frame][4096].
 __global__ void __launch_bounds__(256) k_hist(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_px,
-                                              uint32_t *__restrict__ hist, int chunks) {
+                                              uint32_t *__restrict__ hist, uint16_t *__restrict__ bins, int chunks) {
   __shared__ uint32_t sh[4096];
   for (int i = threadIdx.x; i < 4096; i += 256) sh[i] = 0;
   __syncthreads();
   const uint32_t *px = reinterpret_cast<const uint32_t *>(rgba + (size_t)blockIdx.y * frame_bytes);
-  const int per = (n_px + chunks - 1) / chunks;
-  const int beg = blockIdx.x * per, end = min(n_px, beg + per);
-  for (int i = beg + threadIdx.x; i < end; i += 256) atomicAdd(&sh[rgb_bin(__ldg(px + i))], 1u);
+  uint16_t *bout = bins ? bins + (size_t)blockIdx.y * n_px : nullptr;
+  const int n_pair = (n_px + 1) / 2;
+  const int per = (n_pair + chunks - 1) / chunks;
+  const int beg = blockIdx.x * per, end = min(n_pair, beg + per);
+  for (int i = beg + threadIdx.x; i < end; i += 256) {
+    const int p0 = 2 * i;
+    if (p0 + 1 < n_px) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2 *>(px + p0));
+      const uint32_t b0 = rgb_bin(v.x), b1 = rgb_bin(v.y);
+      atomicAdd(&sh[b0], 1u);
+      atomicAdd(&sh[b1], 1u);
+      if (bout) *reinterpret_cast<uint32_t *>(bout + p0) = b0 | (b1 << 16);
+    } else {
+      const uint32_t b0 = rgb_bin(__ldg(px + p0));
+      atomicAdd(&sh[b0], 1u);
+      if (bout) bout[p0] = (uint16_t)b0;
+    }
+  }
   __syncthreads();
   uint32_t *out = hist + (size_t)blockIdx.y * 4096;
   if (chunks == 1) {
@@ -124,13 +142,13 @@ __device__ __forceinline__ bool trunc_ambiguous(double v) {
 
 // Moments in the reference's exact order (x outer, y inner, one accumulator each) —
 // src/camshift.js:90-107.  Used by one thread only when a truncation decision is ambiguous.
-__device__ __noinline__ Mom moments_serial(const uint32_t *__restrict__ px, int W, int x, int y, int w, int h,
+__device__ __noinline__ Mom moments_serial(const uint16_t *__restrict__ px, int W, int x, int y, int w, int h,
                                            const double *__restrict__ wsm) {
   Mom m = {0, 0, 0, 0, 0, 0};
   for (int i = x; i < w; ++i) {
     const double vx = (double)(i - x);
     for (int j = y; j < h; ++j) {
-      const double val = wsm[rgb_bin(px[(size_t)j * W + i])];
+      const double val = wsm[px[(size_t)j * W + i]];
       const double vy = (double)(j - y);
       m.m00 += val;
       m.m01 += vy * val;
@@ -149,23 +167,60 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba, size_t frame_bytes, int W, int H,
-                                               const int32_t *__restrict__ slots,
-                                               const uint32_t *__restrict__ model_hist,
-                                               const uint32_t *__restrict__ cur_hist, TrackState *__restrict__ state,
-                                               int n_calls, int32_t *__restrict__ out_objs /* 6 x i32 per frame */,
-                                               int32_t *__restrict__ out_windows, int32_t *__restrict__ err_flag,
-                                               unsigned long long *__restrict__ stats) {
+// One thread-block CLUSTER per slot: TRACK_CLUSTER CTAs split the rows of every window pass and
+// combine their partial moments through distributed shared memory.  Mean-shift is a serial chain
+// of passes per stream (up to 10 per track() call); spreading one pass over several SMs shortens
+// the chain of the streams with large windows, which otherwise set the kernel's duration.
+constexpr int TRACK_CLUSTER = 4;
+
+__device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, const double *__restrict__ wsm, int lane,
+                                            int wx, int xbeg, int xend, bool vec4, double &r0, double &r1, double &r2) {
+  if (vec4) {
+    for (int x4 = xbeg + 4 * lane; x4 < xend; x4 += 128) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row + x4));
+      const uint32_t b[4] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = x4 + i;
+        const double val = (x >= wx && x < xend) ? wsm[b[i]] : 0.0;   // +0.0 terms leave the sums unchanged
+        const double vx = (double)(x - wx);
+        r0 += val;
+        r1 += vx * val;
+        r2 += (vx * vx) * val;
+      }
+    }
+  } else {
+    for (int x = wx + lane; x < xend; x += 32) {
+      const double val = wsm[row[x]];
+      const double vx = (double)(x - wx);
+      r0 += val;
+      r1 += vx * val;
+      r2 += (vx * vx) * val;
+    }
+  }
+}
+
+__global__ void __cluster_dims__(TRACK_CLUSTER, 1, 1) __launch_bounds__(256, 4)
+k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restrict__ slots,
+        const uint32_t *__restrict__ model_hist, const uint32_t *__restrict__ cur_hist, TrackState *__restrict__ state,
+        int n_calls, int32_t *__restrict__ out_objs /* 6 x i32 per frame */, int32_t *__restrict__ out_windows,
+        int32_t *__restrict__ err_flag, unsigned long long *__restrict__ stats) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double wsm[4096];
   __shared__ double red[8][6];
-  __shared__ int win[4];   // wadx, wady, wadw, wadh
-  __shared__ int ctrl;     // 0 = next iteration, 1 = call finished
-  const int k = blockIdx.x;
+  __shared__ double cpart[TRACK_CLUSTER][6];  // used in rank 0: partial moments of every CTA of the cluster
+  __shared__ int win[4];                      // wadx, wady, wadw, wadh (written by rank 0 into every CTA)
+  __shared__ int ctrl[2];                     // per pass parity: 0 = next iteration, 1 = call finished.  Two slots so the
+                                              // leader's write for pass p+1 cannot race a slow CTA still reading pass p.
+  const int crank = (int)cluster.block_rank();
+  const int k = blockIdx.x / TRACK_CLUSTER;
   const int slot = slots ? slots[k] : k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool leader = (crank == 0 && tid == 0);
   TrackState s = state[slot];
-  if (!s.initialised) {
-    if (tid == 0) {
+  if (!s.initialised) {   // uniform over the cluster
+    if (leader) {
       atomicOr(err_flag, 1);
       int32_t *o = out_objs + 6 * (size_t)k;
       o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0;  // TrackObj() defaults
@@ -173,7 +228,7 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
     }
     return;
   }
-  // getWeights — src/camshift.js:314-330
+  // getWeights — src/camshift.js:314-330 (every CTA keeps its own copy)
   {
     const uint32_t *mh = model_hist + (size_t)slot * 4096, *ch = cur_hist + (size_t)k * 4096;
     for (int i = tid; i < 4096; i += 256) {
@@ -183,37 +238,44 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
       wsm[i] = p;
     }
   }
-  const uint32_t *px = reinterpret_cast<const uint32_t *>(rgba + (size_t)k * frame_bytes);
-  __syncthreads();
+  const uint16_t *px = bins + (size_t)k * W * H;   // 12-bit colour bin of every pixel of this slot's frame (k_hist)
+  const bool vec4 = (W & 3) == 0;
+  double *cpart0 = cluster.map_shared_rank(&cpart[0][0], 0);
+  cluster.sync();  // all CTAs of the cluster are resident before any remote shared-memory access
 
-  unsigned long long st_pass = 0, st_serial = 0, st_px = 0;  // thread 0 only
+  unsigned long long st_pass = 0, st_serial = 0, st_px = 0;  // leader only
+  constexpr int ROW_STRIDE = 8 * TRACK_CLUSTER;
+  int pc = 0;  // pass counter (identical in every thread of the cluster)
   for (int call = 0; call < n_calls; ++call) {
     int prevx = s.sx, prevy = s.sy;                                  // :280-281
     Mom m = {0, 0, 0, 0, 0, 0};
-    for (int it = 0; it < 10; ++it) {                                // :284
-      if (tid == 0) {
-        win[0] = max(s.sx, 0);                                       // :286-289
-        win[1] = max(s.sy, 0);
-        win[2] = min(win[0] + s.sw, W);
-        win[3] = min(win[1] + s.sh, H);
-        ctrl = 0;
-      }
-      __syncthreads();
-      const int wx = win[0], wy = win[1], ww = win[2] - win[0], wh = win[3] - win[1];
-      double a00 = 0, a10 = 0, a01 = 0, a11 = 0, a20 = 0, a02 = 0;
-      for (int yy = warp; yy < wh; yy += 8) {
-        const uint32_t *row = px + (size_t)(wy + yy) * W + wx;
-        const double vy = (double)yy;
-        for (int xx = lane; xx < ww; xx += 32) {
-          const double val = wsm[rgb_bin(__ldg(row + xx))];
-          const double vx = (double)xx;
-          a00 += val;
-          a01 += vy * val;
-          a10 += vx * val;
-          a11 += vx * vy * val;
-          a02 += vy * vy * val;
-          a20 += vx * vx * val;
+    for (int it = 0; it < 10; ++it, ++pc) {                          // :284
+      if (leader) {
+        const int w0 = max(s.sx, 0), w1 = max(s.sy, 0);              // :286-289
+        const int w2 = min(w0 + s.sw, W), w3 = min(w1 + s.sh, H);
+        for (int r = 0; r < TRACK_CLUSTER; ++r) {
+          int *rw = cluster.map_shared_rank(win, r);
+          rw[0] = w0; rw[1] = w1; rw[2] = w2; rw[3] = w3;
+          cluster.map_shared_rank(ctrl, r)[pc & 1] = 0;
         }
+      }
+      cluster.sync();
+      const int wx = win[0], wy = win[1], ww = win[2] - win[0], wh = win[3] - win[1];
+      // Each warp takes rows (two at a time for memory-level parallelism), each lane 4 adjacent pixels
+      // (one 8 B load of 4 bins).  Per row: r0 = sum v, r1 = sum vx v, r2 = sum vx^2 v; the vy factors
+      // are applied once per row.
+      double a00 = 0, a10 = 0, a01 = 0, a11 = 0, a20 = 0, a02 = 0;
+      const int xbeg = wx & ~3, xend = wx + ww;
+      for (int yy = crank * 8 + warp; yy < wh; yy += 2 * ROW_STRIDE) {
+        const int yb = yy + ROW_STRIDE;
+        double r0 = 0, r1 = 0, r2 = 0, q0 = 0, q1 = 0, q2 = 0;
+        row_partial(px + (size_t)(wy + yy) * W, wsm, lane, wx, xbeg, xend, vec4, r0, r1, r2);
+        if (yb < wh) row_partial(px + (size_t)(wy + yb) * W, wsm, lane, wx, xbeg, xend, vec4, q0, q1, q2);
+        const double vy = (double)yy, vyb = (double)yb;
+        a00 += r0; a10 += r1; a20 += r2;
+        a01 += vy * r0; a11 += vy * r1; a02 += (vy * vy) * r0;
+        a00 += q0; a10 += q1; a20 += q2;
+        a01 += vyb * q0; a11 += vyb * q1; a02 += (vyb * vyb) * q0;
       }
       a00 = warp_sum(a00); a10 = warp_sum(a10); a01 = warp_sum(a01);
       a11 = warp_sum(a11); a20 = warp_sum(a20); a02 = warp_sum(a02);
@@ -222,11 +284,17 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
         red[warp][3] = a11; red[warp][4] = a20; red[warp][5] = a02;
       }
       __syncthreads();
-      if (tid == 0) {
+      if (tid < 6) {   // fixed-order sums: run-to-run deterministic
+        double t = 0;
+        for (int w8 = 0; w8 < 8; ++w8) t += red[w8][tid];
+        cpart0[crank * 6 + tid] = t;
+      }
+      cluster.sync();
+      if (leader) {
         m = Mom{0, 0, 0, 0, 0, 0};
-        for (int w8 = 0; w8 < 8; ++w8) {
-          m.m00 += red[w8][0]; m.m10 += red[w8][1]; m.m01 += red[w8][2];
-          m.m11 += red[w8][3]; m.m20 += red[w8][4]; m.m02 += red[w8][5];
+        for (int r = 0; r < TRACK_CLUSTER; ++r) {
+          m.m00 += cpart[r][0]; m.m10 += cpart[r][1]; m.m01 += cpart[r][2];
+          m.m11 += cpart[r][3]; m.m20 += cpart[r][4]; m.m02 += cpart[r][5];
         }
         bool exact = false;
         ++st_pass;
@@ -259,16 +327,16 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
             }
             if (amb) { m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm); ++st_serial; }
           }
-          ctrl = 1;
+          for (int r = 0; r < TRACK_CLUSTER; ++r) cluster.map_shared_rank(ctrl, r)[pc & 1] = 1;
         } else {
           prevx = s.sx;
           prevy = s.sy;
         }
       }
-      __syncthreads();
-      if (ctrl) break;
+      cluster.sync();
+      if (ctrl[pc & 1]) { ++pc; break; }
     }
-    if (tid == 0) {
+    if (leader) {
       s.sx = max(0, min(s.sx, W));                                   // :308-309
       s.sy = max(0, min(s.sy, H));
       // camShift epilogue — src/camshift.js:230-258
@@ -295,9 +363,8 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
       s.sw = (int32_t)floor(1.1 * s.tw);                             // :257-258
       s.sh = (int32_t)floor(1.1 * s.th);
     }
-    __syncthreads();
   }
-  if (tid == 0) {
+  if (leader) {
     if (stats) {
       atomicAdd(&stats[0], st_pass); atomicAdd(&stats[1], st_serial);
       atomicAdd(&stats[2], st_px); atomicAdd(&stats[3], (unsigned long long)n_calls);
@@ -311,6 +378,7 @@ __global__ void __launch_bounds__(256) k_track(const uint8_t *__restrict__ rgba,
       w4[0] = s.sx; w4[1] = s.sy; w4[2] = s.sw; w4[3] = s.sh;
     }
   }
+  cluster.sync();  // no CTA may exit while another one can still address its shared memory
 }
 
 // getBackProjectionImg — src/camshift.js:177-196 (debug path)
