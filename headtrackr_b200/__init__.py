@@ -9,7 +9,23 @@ Host-side mirror of the reference's L1 interface:
 All pixel work runs in libheadtrackr_b200.so (CUDA, C ABI in include/headtrackr_b200.h).
 """
 from . import _lib  # noqa: F401
+from . import camshift, ccv, facetrackr  # noqa: F401
+from .canvas import Canvas, as_pixels  # noqa: F401
 from .context import Context  # noqa: F401
 from .synth import load_cascade_blob  # noqa: F401
 
-__all__ = ["Context", "load_cascade_blob"]
+
+def cascade():
+    """headtrackr.cascade (src/cascade.js:19) as the packed "HTC1" blob the C ABI consumes."""
+    return load_cascade_blob()
+
+
+def getWhitebalance(canvas, context=None):
+    """headtrackr.getWhitebalance(canvas) — src/whitebalance.js:5-29 (average gray of the frame)."""
+    from .runtime import default_context
+    px = as_pixels(canvas)
+    ctx = context or default_context(px.shape[1], px.shape[0])
+    return float(ctx.whitebalance(px)[0])
+
+
+__all__ = ["Context", "Canvas", "load_cascade_blob", "cascade", "getWhitebalance", "ccv", "camshift", "facetrackr"]
