@@ -171,7 +171,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // combine their partial moments through distributed shared memory.  Mean-shift is a serial chain
 // of passes per stream (up to 10 per track() call); spreading one pass over several SMs shortens
 // the chain of the streams with large windows, which otherwise set the kernel's duration.
-constexpr int TRACK_CLUSTER = 4;
+constexpr int TRACK_CLUSTER_MAX = 8;   // the cluster size is a launch-time choice (1, 2, 4 or 8 CTAs per stream)
 
 __device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, const double *__restrict__ wsm, int lane,
                                             int wx, int xbeg, int xend, bool vec4, double &r0, double &r1, double &r2) {
@@ -200,21 +200,31 @@ __device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, co
   }
 }
 
-__global__ void __cluster_dims__(TRACK_CLUSTER, 1, 1) __launch_bounds__(256, 4)
+template <int TRACK_CLUSTER>
+__global__ void __launch_bounds__(256, 3)
 k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restrict__ slots,
         const uint32_t *__restrict__ model_hist, const uint32_t *__restrict__ cur_hist, TrackState *__restrict__ state,
         int n_calls, int32_t *__restrict__ out_objs /* 6 x i32 per frame */, int32_t *__restrict__ out_windows,
-        int32_t *__restrict__ err_flag, unsigned long long *__restrict__ stats) {
+        int32_t *__restrict__ err_flag, unsigned long long *__restrict__ stats,
+        // two-phase scheduling: phase A (one CTA per stream) hands streams whose search window outgrows
+        // `bail_area` to phase B (a cluster per stream) through bail_list/calls_done
+        int bail_area, int32_t *__restrict__ calls_done, int32_t *__restrict__ bail_list,
+        int32_t *__restrict__ bail_count, int use_list) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double wsm[4096];
   __shared__ double red[8][6];
-  __shared__ double cpart[TRACK_CLUSTER][6];  // used in rank 0: partial moments of every CTA of the cluster
-  __shared__ int win[4];                      // wadx, wady, wadw, wadh (written by rank 0 into every CTA)
-  __shared__ int ctrl[2];                     // per pass parity: 0 = next iteration, 1 = call finished.  Two slots so the
-                                              // leader's write for pass p+1 cannot race a slow CTA still reading pass p.
+  __shared__ double cpart[TRACK_CLUSTER_MAX][6];  // used in rank 0: partial moments of every CTA of the cluster
+  __shared__ int win[4];                          // wadx, wady, wadw, wadh (written by rank 0 into every CTA)
+  __shared__ int ctrl;                            // 0 = run another pass over win[], 1 = this stream is finished
   const int crank = (int)cluster.block_rank();
-  const int k = blockIdx.x / TRACK_CLUSTER;
+  int k = blockIdx.x / TRACK_CLUSTER;
+  int call0 = 0;
+  if (use_list) {                                 // phase B: k-th entry of the bail list (uniform over the cluster)
+    if (k >= *bail_count) return;
+    k = bail_list[k];
+    call0 = calls_done[k];
+  }
   const int slot = slots ? slots[k] : k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool leader = (crank == 0 && tid == 0);
@@ -241,144 +251,198 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   const uint16_t *px = bins + (size_t)k * W * H;   // 12-bit colour bin of every pixel of this slot's frame (k_hist)
   const bool vec4 = (W & 3) == 0;
   double *cpart0 = cluster.map_shared_rank(&cpart[0][0], 0);
-  cluster.sync();  // all CTAs of the cluster are resident before any remote shared-memory access
 
-  unsigned long long st_pass = 0, st_serial = 0, st_px = 0;  // leader only
+  // leader-only bookkeeping of the reference's loops (src/camshift.js:213-312)
+  unsigned long long st_pass = 0, st_serial = 0, st_px = 0;
+  int call = call0, it = 0, prevx = s.sx, prevy = s.sy;
+  bool bailed = false;
+  auto publish = [&](int done) {   // leader: next window (or the finish flag) into every CTA of the cluster
+    const int w0 = max(s.sx, 0), w1 = max(s.sy, 0);                // :286-289
+    const int w2 = min(w0 + s.sw, W), w3 = min(w1 + s.sh, H);
+    for (int r = 0; r < TRACK_CLUSTER; ++r) {
+      int *rw = cluster.map_shared_rank(win, r);
+      rw[0] = w0; rw[1] = w1; rw[2] = w2; rw[3] = w3;
+      *cluster.map_shared_rank(&ctrl, r) = done;
+    }
+  };
+  auto start_call = [&]() {        // leader: returns true when the stream stops here (all calls done, or bail-out)
+    if (call >= n_calls) return true;
+    if (bail_area > 0 && (long long)s.sw * (long long)s.sh > (long long)bail_area) { bailed = true; return true; }
+    it = 0; prevx = s.sx; prevy = s.sy;                            // :280-281
+    return false;
+  };
+  if (TRACK_CLUSTER > 1) cluster.sync();  // every CTA is resident before the first remote shared-memory access
+  if (leader) publish(start_call() ? 1 : 0);
+  if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
+
   constexpr int ROW_STRIDE = 8 * TRACK_CLUSTER;
-  int pc = 0;  // pass counter (identical in every thread of the cluster)
-  for (int call = 0; call < n_calls; ++call) {
-    int prevx = s.sx, prevy = s.sy;                                  // :280-281
-    Mom m = {0, 0, 0, 0, 0, 0};
-    for (int it = 0; it < 10; ++it, ++pc) {                          // :284
-      if (leader) {
-        const int w0 = max(s.sx, 0), w1 = max(s.sy, 0);              // :286-289
-        const int w2 = min(w0 + s.sw, W), w3 = min(w1 + s.sh, H);
-        for (int r = 0; r < TRACK_CLUSTER; ++r) {
-          int *rw = cluster.map_shared_rank(win, r);
-          rw[0] = w0; rw[1] = w1; rw[2] = w2; rw[3] = w3;
-          cluster.map_shared_rank(ctrl, r)[pc & 1] = 0;
-        }
-      }
-      cluster.sync();
-      const int wx = win[0], wy = win[1], ww = win[2] - win[0], wh = win[3] - win[1];
-      // Each warp takes rows (two at a time for memory-level parallelism), each lane 4 adjacent pixels
-      // (one 8 B load of 4 bins).  Per row: r0 = sum v, r1 = sum vx v, r2 = sum vx^2 v; the vy factors
-      // are applied once per row.
-      double a00 = 0, a10 = 0, a01 = 0, a11 = 0, a20 = 0, a02 = 0;
-      const int xbeg = wx & ~3, xend = wx + ww;
-      for (int yy = crank * 8 + warp; yy < wh; yy += 2 * ROW_STRIDE) {
-        const int yb = yy + ROW_STRIDE;
-        double r0 = 0, r1 = 0, r2 = 0, q0 = 0, q1 = 0, q2 = 0;
-        row_partial(px + (size_t)(wy + yy) * W, wsm, lane, wx, xbeg, xend, vec4, r0, r1, r2);
-        if (yb < wh) row_partial(px + (size_t)(wy + yb) * W, wsm, lane, wx, xbeg, xend, vec4, q0, q1, q2);
-        const double vy = (double)yy, vyb = (double)yb;
-        a00 += r0; a10 += r1; a20 += r2;
-        a01 += vy * r0; a11 += vy * r1; a02 += (vy * vy) * r0;
-        a00 += q0; a10 += q1; a20 += q2;
-        a01 += vyb * q0; a11 += vyb * q1; a02 += (vyb * vyb) * q0;
-      }
-      a00 = warp_sum(a00); a10 = warp_sum(a10); a01 = warp_sum(a01);
-      a11 = warp_sum(a11); a20 = warp_sum(a20); a02 = warp_sum(a02);
-      if (lane == 0) {
-        red[warp][0] = a00; red[warp][1] = a10; red[warp][2] = a01;
-        red[warp][3] = a11; red[warp][4] = a20; red[warp][5] = a02;
-      }
-      __syncthreads();
-      if (tid < 6) {   // fixed-order sums: run-to-run deterministic
-        double t = 0;
-        for (int w8 = 0; w8 < 8; ++w8) t += red[w8][tid];
-        cpart0[crank * 6 + tid] = t;
-      }
-      cluster.sync();
-      if (leader) {
-        m = Mom{0, 0, 0, 0, 0, 0};
-        for (int r = 0; r < TRACK_CLUSTER; ++r) {
-          m.m00 += cpart[r][0]; m.m10 += cpart[r][1]; m.m01 += cpart[r][2];
-          m.m11 += cpart[r][3]; m.m20 += cpart[r][4]; m.m02 += cpart[r][5];
-        }
-        bool exact = false;
-        ++st_pass;
-        st_px += (unsigned long long)(max(ww, 0)) * (unsigned long long)(max(wh, 0));
-        double inv = 1.0 / m.m00;                                    // :109-111
-        double vxf = m.m10 * inv - s.sw / 2.0, vyf = m.m01 * inv - s.sh / 2.0;
-        if (trunc_ambiguous(vxf) || trunc_ambiguous(vyf)) {
-          m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm);
-          exact = true;
-          ++st_serial;
-          inv = 1.0 / m.m00;
-          vxf = m.m10 * inv - s.sw / 2.0;
-          vyf = m.m01 * inv - s.sh / 2.0;
-        }
-        s.sx += js_to_int32(vxf);                                    // :295-296
-        s.sy += js_to_int32(vyf);
-        const bool conv = (s.sx == prevx && s.sy == prevy);         // :299
-        if (conv || it == 9) {
-          // final moments (second == true) are those of this window; make the <<2 truncations safe
-          if (!exact) {
-            const double xc = m.m10 * inv, yc = m.m01 * inv;
-            const double a = (m.m20 - m.m10 * xc) * inv, c = (m.m02 - m.m01 * yc) * inv;
-            bool amb;
-            if (s.calc_angles) {
-              const double b = (m.m11 - m.m01 * xc) * inv, d = a + c;
-              const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
-              amb = trunc_ambiguous(sqrt((d - e) * 0.5)) || trunc_ambiguous(sqrt((d + e) * 0.5));
-            } else {
-              amb = trunc_ambiguous(sqrt(a)) || trunc_ambiguous(sqrt(c));
+  while (!ctrl) {
+    const int wx = win[0], wy = win[1], ww = win[2] - win[0], wh = win[3] - win[1];
+    // Each lane reads 4 adjacent pixels (one 8 B load of 4 colour bins).  Per row: r0 = sum v,
+    // r1 = sum vx v, r2 = sum vx^2 v; the vy factors are applied once per row.  Rows are assigned by
+    // ABSOLUTE frame row (a CTA keeps hitting its own L1 lines when the window shifts between passes) and
+    // processed four at a time: four loads in flight feeding 12 independent accumulation chains.
+    double a00 = 0, a10 = 0, a01 = 0, a11 = 0, a20 = 0, a02 = 0;
+    const int xbeg = wx & ~3, xend = wx + ww;
+    {
+      const int mine = crank * 8 + warp;                        // rows with (wy+yy) % ROW_STRIDE == mine
+      int yy = (mine - (wy % ROW_STRIDE) + ROW_STRIDE) % ROW_STRIDE;
+      for (; yy < wh; yy += 4 * ROW_STRIDE) {
+        double r[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j][0] = r[j][1] = r[j][2] = 0.0;
+        if (vec4) {
+          for (int x4 = xbeg + 4 * lane; x4 < xend; x4 += 128) {
+            uint2 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int y = yy + j * ROW_STRIDE;
+              v[j] = (y < wh) ? __ldg(reinterpret_cast<const uint2 *>(px + (size_t)(wy + y) * W + x4)) : make_uint2(0, 0);
             }
-            if (amb) { m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm); ++st_serial; }
+            double vx[4], vx2[4];
+            bool in[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int x = x4 + i;
+              in[i] = (x >= wx && x < xend);
+              vx[i] = (double)(x - wx);
+              vx2[i] = vx[i] * vx[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool rowok = (yy + j * ROW_STRIDE) < wh;
+              const uint32_t b[4] = {v[j].x & 0xffffu, v[j].x >> 16, v[j].y & 0xffffu, v[j].y >> 16};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const double val = (in[i] && rowok) ? wsm[b[i]] : 0.0;   // +0.0 terms leave the sums unchanged
+                r[j][0] += val;
+                r[j][1] += vx[i] * val;
+                r[j][2] += vx2[i] * val;
+              }
+            }
           }
-          for (int r = 0; r < TRACK_CLUSTER; ++r) cluster.map_shared_rank(ctrl, r)[pc & 1] = 1;
         } else {
-          prevx = s.sx;
-          prevy = s.sy;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int y = yy + j * ROW_STRIDE;
+            if (y < wh) row_partial(px + (size_t)(wy + y) * W, wsm, lane, wx, xbeg, xend, false, r[j][0], r[j][1], r[j][2]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double vy = (double)(yy + j * ROW_STRIDE);
+          a00 += r[j][0]; a10 += r[j][1]; a20 += r[j][2];
+          a01 += vy * r[j][0]; a11 += vy * r[j][1]; a02 += (vy * vy) * r[j][0];
         }
       }
-      cluster.sync();
-      if (ctrl[pc & 1]) { ++pc; break; }
     }
+    a00 = warp_sum(a00); a10 = warp_sum(a10); a01 = warp_sum(a01);
+    a11 = warp_sum(a11); a20 = warp_sum(a20); a02 = warp_sum(a02);
+    if (lane == 0) {
+      red[warp][0] = a00; red[warp][1] = a10; red[warp][2] = a01;
+      red[warp][3] = a11; red[warp][4] = a20; red[warp][5] = a02;
+    }
+    __syncthreads();
+    if (tid < 6) {   // fixed-order sums: run-to-run deterministic
+      double t = 0;
+      for (int w8 = 0; w8 < 8; ++w8) t += red[w8][tid];
+      cpart0[crank * 6 + tid] = t;
+    }
+    if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
     if (leader) {
-      s.sx = max(0, min(s.sx, W));                                   // :308-309
-      s.sy = max(0, min(s.sy, H));
-      // camShift epilogue — src/camshift.js:230-258
-      const double invM00 = 1.0 / m.m00;
-      const double xc = m.m10 * invM00, yc = m.m01 * invM00;
-      const double mu20 = m.m20 - m.m10 * xc, mu02 = m.m02 - m.m01 * yc, mu11 = m.m11 - m.m01 * xc;
-      const double a = mu20 * invM00, c = mu02 * invM00;
-      if (s.calc_angles) {
-        const double b = mu11 * invM00;
-        const double d = a + c;
-        const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
-        s.tw = (int32_t)((uint32_t)js_to_int32(sqrt((d - e) * 0.5)) << 2);
-        s.th = (int32_t)((uint32_t)js_to_int32(sqrt((d + e) * 0.5)) << 2);
-        double ang = atan2(2 * b, a - c + e);
-        if (ang < 0) ang = ang + 3.141592653589793;
-        s.angle = ang;
-      } else {
-        s.tw = (int32_t)((uint32_t)js_to_int32(sqrt(a)) << 2);
-        s.th = (int32_t)((uint32_t)js_to_int32(sqrt(c)) << 2);
-        s.angle = 3.141592653589793 / 2;
+      Mom m = {0, 0, 0, 0, 0, 0};
+      for (int r = 0; r < TRACK_CLUSTER; ++r) {
+        m.m00 += cpart[r][0]; m.m10 += cpart[r][1]; m.m01 += cpart[r][2];
+        m.m11 += cpart[r][3]; m.m20 += cpart[r][4]; m.m02 += cpart[r][5];
       }
-      s.tx = (int32_t)floor(fmax(0.0, fmin(s.sx + s.sw / 2.0, (double)W)));   // :253-254
-      s.ty = (int32_t)floor(fmax(0.0, fmin(s.sy + s.sh / 2.0, (double)H)));
-      s.sw = (int32_t)floor(1.1 * s.tw);                             // :257-258
-      s.sh = (int32_t)floor(1.1 * s.th);
+      bool exact = false;
+      ++st_pass;
+      st_px += (unsigned long long)(max(ww, 0)) * (unsigned long long)(max(wh, 0));
+      double inv = 1.0 / m.m00;                                    // :109-111
+      double vxf = m.m10 * inv - s.sw / 2.0, vyf = m.m01 * inv - s.sh / 2.0;
+      if (trunc_ambiguous(vxf) || trunc_ambiguous(vyf)) {
+        m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm);
+        exact = true;
+        ++st_serial;
+        inv = 1.0 / m.m00;
+        vxf = m.m10 * inv - s.sw / 2.0;
+        vyf = m.m01 * inv - s.sh / 2.0;
+      }
+      s.sx += js_to_int32(vxf);                                    // :295-296
+      s.sy += js_to_int32(vyf);
+      const bool conv = (s.sx == prevx && s.sy == prevy);         // :299
+      bool done = false;
+      if (conv || it == 9) {
+        // final moments (second == true) are those of this window; make the <<2 truncations safe
+        if (!exact) {
+          const double xc = m.m10 * inv, yc = m.m01 * inv;
+          const double a = (m.m20 - m.m10 * xc) * inv, c = (m.m02 - m.m01 * yc) * inv;
+          bool amb;
+          if (s.calc_angles) {
+            const double b = (m.m11 - m.m01 * xc) * inv, d = a + c;
+            const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
+            amb = trunc_ambiguous(sqrt((d - e) * 0.5)) || trunc_ambiguous(sqrt((d + e) * 0.5));
+          } else {
+            amb = trunc_ambiguous(sqrt(a)) || trunc_ambiguous(sqrt(c));
+          }
+          if (amb) { m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm); ++st_serial; }
+        }
+        s.sx = max(0, min(s.sx, W));                                   // :308-309
+        s.sy = max(0, min(s.sy, H));
+        // camShift epilogue — src/camshift.js:230-258
+        const double invM00 = 1.0 / m.m00;
+        const double xc = m.m10 * invM00, yc = m.m01 * invM00;
+        const double mu20 = m.m20 - m.m10 * xc, mu02 = m.m02 - m.m01 * yc, mu11 = m.m11 - m.m01 * xc;
+        const double a = mu20 * invM00, c = mu02 * invM00;
+        if (s.calc_angles) {
+          const double b = mu11 * invM00;
+          const double d = a + c;
+          const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
+          s.tw = (int32_t)((uint32_t)js_to_int32(sqrt((d - e) * 0.5)) << 2);
+          s.th = (int32_t)((uint32_t)js_to_int32(sqrt((d + e) * 0.5)) << 2);
+          double ang = atan2(2 * b, a - c + e);
+          if (ang < 0) ang = ang + 3.141592653589793;
+          s.angle = ang;
+        } else {
+          s.tw = (int32_t)((uint32_t)js_to_int32(sqrt(a)) << 2);
+          s.th = (int32_t)((uint32_t)js_to_int32(sqrt(c)) << 2);
+          s.angle = 3.141592653589793 / 2;
+        }
+        s.tx = (int32_t)floor(fmax(0.0, fmin(s.sx + s.sw / 2.0, (double)W)));   // :253-254
+        s.ty = (int32_t)floor(fmax(0.0, fmin(s.sy + s.sh / 2.0, (double)H)));
+        s.sw = (int32_t)floor(1.1 * s.tw);                             // :257-258
+        s.sh = (int32_t)floor(1.1 * s.th);
+        ++call;
+        done = start_call();
+      } else {
+        prevx = s.sx;
+        prevy = s.sy;
+        ++it;
+      }
+      publish(done ? 1 : 0);
     }
+    if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
   }
   if (leader) {
     if (stats) {
       atomicAdd(&stats[0], st_pass); atomicAdd(&stats[1], st_serial);
-      atomicAdd(&stats[2], st_px); atomicAdd(&stats[3], (unsigned long long)n_calls);
+      atomicAdd(&stats[2], st_px); atomicAdd(&stats[3], (unsigned long long)(call - call0));
     }
     state[slot] = s;
-    int32_t *o = out_objs + 6 * (size_t)k;
-    o[0] = s.tx; o[1] = s.ty; o[2] = s.tw; o[3] = s.th;
-    *reinterpret_cast<double *>(o + 4) = s.angle;
-    if (out_windows) {
-      int32_t *w4 = out_windows + 4 * (size_t)k;
-      w4[0] = s.sx; w4[1] = s.sy; w4[2] = s.sw; w4[3] = s.sh;
+    if (bailed) {   // phase B continues this stream from call `call`
+      calls_done[k] = call;
+      bail_list[atomicAdd(bail_count, 1)] = k;
+    } else {
+      int32_t *o = out_objs + 6 * (size_t)k;
+      o[0] = s.tx; o[1] = s.ty; o[2] = s.tw; o[3] = s.th;
+      *reinterpret_cast<double *>(o + 4) = s.angle;
+      if (out_windows) {
+        int32_t *w4 = out_windows + 4 * (size_t)k;
+        w4[0] = s.sx; w4[1] = s.sy; w4[2] = s.sw; w4[3] = s.sh;
+      }
     }
   }
-  cluster.sync();  // no CTA may exit while another one can still address its shared memory
+  if (TRACK_CLUSTER > 1) cluster.sync();  // no CTA may exit while another one can still address its shared memory
 }
 
 // getBackProjectionImg — src/camshift.js:177-196 (debug path)
