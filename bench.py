@@ -100,20 +100,10 @@ class ClockSampler:
 def cpu_step(frames, blob, track_calls, threads):
     import oracle
 
-    def one(i):
-        f = frames[i]
-        res = oracle.detect(f, blob, 5, 1)
-        if track_calls > 0 and res:
-            cand = res[0]
-            for r in res[1:]:
-                if r[4] > cand[4]:
-                    cand = r
-            if cand[4] > -10:
-                t = oracle.CamshiftTracker(calc_angles=False)
-                t.init_tracker(f, *[int(np.floor(v)) for v in cand[:4]])
-                for _ in range(track_calls):
-                    t.track(f)
-        return len(res)
+    def one(i):   # one C call per frame (the GIL is released for its whole duration)
+        if track_calls > 0:
+            return oracle.detect_track(frames[i], blob, 5, 1, False, track_calls)[0]
+        return len(oracle.detect(frames[i], blob, 5, 1))
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:   # ctypes releases the GIL inside the C oracle

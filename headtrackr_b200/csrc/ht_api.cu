@@ -964,9 +964,11 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
       CK(cudaStreamWaitEvent(st, ctx->chunk_events[c], 0));
       rc = run_detect(ctx, P, d_frames, f0, nf, min_neighbors, d_rects, d_counts);
       if (rc != HT_OK) return rc;
-      rc = run_track_from_detect(ctx, d_frames, w, h, f0, nf, d_rects, d_counts, calc_angles, n_calls, d_found, d_objs, d_win);
-      if (rc != HT_OK) return rc;
     }
+    // Tracking runs once over the whole batch: mean-shift is a serial chain per stream, so every launch of
+    // k_track costs at least its slowest stream — per-chunk launches would pay that tail once per chunk.
+    rc = run_track_from_detect(ctx, d_frames, w, h, 0, n, d_rects, d_counts, calc_angles, n_calls, d_found, d_objs, d_win);
+    if (rc != HT_OK) return rc;
   }
   ctx->last_plan = P;
   ctx->last_n = n;

@@ -113,12 +113,20 @@ __constant__ ConstCascade c_casc;
 __host__ __device__ constexpr unsigned gen_off(int z, int x, int y) {
   return z == 0 ? (unsigned)(y * TP + x) : z == 1 ? (unsigned)(REGION + TP + 2 * x + 2 * y * TP) : (unsigned)(REGION + 4 * x + 4 * y * TP);
 }
+// sum += (pmin > nmax) ? alpha[2k+1] : alpha[2k]  with alpha[2k] == -alpha[2k+1] (src/ccv.js:194,219):
+// add `a` with its sign bit flipped unless pm > nm.  d = nm - pm is negative exactly when the feature
+// fires, so the flip mask is ~d & 0x80000000 — one IADD + one LOP3 instead of a compare and two selects.
+__device__ __forceinline__ double bbf_accumulate(double s, unsigned pm, unsigned nm, double a) {
+  const int d = (int)nm - (int)pm;
+  const int hi = __double2hiint(a) ^ (~d & (int)0x80000000);
+  return s + __hiloint2double(hi, __double2loint(a));
+}
 #define HT_W(z, x, y) ((unsigned)win[gen_off(z, x, y)])
-#define HT_MIN2(a, b) min(a, b)
-#define HT_MIN3(a, b, c) min(min(a, b), c)
-#define HT_MAX2(a, b) max(a, b)
-#define HT_MAX3(a, b, c) max(max(a, b), c)
-#define HT_ALPHA(k) (c_casc.alpha[k])
+#define HT_MIN2(a, b) __vimin3_u32(a, b, b)      /* VIMNMX3.U32 (plain min() is turned into U16x2 + masks) */
+#define HT_MIN3(a, b, c) __vimin3_u32(a, b, c)
+#define HT_MAX2(a, b) __vimax3_u32(a, b, b)
+#define HT_MAX3(a, b, c) __vimax3_u32(a, b, c)
+#define HT_ACC(s, pm, nm, k) bbf_accumulate(s, pm, nm, c_casc.alpha[k])
 #define HT_THRESHOLD(j) (c_casc.stage[j].threshold)
 #include "cascade_face_gen.inc"
 #undef HT_W
@@ -126,7 +134,7 @@ __host__ __device__ constexpr unsigned gen_off(int z, int x, int y) {
 #undef HT_MIN3
 #undef HT_MAX2
 #undef HT_MAX3
-#undef HT_ALPHA
+#undef HT_ACC
 #undef HT_THRESHOLD
 
 __device__ __forceinline__ unsigned ldpx(const uint8_t *__restrict__ win, unsigned off) { return win[off]; }
@@ -160,8 +168,7 @@ __device__ __forceinline__ bool stage_pass(const uint8_t *__restrict__ win, int 
         }
       }
     }
-    const double a = c_casc.alpha[k];
-    sum += (pmin > nmax) ? a : -a;   // src/ccv.js:194,219 (alpha[2k] == -alpha[2k+1])
+    sum = bbf_accumulate(sum, pmin, nmax, c_casc.alpha[k]);   // src/ccv.js:194,219
   }
   sum_out = sum;
   return alive && !(sum < c_casc.stage[j].threshold);  // src/ccv.js:222
@@ -174,8 +181,11 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
                                                               double *__restrict__ raw_conf,
                                                               uint32_t *__restrict__ raw_count, int raw_cap) {
   __shared__ __align__(16) uint8_t tile[2 * REGION];
-  __shared__ uint16_t queue[2][NWIN];
-  __shared__ int qcount[2];
+  __shared__ uint16_t raw[NWIN];   // [slot][class] survivor cells of the group that just ran
+  __shared__ uint16_t cl[NWIN];    // [entry][class] compacted per-bank-class lists
+  __shared__ int cnt[8][32];
+  __shared__ int len_s[32], pre_s[32];
+  __shared__ int maxlen_s, total_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int frame = blockIdx.y;
@@ -224,49 +234,95 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
       d[0] = (uint8_t)v; d[4] = (uint8_t)(v >> 8); d[8] = (uint8_t)(v >> 16); d[12] = (uint8_t)(v >> 24);
     }
   }
-  if (tid < 2) qcount[tid] = 0;
   __syncthreads();
 
   // ---- stage groups ----
-  // eval(win, alive, sum) runs the stages of one group for one window per lane (warp-uniform control flow)
-  int cur = 0;  // queue written by the current group
-  auto run_group = [&](const int g, const bool last, auto eval) {
-    const int n_in = (g == 0) ? NWIN : qcount[cur ^ 1];
-    const int n_iter = (n_in + CASCADE_THREADS - 1) / CASCADE_THREADS;
-    for (int it = 0; it < n_iter; ++it) {
-      const int i = it * CASCADE_THREADS + tid;
-      int wid = 0;
-      bool alive = i < n_in;
-      if (g > 0 && alive) wid = queue[cur ^ 1][i];
-      if (g == 0) wid = i;
-      const int lx = wid & (TW - 1), ly = (wid / TW) & (TH - 1), q = wid / (TW * TH);
-      const int dx = q & 1, dy = q >> 1;
-      if (g == 0) alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh);
-      const uint8_t *win = tile + (4 * lx + 2 * dx) + (4 * ly + 2 * dy) * TP;
-      double sum = 0.0;
-      alive = eval(win, alive, sum);
-      const unsigned m = __ballot_sync(0xffffffffu, alive);
-      if (m) {
-        if (!last) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&qcount[cur], __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (alive) queue[cur][base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
-        } else if (alive) {  // src/ccv.js:227-234: emit (window id in reference order, last stage sum)
-          const uint32_t key = sc.win_base + (uint32_t)((q * sc.qh + (y0 + ly)) * sc.qw + (x0 + lx));
-          const uint32_t pos = atomicAdd(&raw_count[frame], 1u);
-          if (pos < (uint32_t)raw_cap) {
-            raw_keys[(size_t)frame * raw_cap + pos] = key;
-            raw_conf[(size_t)frame * raw_cap + pos] = sum;
-          }
-        }
+  // Survivors of a group are kept in 32 per-BANK-CLASS lists: class(window) = (lx + 16*dy) & 31 is the shared-
+  // memory bank of the window's base a0 (TP = 160: four tile rows are a multiple of 128 B).  Lane L of every warp
+  // only ever evaluates windows of class L, so a warp's 32 pixel loads hit 32 different banks in the compacted
+  // groups too (ballot compaction of arbitrary survivors measured ~2.7 wavefronts per load).
+  //   raw[slot][class] : one writer per cell (window id or 0xFFFF), slot-major so a warp's stores are contiguous
+  //   cl[entry][class] : compacted per-class lists; len_s[class], maxlen_s, pre_s[class] (exclusive scan), total_s
+  const int warp = tid >> 5;
+  auto decode = [&](int wid, int &lx, int &ly, int &q) {
+    lx = wid & (TW - 1); ly = (wid / TW) & (TH - 1); q = wid / (TW * TH);
+    return tile + (4 * lx + 2 * (q & 1)) + (4 * ly + 2 * (q >> 1)) * TP;
+  };
+  auto emit = [&](int lx, int ly, int q, double sum) {  // src/ccv.js:227-234: (window id in reference order, last stage sum)
+    const uint32_t key = sc.win_base + (uint32_t)((q * sc.qh + (y0 + ly)) * sc.qw + (x0 + lx));
+    const uint32_t pos = atomicAdd(&raw_count[frame], 1u);
+    if (pos < (uint32_t)raw_cap) {
+      raw_keys[(size_t)frame * raw_cap + pos] = key;
+      raw_conf[(size_t)frame * raw_cap + pos] = sum;
+    }
+  };
+  // compaction of raw[0..n_slots) into the class lists; every thread calls it
+  auto compact = [&](int n_slots) {
+    __syncthreads();
+    uint16_t v[8];
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int slot = warp * 8 + s;
+      v[s] = (slot < n_slots) ? raw[slot * 32 + lane] : (uint16_t)0xFFFFu;
+      c += (v[s] != 0xFFFFu) ? 1 : 0;
+    }
+    cnt[warp][lane] = c;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) {
+      const int x = cnt[w2][lane];
+      off += (w2 < warp) ? x : 0;
+      tot += x;
+    }
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      if (v[s] != 0xFFFFu) cl[(off++) * 32 + lane] = v[s];
+    if (warp == 0) {
+      len_s[lane] = tot;
+      int mx = tot, incl = tot;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
       }
+      pre_s[lane] = incl - tot;
+      if (lane == 31) total_s = incl;
+      if (lane == 0) maxlen_s = mx;
     }
     __syncthreads();
-    cur ^= 1;
-    if (tid == 0) qcount[cur] = 0;  // the queue two groups back is free again
-    __syncthreads();
-    return last || qcount[cur ^ 1] == 0;  // true: nothing left to do
+  };
+  // dense first group: thread (warp, lane) owns lx = lane; iteration `it` -> q = it >> 1, ly = (it & 1) * 8 + warp
+  auto run_dense = [&](bool emit_here, auto eval) {
+    for (int it = 0; it < NWIN / CASCADE_THREADS; ++it) {
+      const int wid = it * CASCADE_THREADS + tid;
+      int lx, ly, q;
+      const uint8_t *win = decode(wid, lx, ly, q);
+      bool alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh);
+      double sum = 0.0;
+      alive = eval(win, alive, sum);
+      if (emit_here) { if (alive) emit(lx, ly, q, sum); }
+      else raw[(warp * 8 + it) * 32 + ((lane + 16 * (q >> 1)) & 31)] = alive ? (uint16_t)wid : (uint16_t)0xFFFFu;
+    }
+    return NWIN / 32;
+  };
+  // later groups: lane L takes entries warp, warp+8, ... of class L
+  auto run_lists = [&](bool emit_here, auto eval) {
+    const int ml = maxlen_s, mylen = len_s[lane];
+    for (int e = warp; e < ml; e += 8) {
+      bool alive = e < mylen;
+      const int wid = alive ? cl[e * 32 + lane] : 0;
+      int lx, ly, q;
+      const uint8_t *win = decode(wid, lx, ly, q);
+      double sum = 0.0;
+      alive = eval(win, alive, sum);
+      if (emit_here) { if (alive) emit(lx, ly, q, sum); }
+      else raw[e * 32 + lane] = alive ? (uint16_t)wid : (uint16_t)0xFFFFu;
+    }
+    return ml;
   };
   auto table_stages = [&](const int jb, const int je) {
     return [=](const uint8_t *win, bool alive, double &sum) {
@@ -289,25 +345,38 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
     if (__any_sync(0xffffffffu, alive)) alive = gen_stage##B(win, sum) && alive; \
     return alive;                                                           \
   }
-    if (run_group(0, false, HT_GEN_PAIR(0, 1))) return;
-    if (run_group(1, false, HT_GEN_PAIR(2, 3))) return;
-    if (run_group(2, false, HT_GEN_PAIR(4, 5))) return;
+    compact(run_dense(false, HT_GEN_PAIR(0, 1)));
+    if (total_s == 0) return;
+    compact(run_lists(false, HT_GEN_PAIR(2, 3)));
+    if (total_s == 0) return;
+    compact(run_lists(false, HT_GEN_PAIR(4, 5)));
+    if (total_s == 0) return;
 #undef HT_GEN_PAIR
     g = 3;
   }
-  for (; g < c_casc.n_groups; ++g)
-    if (run_group(g, g == c_casc.n_groups - 1 && !has_late,
-                  table_stages(c_casc.group_first[g], c_casc.group_first[g + 1]))) return;
+  for (; g < c_casc.n_groups; ++g) {
+    const bool emit_here = (g == c_casc.n_groups - 1) && !has_late;
+    auto ev = table_stages(c_casc.group_first[g], c_casc.group_first[g + 1]);
+    const int n_slots = (g == 0) ? run_dense(emit_here, ev) : run_lists(emit_here, ev);
+    if (emit_here) return;
+    compact(n_slots);
+    if (total_s == 0) return;
+  }
   if (!has_late) return;
 
   // ---- late stages: one warp per surviving window, one feature per lane, exact integer sums ----
   {
-    const int n_in = qcount[cur ^ 1];
-    const uint16_t *qin = queue[cur ^ 1];
-    for (int w = tid >> 5; w < n_in; w += CASCADE_THREADS / 32) {
-      const int wid = qin[w];
-      const int lx = wid & (TW - 1), ly = (wid / TW) & (TH - 1), q = wid / (TW * TH);
-      const uint8_t *win = tile + (4 * lx + 2 * (q & 1)) + (4 * ly + 2 * (q >> 1)) * TP;
+    // flatten the class lists (raw[] is free again after the last compaction)
+    {
+      const int mylen = len_s[lane], base = pre_s[lane];
+      for (int e = warp; e < mylen; e += 8) raw[base + e] = cl[e * 32 + lane];
+    }
+    __syncthreads();
+    const int n_in = total_s;
+    for (int w = warp; w < n_in; w += CASCADE_THREADS / 32) {
+      const int wid = raw[w];
+      int lx, ly, q;
+      const uint8_t *win = decode(wid, lx, ly, q);
       bool pass = true;
       for (int j = late_first; j < c_casc.n_stages && pass; ++j) {
         const int first = c_casc.stage[j].first, count = c_casc.stage[j].count;
@@ -341,17 +410,10 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
           pass = acc > thr;
         }
       }
-      if (pass) {  // src/ccv.js:227-234; confidence = ordered fp64 sum of the last stage
+      if (pass) {  // confidence = ordered fp64 sum of the last stage
         double s;
         stage_pass(win, c_casc.n_stages - 1, true, s);
-        if (lane == 0) {
-          const uint32_t key = sc.win_base + (uint32_t)((q * sc.qh + (y0 + ly)) * sc.qw + (x0 + lx));
-          const uint32_t pos = atomicAdd(&raw_count[frame], 1u);
-          if (pos < (uint32_t)raw_cap) {
-            raw_keys[(size_t)frame * raw_cap + pos] = key;
-            raw_conf[(size_t)frame * raw_cap + pos] = s;
-          }
-        }
+        if (lane == 0) emit(lx, ly, q, s);
       }
     }
   }

@@ -84,6 +84,8 @@ def lib():
         L.hto_tracker_track.argtypes = [C.POINTER(Tracker), u8p, C.c_int, C.c_int, C.POINTER(TrackTrace)]
         L.hto_backprojection_img.argtypes = [C.POINTER(Tracker), u8p, C.c_int, C.c_int, u8p]
         L.hto_backprojection_img.restype = None
+        L.hto_detect_track.argtypes = [u8p, C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.POINTER(Tracker), C.POINTER(C.c_int)]
         L.hto_whitebalance.argtypes = [u8p, C.c_int, C.c_int]
         L.hto_whitebalance.restype = C.c_double
         _lib = L
@@ -234,6 +236,17 @@ class CamshiftTracker:
         out = np.zeros((H, W, 4), np.uint8)
         lib().hto_backprojection_img(C.byref(self.t), p, W, H, out.ctypes.data_as(C.POINTER(C.c_uint8)))
         return out
+
+
+def detect_track(rgba, blob, interval=5, min_neighbors=1, calc_angles=False, n_calls=30):
+    """One C call: detect, VJ->CS hand-off, n_calls x track().  -> (n_detections, found, track_obj dict)."""
+    rgba, p = _u8(rgba)
+    H, W = rgba.shape[:2]
+    t = Tracker()
+    found = C.c_int()
+    n = lib().hto_detect_track(p, W, H, blob, len(blob), interval, min_neighbors, int(calc_angles), n_calls,
+                               C.byref(t), C.byref(found))
+    return n, found.value, dict(x=t.tx, y=t.ty, width=t.tw, height=t.th, angle=t.angle)
 
 
 def whitebalance(rgba):

@@ -586,6 +586,30 @@ void hto_backprojection_img(const hto_tracker *t, const uint8_t *rgba, int W, in
   free(cur); free(weights);
 }
 
+/* One facetrackr VJ frame followed by its CS frames (src/facetrackr.js:67-126) in a single C call, so that the
+ * CPU baseline can run one frame per host thread without Python in the loop:
+ * detect -> first max-confidence candidate (:157-165) -> confidence > -10 (:97) -> floor (:101-106) ->
+ * initTracker -> n_calls x track().  Returns the number of detections; *found = 1 if a tracker was seeded. */
+int hto_detect_track(const uint8_t *rgba, int W, int H, const void *blob, size_t blob_len, int interval,
+                     int min_neighbors, int calc_angles, int n_calls, hto_tracker *t_out, int *found) {
+  hto_rect res[256];
+  int n = hto_detect(rgba, W, H, blob, blob_len, interval, min_neighbors, res, 256, NULL, 0, NULL);
+  if (found) *found = 0;
+  if (n <= 0) return n;
+  int m = n < 256 ? n : 256, best = 0;
+  for (int i = 1; i < m; ++i)
+    if (res[i].confidence > res[best].confidence) best = i;
+  if (!(res[best].confidence > -10)) return n;
+  hto_tracker t;
+  if (hto_tracker_init(&t, rgba, W, H, (int)floor(res[best].x), (int)floor(res[best].y), (int)floor(res[best].width),
+                       (int)floor(res[best].height), calc_angles) != 0)
+    return n;
+  for (int c = 0; c < n_calls; ++c) hto_tracker_track(&t, rgba, W, H, NULL);
+  if (t_out) *t_out = t;
+  if (found) *found = 1;
+  return n;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* whitebalance — src/whitebalance.js:5-29                                                     */
 

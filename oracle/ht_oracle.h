@@ -126,6 +126,10 @@ int hto_tracker_track(hto_tracker *t, const uint8_t *rgba, int W, int H, hto_tra
 /* src/camshift.js:177-196 : floor(255*w[bin]) gray image (debug getBackProjectionImg) as RGBA */
 void hto_backprojection_img(const hto_tracker *t, const uint8_t *rgba, int W, int H, uint8_t *out_rgba);
 
+/* detect -> VJ->CS hand-off (src/facetrackr.js:97-108,157-165) -> n_calls x track() in one call (CPU baseline) */
+int hto_detect_track(const uint8_t *rgba, int W, int H, const void *blob, size_t blob_len, int interval,
+                     int min_neighbors, int calc_angles, int n_calls, hto_tracker *t_out, int *found);
+
 /* src/whitebalance.js:5-29 */
 double hto_whitebalance(const uint8_t *rgba, int W, int H);
 
