@@ -515,21 +515,21 @@ int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_
 // outgrows bail_area stop and are queued.  Phase B: one 8-CTA cluster per queued stream finishes their calls.
 // Mean-shift is a serial chain of window passes per stream, so the few streams with large windows would
 // otherwise set the duration of the whole launch.
-template <int C>
+template <int C, int NT = 256>
 cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, int h, const int32_t *d_slots,
                            const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
                            int32_t *d_win, int32_t *flag, unsigned long long *stats, int bail_area, int32_t *calls_done,
                            int32_t *bail_list, int32_t *bail_count, int use_list) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)n * C);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_track<C>, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
+  return cudaLaunchKernelEx(&cfg, k_track<C, NT>, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
                             bail_area, calls_done, bail_list, bail_count, use_list);
 }
 
@@ -556,7 +556,9 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
   } else {
     // single phase: many streams -> 4 CTAs per stream (throughput); few streams -> 8 (latency of one stream)
     int c = ctx->track_cluster;
-    if (c <= 0) c = (n >= 64) ? 4 : 8;
+    // measured on 1024 streams x 30 calls: 1 CTA 9.7 ms, 2 CTAs 6.1 ms, 4 CTAs 6.2 ms, 8 CTAs 10.1 ms (512- and
+    // 1024-thread single CTAs: 8.8 ms)
+    if (c <= 0) c = (n >= 256) ? 2 : (n >= 32 ? 4 : 8);
     switch (c) {
       case 1: e = launch_track_c<1>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, bail_list, bail_count, 0); break;
       case 2: e = launch_track_c<2>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, bail_list, bail_count, 0); break;

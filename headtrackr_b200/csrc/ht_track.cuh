@@ -200,8 +200,8 @@ __device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, co
   }
 }
 
-template <int TRACK_CLUSTER>
-__global__ void __launch_bounds__(256, 3)
+template <int TRACK_CLUSTER, int NT>
+__global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : (NT >= 512 ? 2 : 3))
 k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restrict__ slots,
         const uint32_t *__restrict__ model_hist, const uint32_t *__restrict__ cur_hist, TrackState *__restrict__ state,
         int n_calls, int32_t *__restrict__ out_objs /* 6 x i32 per frame */, int32_t *__restrict__ out_windows,
@@ -213,7 +213,8 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double wsm[4096];
-  __shared__ double red[8][6];
+  constexpr int NW = NT / 32;   // warps per CTA
+  __shared__ double red[NW][6];
   __shared__ double cpart[TRACK_CLUSTER_MAX][6];  // used in rank 0: partial moments of every CTA of the cluster
   __shared__ int win[4];                          // wadx, wady, wadw, wadh (written by rank 0 into every CTA)
   __shared__ int ctrl;                            // 0 = run another pass over win[], 1 = this stream is finished
@@ -241,7 +242,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   // getWeights — src/camshift.js:314-330 (every CTA keeps its own copy)
   {
     const uint32_t *mh = model_hist + (size_t)slot * 4096, *ch = cur_hist + (size_t)k * 4096;
-    for (int i = tid; i < 4096; i += 256) {
+    for (int i = tid; i < 4096; i += NT) {
       const uint32_t c = ch[i];
       double p = 0.0;
       if (c != 0) p = fmin((double)mh[i] / (double)c, 1.0);
@@ -275,7 +276,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   if (leader) publish(start_call() ? 1 : 0);
   if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
 
-  constexpr int ROW_STRIDE = 8 * TRACK_CLUSTER;
+  constexpr int ROW_STRIDE = NW * TRACK_CLUSTER;
   while (!ctrl) {
     const int wx = win[0], wy = win[1], ww = win[2] - win[0], wh = win[3] - win[1];
     // Each lane reads 4 adjacent pixels (one 8 B load of 4 colour bins).  Per row: r0 = sum v,
@@ -285,7 +286,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
     double a00 = 0, a10 = 0, a01 = 0, a11 = 0, a20 = 0, a02 = 0;
     const int xbeg = wx & ~3, xend = wx + ww;
     {
-      const int mine = crank * 8 + warp;                        // rows with (wy+yy) % ROW_STRIDE == mine
+      const int mine = crank * NW + warp;                        // rows with (wy+yy) % ROW_STRIDE == mine
       int yy = (mine - (wy % ROW_STRIDE) + ROW_STRIDE) % ROW_STRIDE;
       for (; yy < wh; yy += 4 * ROW_STRIDE) {
         double r[4][3];
@@ -345,7 +346,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
     __syncthreads();
     if (tid < 6) {   // fixed-order sums: run-to-run deterministic
       double t = 0;
-      for (int w8 = 0; w8 < 8; ++w8) t += red[w8][tid];
+      for (int w8 = 0; w8 < NW; ++w8) t += red[w8][tid];
       cpart0[crank * 6 + tid] = t;
     }
     if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
