@@ -139,6 +139,13 @@ __device__ __forceinline__ double bbf_accumulate(double s, unsigned pm, unsigned
 
 __device__ __forceinline__ unsigned ldpx(const uint8_t *__restrict__ win, unsigned off) { return win[off]; }
 
+// predicated ld.shared.u8: lanes with p == false issue no shared-memory access and return dflt
+__device__ __forceinline__ unsigned lds_u8_if(unsigned saddr, bool p, unsigned dflt) {
+  unsigned v = dflt;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.u8 %0, [%1];\n\t}" : "+r"(v) : "r"(saddr), "r"((unsigned)p));
+  return v;
+}
+
 // one stage for one window per lane; all control flow is warp-uniform (table reads are uniform)
 __device__ __forceinline__ bool stage_pass(const uint8_t *__restrict__ win, int j, bool alive, double &sum_out) {
   const int first = c_casc.stage[j].first, last = first + c_casc.stage[j].count;
@@ -387,15 +394,14 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
             const uint4 *f = reinterpret_cast<const uint4 *>(late + first + kk);
             const uint4 a = __ldg(f), b = __ldg(f + 1);
             const unsigned np = b.z & 0xffu, nn = (b.z >> 8) & 0xffu;
-            unsigned pm = win[a.x & 0xffffu], nm = win[a.z >> 16];
-            if (np > 1) pm = min(pm, (unsigned)win[a.x >> 16]);
-            if (np > 2) pm = min(pm, (unsigned)win[a.y & 0xffffu]);
-            if (np > 3) pm = min(pm, (unsigned)win[a.y >> 16]);
-            if (np > 4) pm = min(pm, (unsigned)win[a.z & 0xffffu]);
-            if (nn > 1) nm = max(nm, (unsigned)win[a.w & 0xffffu]);
-            if (nn > 2) nm = max(nm, (unsigned)win[a.w >> 16]);
-            if (nn > 3) nm = max(nm, (unsigned)win[b.x & 0xffffu]);
-            if (nn > 4) nm = max(nm, (unsigned)win[b.x >> 16]);
+            // branch-free: predicated shared loads (inactive slots keep the neutral element and cost no bank traffic)
+            const unsigned wbase = (unsigned)__cvta_generic_to_shared(win);
+            unsigned pm = lds_u8_if(wbase + (a.x & 0xffffu), true, 255u);
+            unsigned nm = lds_u8_if(wbase + (a.z >> 16), true, 0u);
+            pm = __vimin3_u32(pm, lds_u8_if(wbase + (a.x >> 16), np > 1, 255u), lds_u8_if(wbase + (a.y & 0xffffu), np > 2, 255u));
+            pm = __vimin3_u32(pm, lds_u8_if(wbase + (a.y >> 16), np > 3, 255u), lds_u8_if(wbase + (a.z & 0xffffu), np > 4, 255u));
+            nm = __vimax3_u32(nm, lds_u8_if(wbase + (a.w & 0xffffu), nn > 1, 0u), lds_u8_if(wbase + (a.w >> 16), nn > 2, 0u));
+            nm = __vimax3_u32(nm, lds_u8_if(wbase + (b.x & 0xffffu), nn > 3, 0u), lds_u8_if(wbase + (b.x >> 16), nn > 4, 0u));
             const int ai = (int)b.y;
             acc += (pm > nm) ? (long long)ai : -(long long)ai;
           }
