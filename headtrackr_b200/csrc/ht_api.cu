@@ -333,10 +333,11 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   // or, when the cascade's numbers are not 8-digit decimals, two more lane-per-window groups.
   {
     int g = 0;
-    const int cuts_int[] = {0, 2, 4}, cuts_fp[] = {0, 2, 4, 6, 9};
+    const int cuts_fp[] = {0, 2, 4, 6, 9};
     if (ints_ok && !getenv("HT_NO_LATE")) {
-      for (int cpos : cuts_int) if (cpos < hc.n_stages) cc.group_first[g++] = cpos;
-      cc.group_first[g] = std::min(6, hc.n_stages);
+      // lane-per-window pairs up to the last generated stage, then warp-per-window
+      for (int cpos = 0; cpos < HT_GEN_STAGES && cpos < hc.n_stages; cpos += 2) cc.group_first[g++] = cpos;
+      cc.group_first[g] = std::min((int)HT_GEN_STAGES, hc.n_stages);
       cc.late_int = 1;
     } else {
       for (int cpos : cuts_fp) if (cpos < hc.n_stages) cc.group_first[g++] = cpos;
@@ -351,8 +352,8 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   hc.id = hsh ? hsh : 1;
   uint64_t bh = 1469598103934665603ull;
   for (size_t i = 0; i < len; ++i) { bh ^= b[i]; bh *= 1099511628211ull; }
-  hc.fast = (bh == HT_GEN_BLOB_ID) && (len == need) && cc.n_groups >= 3 && cc.group_first[1] == 2 &&
-            cc.group_first[2] == 4 && cc.group_first[3] == 6;
+  hc.fast = (bh == HT_GEN_BLOB_ID) && (len == need) && cc.late_int && cc.n_groups == HT_GEN_STAGES / 2 &&
+            cc.group_first[cc.n_groups] == HT_GEN_STAGES;
   if (getenv("HT_NO_FAST")) hc.fast = false;  // A/B switch for profiling: table-driven stages only
   return HT_OK;
 }

@@ -344,8 +344,10 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
   const bool has_late = late_first < c_casc.n_stages;
   int g = 0;
   if (FAST) {
-    // specialised groups {0,1} {2,3} {4,5}: straight-line code generated from the cascade (cascade_face_gen.inc)
-    static_assert(HT_GEN_STAGES == 6, "the FAST path hard-codes three groups of two generated stages");
+    // specialised groups {0,1} {2,3} {4,5} {6,7} {8,9}: straight-line code generated from the cascade
+    // (cascade_face_gen.inc).  Lane-per-window stays cheaper than warp-per-window while a warp iteration still
+    // carries >~2 live windows, i.e. up to stage 9 for this cascade (stage-10 entrants: ~2 per tile).
+    static_assert(HT_GEN_STAGES == 6 || HT_GEN_STAGES == 8 || HT_GEN_STAGES == 10, "generated stages come in pairs");
 #define HT_GEN_PAIR(A, B)                                                   \
   [&](const uint8_t *win, bool alive, double &sum) {                        \
     alive = alive && gen_stage##A(win, sum);                                \
@@ -358,8 +360,16 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
     if (total_s == 0) return;
     compact(run_lists(false, HT_GEN_PAIR(4, 5)));
     if (total_s == 0) return;
+#if HT_GEN_STAGES >= 8
+    compact(run_lists(false, HT_GEN_PAIR(6, 7)));
+    if (total_s == 0) return;
+#endif
+#if HT_GEN_STAGES >= 10
+    compact(run_lists(false, HT_GEN_PAIR(8, 9)));
+    if (total_s == 0) return;
+#endif
 #undef HT_GEN_PAIR
-    g = 3;
+    g = HT_GEN_STAGES / 2;
   }
   for (; g < c_casc.n_groups; ++g) {
     const bool emit_here = (g == c_casc.n_groups - 1) && !has_late;
