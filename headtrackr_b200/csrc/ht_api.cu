@@ -158,10 +158,32 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
         }
         return first;
       };
-      while (P.taps.size() & 3) P.taps.push_back(TapEnt{0, 0, 0, 0}); // column tables start 32 B aligned
-      j.col_off = make_taps(dw, js.sw, js.sx);
-      while (P.taps.size() & 3) P.taps.push_back(TapEnt{0, 0, 0, 0}); // k_resample reads column taps four at a time
-      j.row_off = make_taps(dh, js.sh, js.sy);
+      const uint32_t col_first = make_taps(dw, js.sw, js.sx);
+      const uint32_t row_first = make_taps(dh, js.sh, js.sy);
+      if (js.sw < dw || js.sh < dh) { err = "internal: the pyramid must only shrink"; return HT_ERR_ARG; }
+      // magic division by 2dw / 2dh, verified against the divided tables for every column / row
+      auto magic_for = [&](int dn, int sn, uint32_t first, int s0, uint32_t &m_out, uint32_t &k_out) {
+        const unsigned long long D = 2ull * dn, nmax = 2ull * dn * sn;
+        int k = 32;
+        while ((1ull << k) <= nmax * D && k < 62) ++k;
+        const unsigned long long M = ((1ull << k) / D) + 1;
+        if (M >= (1ull << 32)) return false;
+        for (int X = 0; X < dn; ++X) {
+          const unsigned long long un = (2ull * X + 1) * sn - dn;
+          const unsigned long long x0 = (un * M) >> k;
+          const TapEnt &t = P.taps[first + X];
+          const unsigned long long xb = std::min<unsigned long long>(x0 + 1, (unsigned long long)sn - 1);
+          if (x0 + s0 != t.a || xb + s0 != t.b || un - x0 * D != t.f) return false;
+        }
+        m_out = (uint32_t)M; k_out = (uint32_t)k;
+        return true;
+      };
+      uint32_t kx = 0, ky = 0;
+      if (!magic_for(dw, js.sw, col_first, js.sx, j.mx, kx) || !magic_for(dh, js.sh, row_first, js.sy, j.my, ky)) {
+        err = "internal: tap magic-division check failed"; return HT_ERR_ARG;
+      }
+      j.sxy = (uint32_t)js.sx | ((uint32_t)js.sy << 16);
+      j.swh = (uint32_t)js.sw | ((uint32_t)js.sh << 16);
       const unsigned long long d = 4ull * dw * dh;
       const unsigned __int128 nmax = (unsigned __int128)d * 255 + d / 2 + 1;
       if (nmax >= ((unsigned __int128)1 << 32)) { err = "frame too large for 32-bit bilinear numerators"; return HT_ERR_SIZE; }
@@ -171,7 +193,7 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
       if (k > 63 || M >= ((unsigned __int128)1 << 32) || nmax * M >= ((unsigned __int128)1 << 64)) {
         err = "frame too large for the exact-division constants"; return HT_ERR_SIZE;
       }
-      j.magic = (uint32_t)M; j.shift = (uint32_t)k; j.half = (uint32_t)(d / 2);
+      j.magic = (uint32_t)M; j.shifts = (uint32_t)k | (kx << 8) | (ky << 16); j.half = (uint32_t)(d / 2);
     }
     const int job_id = (int)P.jobs.size();
     P.jobs.push_back(j);

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
 // K2  pyramid level = canvas-shim drawImage (exact integer bilinear, see oracle/ht_oracle.h and
 // src/ccv.js:121,128,135,140,145).  One launch per pyramid "generation" (levels whose sources are
 // complete).  Block = 8 rows x 128 columns of one destination plane; thread = 4 adjacent pixels.
+// LSU-bound (L1 wavefronts): the only memory instructions are 5 metadata vector loads, 16 pixel byte
+// loads and one 4 B store per thread — tap positions and weights are integer arithmetic.
 __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8_t *__restrict__ arena,
                                                   size_t arena_stride) {
   // per-block metadata: one 8 B tile record and one 64 B job record, fetched with vector loads
@@ -57,12 +59,13 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
   const int job_id = (int)(tl.x & 0xffffu), tx = (int)(tl.x >> 16), ty = (int)(tl.y & 0xffffu);
   const uint4 *jp = reinterpret_cast<const uint4 *>(plan.jobs + job_id);
   const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1), j2 = __ldg(jp + 2), j3 = __ldg(jp + 3);
-  // DevJob: {src_off, dst_off, src_pitch, dst_pitch} {dst_h, dw, dh, col_off} {row_off, magic, shift, half} {..}
+  // DevJob: {src_off, dst_off, src_pitch, dst_pitch} {dst_h, dw, dh, sxy} {swh, magic, shifts, half} {mx, my, ..}
   const uint32_t src_off = j0.x, dst_off = j0.y;
   const int src_pitch = (int)j0.z, dst_pitch = (int)j0.w;
   const int dst_h = (int)j1.x, dw = (int)j1.y, dh = (int)j1.z;
-  const uint32_t col_off = j1.w, row_off = j2.x, magic = j2.y, shift = j2.z, half = j2.w;
-  (void)j3;
+  const uint32_t sx = j1.w & 0xffffu, sy = j1.w >> 16, sw = j2.x & 0xffffu, sh = j2.x >> 16;
+  const uint32_t magic = j2.y, shift = j2.z & 0xffu, kx = (j2.z >> 8) & 0xffu, ky = (j2.z >> 16) & 0xffu, half = j2.w;
+  const uint32_t mx = j3.x, my = j3.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Y = ty * 8 + warp;
   const int X = tx * 128 + lane * 4;
@@ -70,21 +73,21 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
   uint8_t *frame = arena + (size_t)blockIdx.y * arena_stride;
   uint32_t out = 0;
   if (Y < dh && X < dw) {
-    const uint2 ry = __ldg(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // {a | b<<16, f}
-    const uint8_t *ra = frame + src_off + (size_t)(ry.x & 0xffffu) * src_pitch;
-    const uint8_t *rb = frame + src_off + (size_t)(ry.x >> 16) * src_pitch;
+    // bilinear taps computed on the fly (exact: un, vn >= 0 because the pyramid only shrinks; the magic
+    // divisions are verified for every column / row of the job when the plan is built)
     const uint32_t Dx = 2u * (uint32_t)dw, Dy = 2u * (uint32_t)dh;
-    const uint32_t wy1 = ry.y & 0xffffu, wy0 = Dy - wy1;
-    // 4 column taps = 32 B, 16 B aligned (col_off is even, X % 4 == 0); entries past dw are padding
-    const uint4 *cp = reinterpret_cast<const uint4 *>(plan.taps + col_off + X);
-    const uint4 c01 = __ldg(cp), c23 = __ldg(cp + 1);
-    const uint32_t cab[4] = {c01.x, c01.z, c23.x, c23.z};
-    const uint32_t cf[4] = {c01.y & 0xffffu, c01.w & 0xffffu, c23.y & 0xffffu, c23.w & 0xffffu};
+    const uint32_t vn = (2u * (uint32_t)Y + 1u) * sh - (uint32_t)dh;
+    const uint32_t y0 = (uint32_t)(((uint64_t)vn * my) >> ky);
+    const uint32_t wy1 = vn - y0 * Dy, wy0 = Dy - wy1;
+    const uint8_t *ra = frame + src_off + (size_t)(y0 + sy) * src_pitch + sx;
+    const uint8_t *rb = frame + src_off + (size_t)(min(y0 + 1u, sh - 1u) + sy) * src_pitch + sx;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (X + i < dw) {
-        const uint32_t xa = cab[i] & 0xffffu, xb = cab[i] >> 16;
-        const uint32_t wx1 = cf[i], wx0 = Dx - wx1;
+        const uint32_t un = (2u * (uint32_t)(X + i) + 1u) * sw - (uint32_t)dw;
+        const uint32_t xa = (uint32_t)(((uint64_t)un * mx) >> kx);
+        const uint32_t xb = min(xa + 1u, sw - 1u);
+        const uint32_t wx1 = un - xa * Dx, wx0 = Dx - wx1;
         const uint32_t top = wx0 * ra[xa] + wx1 * ra[xb];   // <= 255 * 2dw
         const uint32_t bot = wx0 * rb[xa] + wx1 * rb[xb];
         const uint32_t num = top * wy0 + bot * wy1 + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
