@@ -2,6 +2,7 @@
 // the pyramid/tile planner, and the kernel launches.  sm_100a only; there is no CPU fallback.
 #include "../../include/headtrackr_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -158,32 +159,10 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
         }
         return first;
       };
-      const uint32_t col_first = make_taps(dw, js.sw, js.sx);
-      const uint32_t row_first = make_taps(dh, js.sh, js.sy);
-      if (js.sw < dw || js.sh < dh) { err = "internal: the pyramid must only shrink"; return HT_ERR_ARG; }
-      // magic division by 2dw / 2dh, verified against the divided tables for every column / row
-      auto magic_for = [&](int dn, int sn, uint32_t first, int s0, uint32_t &m_out, uint32_t &k_out) {
-        const unsigned long long D = 2ull * dn, nmax = 2ull * dn * sn;
-        int k = 32;
-        while ((1ull << k) <= nmax * D && k < 62) ++k;
-        const unsigned long long M = ((1ull << k) / D) + 1;
-        if (M >= (1ull << 32)) return false;
-        for (int X = 0; X < dn; ++X) {
-          const unsigned long long un = (2ull * X + 1) * sn - dn;
-          const unsigned long long x0 = (un * M) >> k;
-          const TapEnt &t = P.taps[first + X];
-          const unsigned long long xb = std::min<unsigned long long>(x0 + 1, (unsigned long long)sn - 1);
-          if (x0 + s0 != t.a || xb + s0 != t.b || un - x0 * D != t.f) return false;
-        }
-        m_out = (uint32_t)M; k_out = (uint32_t)k;
-        return true;
-      };
-      uint32_t kx = 0, ky = 0;
-      if (!magic_for(dw, js.sw, col_first, js.sx, j.mx, kx) || !magic_for(dh, js.sh, row_first, js.sy, j.my, ky)) {
-        err = "internal: tap magic-division check failed"; return HT_ERR_ARG;
-      }
-      j.sxy = (uint32_t)js.sx | ((uint32_t)js.sy << 16);
-      j.swh = (uint32_t)js.sw | ((uint32_t)js.sh << 16);
+      while (P.taps.size() & 3) P.taps.push_back(TapEnt{0, 0, 0, 0}); // column tables start 32 B aligned
+      j.col_off = make_taps(dw, js.sw, js.sx);
+      while (P.taps.size() & 3) P.taps.push_back(TapEnt{0, 0, 0, 0}); // k_resample reads column taps four at a time
+      j.row_off = make_taps(dh, js.sh, js.sy);
       const unsigned long long d = 4ull * dw * dh;
       const unsigned __int128 nmax = (unsigned __int128)d * 255 + d / 2 + 1;
       if (nmax >= ((unsigned __int128)1 << 32)) { err = "frame too large for 32-bit bilinear numerators"; return HT_ERR_SIZE; }
@@ -193,7 +172,7 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
       if (k > 63 || M >= ((unsigned __int128)1 << 32) || nmax * M >= ((unsigned __int128)1 << 64)) {
         err = "frame too large for the exact-division constants"; return HT_ERR_SIZE;
       }
-      j.magic = (uint32_t)M; j.shifts = (uint32_t)k | (kx << 8) | (ky << 16); j.half = (uint32_t)(d / 2);
+      j.magic = (uint32_t)M; j.shift = (uint32_t)k; j.half = (uint32_t)(d / 2);
     }
     const int job_id = (int)P.jobs.size();
     P.jobs.push_back(j);
@@ -432,6 +411,11 @@ struct ht_ctx {
   std::vector<cudaEvent_t> chunk_events;
   int h2d_chunk = 64;                       // frames per pipelined upload chunk
   int track_cluster = 0;                    // >0: force single-phase k_track with that cluster size (A/B profiling)
+  bool use_tma = false;                     // stage level-0 tiles with cp.async.bulk.tensor (HT_TMA=1 enables; off by default until re-verified)
+  DevBuf d_tmaps;                           // one 128 B CUtensorMap per scale
+  const void *tmap_arena = nullptr;
+  const void *tmap_plan = nullptr;
+  int casc_minb = 6;                        // CTAs per SM the cascade kernel is compiled for (register cap)
   int track_bail_area = 0;                  // >0: two-phase k_track; phase A hands streams with a larger window (px) to phase B
   DevBuf d_sched;                           // k_track two-phase scheduling scratch
   unsigned sched_seq = 0;
@@ -614,6 +598,45 @@ int track_init_common(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *d
   return HT_OK;
 }
 
+// Tensor maps for the TMA staging of level-0 cascade tiles: one 3-D map (column, row, frame) per scale over the
+// pyramid arena.  Re-encoded whenever the arena allocation or the plan changes.
+int ensure_tensor_maps(ht_ctx *ctx, Plan *P) {
+  if (ctx->tmap_arena == ctx->arena.p && ctx->tmap_plan == P) return HT_OK;
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return ctx->fail(HT_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  std::vector<CUtensorMap> maps(P->scales.size());
+  memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+  for (size_t i = 0; i < P->scales.size(); ++i) {
+    const DevScale &sc = P->scales[i];
+    if (sc.qw <= 0 || sc.qh <= 0) continue;
+    const DevPlane &pl = P->planes[sc.p0];
+    cuuint64_t dims[3] = {(cuuint64_t)pl.pitch, (cuuint64_t)pl.h, (cuuint64_t)ctx->cfg.max_frames};
+    cuuint64_t strides[2] = {(cuuint64_t)pl.pitch, (cuuint64_t)P->arena_stride};
+    cuuint32_t box[3] = {(cuuint32_t)TP, (cuuint32_t)TILE_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->arena.as<uint8_t>() + pl.off, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ctx->fail(HT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for scale %d", (int)r, (int)i);
+  }
+  CK(ctx->d_tmaps.reserve(maps.size() * sizeof(CUtensorMap)));
+  CK(cudaMemcpyAsync(ctx->d_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // `maps` is a local; re-encoding only happens when buffers change
+  ctx->tmap_arena = ctx->arena.p;
+  ctx->tmap_plan = P;
+  return HT_OK;
+}
+
 // gray -> pyramid -> cascade -> sort+group for frames [f0, f0+n) of a device-resident batch.
 // Every per-frame buffer is indexed by absolute frame number so that chunks can be pipelined.
 int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n, int min_neighbors, Rect *d_rects_batch,
@@ -656,9 +679,18 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       g_loaded_cascade[ctx->cfg.device & 63] = ctx->hc.id;
     }
     ctx->prof_begin(HT_PROF_CASCADE);
-    auto kern = ctx->hc.fast ? k_cascade<true> : k_cascade<false>;
+    auto kern = ctx->hc.fast ? k_cascade<true, 4> : k_cascade<false, 4>;
+    if (ctx->hc.fast && ctx->casc_minb == 5) kern = k_cascade<true, 5>;   // experiment: HT_CASC_MINB
+    if (ctx->hc.fast && ctx->casc_minb == 6) kern = k_cascade<true, 6>;
+    if (ctx->hc.fast && ctx->casc_minb == 3) kern = k_cascade<true, 3>;
+    const void *tmaps = nullptr;
+    if (ctx->use_tma) {
+      int trc = ensure_tensor_maps(ctx, P);
+      if (trc != HT_OK) return trc;
+      tmaps = ctx->d_tmaps.p;
+    }
     kern<<<dim3((unsigned)P->casc_tiles.size(), n), CASCADE_THREADS, 0, st>>>(
-        P->dplan, ctx->d_casc.as<LateFeat>(), arena, P->arena_stride, raw_keys, raw_conf, raw_count, ctx->raw_cap);
+        P->dplan, ctx->d_casc.as<LateFeat>(), tmaps, f0, arena, P->arena_stride, raw_keys, raw_conf, raw_count, ctx->raw_cap);
     ctx->prof_end();
     ++ctx->launches;
   }
@@ -750,6 +782,8 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
   }
   if (const char *tc = getenv("HT_TRACK_CLUSTER")) c->track_cluster = atoi(tc);
   if (const char *ba = getenv("HT_TRACK_BAIL")) c->track_bail_area = atoi(ba);
+  if (const char *mb = getenv("HT_CASC_MINB")) c->casc_minb = atoi(mb);
+  if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
   if (const char *hc2 = getenv("HT_H2D_CHUNK")) c->h2d_chunk = std::max(1, atoi(hc2));
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
   // the cascade image is copied into __constant__ memory lazily by run_detect; the late-stage table lives in HBM
@@ -782,7 +816,7 @@ void ht_destroy(ht_ctx *ctx) {
   for (auto &kv : ctx->plans) kv.second->dev.release();
   DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
                     &ctx->labels, &ctx->seq2, &ctx->d_out_rects, &ctx->d_out_counts, &ctx->d_flags, &ctx->model_hist,
-                    &ctx->bins, &ctx->d_sched, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
+                    &ctx->bins, &ctx->d_sched, &ctx->d_tmaps, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
                     &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
   for (DevBuf *b : bufs) b->release();
   for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }

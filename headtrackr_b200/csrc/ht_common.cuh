@@ -53,14 +53,12 @@ struct alignas(16) DevJob {   // 64 B, read by k_resample as four 16 B vectors (
   int32_t src_pitch, dst_pitch;
   int32_t dst_h;
   int32_t dw, dh;             // painted destination size; the rest of the plane is 0
-  uint32_t sxy;               // source rectangle origin  sx | sy << 16
-  uint32_t swh;               // source rectangle size    sw | sh << 16   (sw >= dw, sh >= dh: the pyramid only shrinks)
-  uint32_t magic;             // floor(n / (4 dw dh)) == (uint64(n) * magic) >> shift   for n <= 255.5 * 4 dw dh
-  uint32_t shifts;            // shift | kx << 8 | ky << 16
+  uint32_t col_off;           // first entry of the column tap table (even)
+  uint32_t row_off;           // first entry of the row tap table
+  uint32_t magic, shift;      // floor(n / (4 dw dh)) == (uint64(n) * magic) >> shift   for n <= 255.5 * 4 dw dh
   uint32_t half;              // 2 dw dh (round half up)
-  uint32_t mx, my;            // floor(un / (2 dw)) == (uint64(un) * mx) >> kx for every column numerator un (same for rows);
-                              // verified exhaustively against the divided tap tables when the plan is built
   int32_t src, dst;           // plane ids (host bookkeeping)
+  uint32_t pad_[2];
 };
 static_assert(sizeof(DevJob) == 64, "DevJob is four 16-byte loads");
 

@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
 // K2  pyramid level = canvas-shim drawImage (exact integer bilinear, see oracle/ht_oracle.h and
 // src/ccv.js:121,128,135,140,145).  One launch per pyramid "generation" (levels whose sources are
 // complete).  Block = 8 rows x 128 columns of one destination plane; thread = 4 adjacent pixels.
-// LSU-bound (L1 wavefronts): the only memory instructions are 5 metadata vector loads, 16 pixel byte
-// loads and one 4 B store per thread — tap positions and weights are integer arithmetic.
+// Tap positions / weights come from per-job tables read with 16 B loads (computing them on the fly with magic
+// divisions was measured slower: 4.04 vs 3.89 ms per 1024 frames).
 __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8_t *__restrict__ arena,
                                                   size_t arena_stride) {
   // per-block metadata: one 8 B tile record and one 64 B job record, fetched with vector loads
@@ -59,13 +59,12 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
   const int job_id = (int)(tl.x & 0xffffu), tx = (int)(tl.x >> 16), ty = (int)(tl.y & 0xffffu);
   const uint4 *jp = reinterpret_cast<const uint4 *>(plan.jobs + job_id);
   const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1), j2 = __ldg(jp + 2), j3 = __ldg(jp + 3);
-  // DevJob: {src_off, dst_off, src_pitch, dst_pitch} {dst_h, dw, dh, sxy} {swh, magic, shifts, half} {mx, my, ..}
+  // DevJob: {src_off, dst_off, src_pitch, dst_pitch} {dst_h, dw, dh, col_off} {row_off, magic, shift, half} {..}
   const uint32_t src_off = j0.x, dst_off = j0.y;
   const int src_pitch = (int)j0.z, dst_pitch = (int)j0.w;
   const int dst_h = (int)j1.x, dw = (int)j1.y, dh = (int)j1.z;
-  const uint32_t sx = j1.w & 0xffffu, sy = j1.w >> 16, sw = j2.x & 0xffffu, sh = j2.x >> 16;
-  const uint32_t magic = j2.y, shift = j2.z & 0xffu, kx = (j2.z >> 8) & 0xffu, ky = (j2.z >> 16) & 0xffu, half = j2.w;
-  const uint32_t mx = j3.x, my = j3.y;
+  const uint32_t col_off = j1.w, row_off = j2.x, magic = j2.y, shift = j2.z, half = j2.w;
+  (void)j3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Y = ty * 8 + warp;
   const int X = tx * 128 + lane * 4;
@@ -73,21 +72,21 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
   uint8_t *frame = arena + (size_t)blockIdx.y * arena_stride;
   uint32_t out = 0;
   if (Y < dh && X < dw) {
-    // bilinear taps computed on the fly (exact: un, vn >= 0 because the pyramid only shrinks; the magic
-    // divisions are verified for every column / row of the job when the plan is built)
+    const uint2 ry = __ldg(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // {a | b<<16, f}
+    const uint8_t *ra = frame + src_off + (size_t)(ry.x & 0xffffu) * src_pitch;
+    const uint8_t *rb = frame + src_off + (size_t)(ry.x >> 16) * src_pitch;
     const uint32_t Dx = 2u * (uint32_t)dw, Dy = 2u * (uint32_t)dh;
-    const uint32_t vn = (2u * (uint32_t)Y + 1u) * sh - (uint32_t)dh;
-    const uint32_t y0 = (uint32_t)(((uint64_t)vn * my) >> ky);
-    const uint32_t wy1 = vn - y0 * Dy, wy0 = Dy - wy1;
-    const uint8_t *ra = frame + src_off + (size_t)(y0 + sy) * src_pitch + sx;
-    const uint8_t *rb = frame + src_off + (size_t)(min(y0 + 1u, sh - 1u) + sy) * src_pitch + sx;
+    const uint32_t wy1 = ry.y & 0xffffu, wy0 = Dy - wy1;
+    // 4 column taps = 32 B, 16 B aligned (col_off is even, X % 4 == 0); entries past dw are padding
+    const uint4 *cp = reinterpret_cast<const uint4 *>(plan.taps + col_off + X);
+    const uint4 c01 = __ldg(cp), c23 = __ldg(cp + 1);
+    const uint32_t cab[4] = {c01.x, c01.z, c23.x, c23.z};
+    const uint32_t cf[4] = {c01.y & 0xffffu, c01.w & 0xffffu, c23.y & 0xffffu, c23.w & 0xffffu};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (X + i < dw) {
-        const uint32_t un = (2u * (uint32_t)(X + i) + 1u) * sw - (uint32_t)dw;
-        const uint32_t xa = (uint32_t)(((uint64_t)un * mx) >> kx);
-        const uint32_t xb = min(xa + 1u, sw - 1u);
-        const uint32_t wx1 = un - xa * Dx, wx0 = Dx - wx1;
+        const uint32_t xa = cab[i] & 0xffffu, xb = cab[i] >> 16;
+        const uint32_t wx1 = cf[i], wx0 = Dx - wx1;
         const uint32_t top = wx0 * ra[xa] + wx1 * ra[xb];   // <= 255 * 2dw
         const uint32_t bot = wx0 * rb[xa] + wx1 * rb[xb];
         const uint32_t num = top * wy0 + bot * wy1 + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
@@ -184,13 +183,15 @@ __device__ __forceinline__ bool stage_pass(const uint8_t *__restrict__ win, int 
   return alive && !(sum < c_casc.stage[j].threshold);  // src/ccv.js:222
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
+template <bool FAST, int MINB>
+__global__ void __launch_bounds__(CASCADE_THREADS, MINB) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
+                                                              const void *__restrict__ tmaps, int tma_frame0,
                                                               const uint8_t *__restrict__ arena, size_t arena_stride,
                                                               uint32_t *__restrict__ raw_keys,
                                                               double *__restrict__ raw_conf,
                                                               uint32_t *__restrict__ raw_count, int raw_cap) {
-  __shared__ __align__(16) uint8_t tile[2 * REGION];
+  __shared__ __align__(128) uint8_t tile[2 * REGION];
+  __shared__ __align__(8) unsigned long long tma_bar;
   __shared__ uint16_t raw[NWIN];   // [slot][class] survivor cells of the group that just ran
   __shared__ uint16_t cl[NWIN];    // [entry][class] compacted per-bank-class lists
   __shared__ int cnt[8][32];
@@ -205,7 +206,27 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
   const int x0 = tl.tx * TW, y0 = tl.ty * TH;  // quarter-res origin of the tile
 
   // ---- stage the three levels in shared memory (layout in ht_common.cuh) ----
-  {
+  // Level 0 (13.8 KB, a plain 2-D box of the plane) is staged by the TMA engine when tensor maps are
+  // available: one elected thread issues cp.async.bulk.tensor (3-D map: column, row, frame; out-of-bounds
+  // elements are zero-filled) and the CTA waits on an mbarrier after it has scattered levels 1 and 2 itself.
+  const bool use_tma = (tmaps != nullptr);
+  if (use_tma) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // nobody may poll the barrier before it is initialised
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)REGION) : "memory");
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(tile);
+      const unsigned long long map = (unsigned long long)(reinterpret_cast<const uint8_t *>(tmaps) + 128 * (size_t)tl.scale);
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(dst), "l"(map), "r"(4 * x0), "r"(4 * y0), "r"(tma_frame0 + frame), "r"(bar)
+          : "memory");
+    }
+  } else {
     const DevPlane pl = plan.planes[sc.p0];
     const uint8_t *src = fr + pl.off;
     const int X0 = 4 * x0, Y0 = 4 * y0;
@@ -242,6 +263,14 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 4) k_cascade(DevPlan plan, co
         v = __ldg(reinterpret_cast<const uint32_t *>(fr + pl.off + (size_t)(y0 + r) * pl.pitch + x0 + c));
       uint8_t *d = tile + REGION + (4 * r + 2 * (q >> 1)) * TP + 4 * c + 2 * (q & 1);
       d[0] = (uint8_t)v; d[4] = (uint8_t)(v >> 8); d[8] = (uint8_t)(v >> 16); d[12] = (uint8_t)(v >> 24);
+    }
+  }
+  if (use_tma) {   // every thread observes the completion of the bulk copy (phase 0 of the barrier)
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar) : "memory");
     }
   }
   __syncthreads();
