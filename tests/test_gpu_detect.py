@@ -78,3 +78,18 @@ def test_too_small_frame_is_rejected(ctx):
     with pytest.raises(HtError) as e:
         ctx.detect(f, 5, 1)
     assert e.value.code == HT_ERR_SIZE
+
+
+def test_raw_list_overflow_is_reported(blob):
+    """A raw list longer than max_raw_per_frame is truncated and reported as HT_WARN_OVERFLOW, never silently."""
+    from headtrackr_b200 import Context
+    from headtrackr_b200._lib import HT_WARN_OVERFLOW
+    f = synth.frame(0, 320, 240)
+    assert len(oracle.detect(f, blob, min_neighbors=0)) > 4
+    c = Context(max_width=320, max_height=240, max_frames=2, max_raw_per_frame=4, max_rects_per_frame=2)
+    try:
+        rects, counts = c.detect_raw(f, 5, 0)
+        assert c.last_warning and "overflow" in c.last_warning
+        assert counts[0] == 2
+    finally:
+        c.close()

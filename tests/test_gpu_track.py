@@ -165,3 +165,18 @@ def test_detect_track_host_and_device(ctx, blob):
             assert [(d["x"], d["y"], d["width"], d["height"], d["confidence"], d["neighbors"]) for d in dets[i]] == res
             assert (objs[i]["x"], objs[i]["y"], objs[i]["width"], objs[i]["height"]) == (want["x"], want["y"], want["width"], want["height"])
             assert wins[i] == win
+
+
+def test_track_odd_width_scalar_path(ctx, blob):
+    """W % 4 != 0 takes the scalar bin-plane path of k_track."""
+    f = synth.frame(2, 333, 251)
+    rect = face_rect(blob, f)
+    ot = oracle.CamshiftTracker(calc_angles=True)
+    ot.init_tracker(f, *rect)
+    ctx.track_init(f, [rect], calc_angles=True)
+    for _ in range(3):
+        ot.track(f)
+        objs, wins = ctx.track(f)
+    want = ot.track_obj()
+    assert (objs[0]["x"], objs[0]["y"], objs[0]["width"], objs[0]["height"]) == (want["x"], want["y"], want["width"], want["height"])
+    assert abs(objs[0]["angle"] - want["angle"]) <= 1e-4 and wins[0] == ot.search_window()
