@@ -180,8 +180,8 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
     const DevPlane &spl = P.planes[j.src];
     j.src_off = spl.off; j.dst_off = dp.off; j.src_pitch = spl.pitch; j.dst_pitch = dp.pitch; j.dst_h = dp.h;
     P.jobs.back() = j;
-    for (int ty = 0; ty < (dp.h + 7) / 8; ++ty)
-      for (int tx = 0; tx < (dp.pitch + 127) / 128; ++tx) {
+    for (int ty = 0; ty < (dp.h + 31) / 32; ++ty)
+      for (int tx = 0; tx < (dp.pitch + 31) / 32; ++tx) {
         DevPyrTile t; t.job = (uint16_t)job_id; t.tx = (uint16_t)tx; t.ty = (uint16_t)ty; t.pad_ = 0;
         P.pyr_tiles.push_back(t);
       }

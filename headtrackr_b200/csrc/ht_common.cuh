@@ -68,7 +68,7 @@ struct alignas(8) TapEnt {
   uint16_t a, b, f, pad_;
 };
 
-struct alignas(8) DevPyrTile {  // 8 rows x 128 columns of a destination plane
+struct alignas(8) DevPyrTile {  // 32 x 32 pixels of a destination plane
   uint16_t job, tx, ty, pad_;
 };
 

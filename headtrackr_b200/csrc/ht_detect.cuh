@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
 // ------------------------------------------------------------------------------------------------
 // K2  pyramid level = canvas-shim drawImage (exact integer bilinear, see oracle/ht_oracle.h and
 // src/ccv.js:121,128,135,140,145).  One launch per pyramid "generation" (levels whose sources are
-// complete).  Block = 8 rows x 128 columns of one destination plane; thread = 4 adjacent pixels.
+// complete).  Block = 32 x 32 pixels of one destination plane; thread = one column x 4 rows.
 // Tap positions / weights come from per-job tables read with 16 B loads (computing them on the fly with magic
 // divisions was measured slower: 4.04 vs 3.89 ms per 1024 frames).
 __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8_t *__restrict__ arena,
@@ -65,37 +65,41 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
   const int dst_h = (int)j1.x, dw = (int)j1.y, dh = (int)j1.z;
   const uint32_t col_off = j1.w, row_off = j2.x, magic = j2.y, shift = j2.z, half = j2.w;
   (void)j3;
+  // Block = 32 columns x 32 rows: lane = column (adjacent lanes read adjacent-ish source bytes, so one
+  // warp-wide byte load touches one or two 128 B lines), each thread produces 4 consecutive rows and reuses
+  // its column taps for all of them.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Y = ty * 8 + warp;
-  const int X = tx * 128 + lane * 4;
-  if (Y >= dst_h || X >= dst_pitch) return;
+  const int X = tx * 32 + lane;
+  const int Y0 = ty * 32 + warp * 4;
+  if (Y0 >= dst_h || X >= dst_pitch) return;
   uint8_t *frame = arena + (size_t)blockIdx.y * arena_stride;
-  uint32_t out = 0;
-  if (Y < dh && X < dw) {
-    const uint2 ry = __ldg(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // {a | b<<16, f}
-    const uint8_t *ra = frame + src_off + (size_t)(ry.x & 0xffffu) * src_pitch;
-    const uint8_t *rb = frame + src_off + (size_t)(ry.x >> 16) * src_pitch;
-    const uint32_t Dx = 2u * (uint32_t)dw, Dy = 2u * (uint32_t)dh;
-    const uint32_t wy1 = ry.y & 0xffffu, wy0 = Dy - wy1;
-    // 4 column taps = 32 B, 16 B aligned (col_off is even, X % 4 == 0); entries past dw are padding
-    const uint4 *cp = reinterpret_cast<const uint4 *>(plan.taps + col_off + X);
-    const uint4 c01 = __ldg(cp), c23 = __ldg(cp + 1);
-    const uint32_t cab[4] = {c01.x, c01.z, c23.x, c23.z};
-    const uint32_t cf[4] = {c01.y & 0xffffu, c01.w & 0xffffu, c23.y & 0xffffu, c23.w & 0xffffu};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (X + i < dw) {
-        const uint32_t xa = cab[i] & 0xffffu, xb = cab[i] >> 16;
-        const uint32_t wx1 = cf[i], wx0 = Dx - wx1;
-        const uint32_t top = wx0 * ra[xa] + wx1 * ra[xb];   // <= 255 * 2dw
-        const uint32_t bot = wx0 * rb[xa] + wx1 * rb[xb];
-        const uint32_t num = top * wy0 + bot * wy1 + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
-        const uint32_t q = (uint32_t)(((uint64_t)num * magic) >> shift);
-        out |= q << (8 * i);
-      }
-    }
+  uint32_t xa = 0, xb = 0, wx0 = 0, wx1 = 0;
+  const bool col_ok = X < dw;
+  if (col_ok) {
+    const uint2 cx = __ldg(reinterpret_cast<const uint2 *>(plan.taps + col_off + X));   // {a | b<<16, f}
+    xa = cx.x & 0xffffu; xb = cx.x >> 16;
+    wx1 = cx.y & 0xffffu; wx0 = 2u * (uint32_t)dw - wx1;
   }
-  *reinterpret_cast<uint32_t *>(frame + dst_off + (size_t)Y * dst_pitch + X) = out;
+  const uint32_t Dy = 2u * (uint32_t)dh;
+  const uint8_t *src = frame + src_off;
+  uint8_t *dst = frame + dst_off + (size_t)Y0 * dst_pitch + X;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int Y = Y0 + r;
+    if (Y >= dst_h) break;
+    uint32_t q = 0;
+    if (col_ok && Y < dh) {
+      const uint2 ry = __ldg(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // warp-uniform
+      const uint8_t *ra = src + (size_t)(ry.x & 0xffffu) * src_pitch;
+      const uint8_t *rb = src + (size_t)(ry.x >> 16) * src_pitch;
+      const uint32_t wy1 = ry.y & 0xffffu, wy0 = Dy - wy1;
+      const uint32_t top = wx0 * ra[xa] + wx1 * ra[xb];   // <= 255 * 2dw
+      const uint32_t bot = wx0 * rb[xa] + wx1 * rb[xb];
+      const uint32_t num = top * wy0 + bot * wy1 + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
+      q = (uint32_t)(((uint64_t)num * magic) >> shift);
+    }
+    dst[(size_t)r * dst_pitch] = (uint8_t)q;              // unpainted columns / rows and the pitch padding are 0
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -47,11 +47,12 @@ def main():
         if n in KEEP:
             print(f"{n:45s} {r[ix['Metric Value']]:>16s} {r[ix['Metric Unit']]}")
     rows = page(rep, 'raw')
-    hdr, vals = rows[0], rows[2] if len(rows) > 2 else rows[1]
+    hdr, units, vals = rows[0], rows[1], rows[2] if len(rows) > 2 else rows[1]
     d = dict(zip(hdr, vals))
+    u = dict(zip(hdr, units))
     for k in RAW:
         if k in d:
-            print(f"{k:95s} {d[k]}")
+            print(f"{k:95s} {d[k]} {u.get(k, '')}")
 
 
 if __name__ == '__main__':
