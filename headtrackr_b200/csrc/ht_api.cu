@@ -688,7 +688,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
     if (ctx->hc.fast && ctx->casc_minb == 6) kern = k_cascade<true, 6>;
     if (ctx->hc.fast && ctx->casc_minb == 3) kern = k_cascade<true, 3>;
     const void *tmaps = nullptr;
-    if (ctx->use_tma) {
+    if (ctx->use_tma && TP == TILE_FILL_COLS) {   // the TMA box is TP bytes wide: needs a 16-byte multiple
       int trc = ensure_tensor_maps(ctx, P);
       if (trc != HT_OK) return trc;
       tmaps = ctx->d_tmaps.p;
@@ -1001,16 +1001,19 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   // Detect and track have complementary bottlenecks (k_cascade: shared-memory load wavefronts; k_track: a latency
   // chain of fp64 window passes with < 20 % LSU use), so the batch is cut into parts and the tracking of part p
   // runs on a second stream while part p+1 is being detected.
-  const int parts = (n_calls > 0 && ctx->overlap_track) ? ((n >= 512) ? 4 : (n >= 128 ? 2 : 1)) : 1;
+  // (Tracking host-frame parts on the main stream as their chunks arrive was also measured: e2e 27.3k vs 33.6k fps
+  // for one k_track over the whole batch — every k_track launch costs at least its slowest stream.)
+  const bool use_aux = (n_calls > 0 && ctx->overlap_track);
+  const int parts = use_aux ? ((n >= 512) ? 4 : (n >= 128 ? 2 : 1)) : 1;
   auto part_begin = [&](int p) { return (int)(((long long)n * p) / parts); };
-  if (parts > 1 && !ctx->aux_stream) {
+  if (use_aux && parts > 1 && !ctx->aux_stream) {
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->aux_done, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->part_events[i], cudaEventDisableTiming));
   }
   // run tracking for frames [f0, f0+nf) — on the aux stream when overlapping
   auto track_part = [&](const uint8_t *d_frames_batch, int f0, int nf) -> int {
-    if (parts == 1) return run_track_from_detect(ctx, d_frames_batch, w, h, f0, nf, d_rects, d_counts, calc_angles, n_calls, d_found, d_objs, d_win);
+    if (parts == 1 || !use_aux) return run_track_from_detect(ctx, d_frames_batch, w, h, f0, nf, d_rects, d_counts, calc_angles, n_calls, d_found, d_objs, d_win);
     const int pi = ctx->part_seq++ & 3;
     CK(cudaEventRecord(ctx->part_events[pi], st));
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->part_events[pi], 0));
@@ -1020,8 +1023,6 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
     ctx->stream = saved;
     return r;
   };
-  if (parts > 1) {   // earlier work on the main stream (e.g. buffer reuse) orders before the aux stream via part events
-  }
   if (is_device_ptr(rgba)) {
     for (int p = 0; p < parts; ++p) {
       const int f0 = part_begin(p), nf = part_begin(p + 1) - f0;
@@ -1071,7 +1072,7 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
     }
     if (tracked_to < n) { rc = track_part(d_frames, tracked_to, n - tracked_to); if (rc != HT_OK) return rc; }
   }
-  if (parts > 1) {   // join: results of the aux stream are complete before anything later on the main stream
+  if (use_aux && parts > 1) {   // join: results of the aux stream are complete before anything later on the main stream
     CK(cudaEventRecord(ctx->aux_done, ctx->aux_stream));
     CK(cudaStreamWaitEvent(st, ctx->aux_done, 0));
   }

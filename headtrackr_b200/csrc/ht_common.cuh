@@ -28,7 +28,11 @@ namespace ht {
 // Adjacent lanes (lx, lx+1) are 4 bytes apart in every level -> conflict-free shared-memory reads.
 constexpr int TW = 32;
 constexpr int TH = 16;
-constexpr int TP = 160;                       // tile pitch in bytes (>= 4*TW+22, multiple of 16)
+#ifndef HT_TILE_PITCH
+#define HT_TILE_PITCH 160
+#endif
+constexpr int TP = HT_TILE_PITCH;             // tile pitch in bytes (>= 4*TW+22, multiple of 4; TMA staging needs % 16)
+constexpr int TILE_FILL_COLS = 160;           // level-0 columns staged per row (ten 16 B vectors)
 constexpr int TILE_ROWS = 4 * TH + 22;        // 86 level-0 rows: 4*(TH-1)+2+23+1
 constexpr int REGION = TILE_ROWS * TP;        // bytes per region
 constexpr int L1_ROWS = 2 * TH + 11;          // 43
@@ -36,6 +40,8 @@ constexpr int L1_COLS = 2 * TW + 11;          // 75
 constexpr int L2_ROWS = TH + 5;               // 21
 constexpr int L2_COLS = TW + 5;               // 37
 constexpr int NWIN = TW * TH * 4;             // windows per tile
+// shared-memory bank of a window's base a0 = 4lx + 2dx + (4ly + 2dy) * TP  (bank = word index mod 32)
+__host__ __device__ constexpr int bank_class(int lx, int ly, int dy) { return (lx + (4 * ly + 2 * dy) * (TP / 4)) & 31; }
 constexpr int CASCADE_THREADS = 256;
 
 constexpr int MAX_STAGES = 64;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, MINB) k_cascade(DevPlan plan,
   // Level 0 (13.8 KB, a plain 2-D box of the plane) is staged by the TMA engine when tensor maps are
   // available: one elected thread issues cp.async.bulk.tensor (3-D map: column, row, frame; out-of-bounds
   // elements are zero-filled) and the CTA waits on an mbarrier after it has scattered levels 1 and 2 itself.
-  const bool use_tma = (tmaps != nullptr);
+  const bool use_tma = (tmaps != nullptr) && (TP == TILE_FILL_COLS);
   if (use_tma) {
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
     if (tid == 0) {
@@ -234,12 +234,17 @@ __global__ void __launch_bounds__(CASCADE_THREADS, MINB) k_cascade(DevPlan plan,
     const DevPlane pl = plan.planes[sc.p0];
     const uint8_t *src = fr + pl.off;
     const int X0 = 4 * x0, Y0 = 4 * y0;
-    for (int i = tid; i < TILE_ROWS * (TP / 16); i += CASCADE_THREADS) {
-      const int r = i / (TP / 16), c = (i % (TP / 16)) * 16;
+    for (int i = tid; i < TILE_ROWS * (TILE_FILL_COLS / 16); i += CASCADE_THREADS) {
+      const int r = i / (TILE_FILL_COLS / 16), c = (i % (TILE_FILL_COLS / 16)) * 16;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (Y0 + r < pl.h && X0 + c < pl.pitch)
         v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(Y0 + r) * pl.pitch + X0 + c));
-      *reinterpret_cast<uint4 *>(tile + r * TP + c) = v;
+      if (TP % 16 == 0) {
+        *reinterpret_cast<uint4 *>(tile + r * TP + c) = v;
+      } else {   // rows are only 4 B aligned
+        uint32_t *d = reinterpret_cast<uint32_t *>(tile + r * TP + c);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
     }
   }
   {
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, MINB) k_cascade(DevPlan plan,
       double sum = 0.0;
       alive = eval(win, alive, sum);
       if (emit_here) { if (alive) emit(lx, ly, q, sum); }
-      else raw[(warp * 8 + it) * 32 + ((lane + 16 * (q >> 1)) & 31)] = alive ? (uint16_t)wid : (uint16_t)0xFFFFu;
+      else raw[(warp * 8 + it) * 32 + bank_class(lx, ly, q >> 1)] = alive ? (uint16_t)wid : (uint16_t)0xFFFFu;
     }
     return NWIN / 32;
   };
