@@ -5,9 +5,19 @@
  */
 #include "ht_oracle.h"
 
+#include <malloc.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+
+/* Many host threads run this oracle concurrently in bench.py's CPU baseline.  The restatement allocates
+ * multi-megabyte temporaries per call (whole-frame pdf, pyramid planes) like the reference does; keep them in the
+ * per-thread malloc arenas instead of mmap/munmap'ing each one, which serialises all threads in the kernel. */
+__attribute__((constructor)) static void hto_init_malloc(void) {
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
+  mallopt(M_ARENA_MAX, 256);
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* JS number helpers                                                                           */
