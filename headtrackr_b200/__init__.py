@@ -6,10 +6,11 @@ Host-side mirror of the reference's L1 interface:
     headtrackr_b200.camshift.Tracker / Rectangle / TrackObj  <- /root/reference/src/camshift.js
     headtrackr_b200.getWhitebalance                          <- /root/reference/src/whitebalance.js
     headtrackr_b200.facetrackr.Tracker                       <- /root/reference/src/facetrackr.js (host state machine)
+    headtrackr_b200.smoother.Smoother, headposition.Tracker  <- src/smoother.js, src/headposition.js (host scalars)
 All pixel work runs in libheadtrackr_b200.so (CUDA, C ABI in include/headtrackr_b200.h).
 """
 from . import _lib  # noqa: F401
-from . import camshift, ccv, facetrackr  # noqa: F401
+from . import camshift, ccv, facetrackr, headposition, smoother  # noqa: F401
 from .canvas import Canvas, as_pixels  # noqa: F401
 from .context import Context  # noqa: F401
 from .synth import load_cascade_blob  # noqa: F401
@@ -28,4 +29,4 @@ def getWhitebalance(canvas, context=None):
     return float(ctx.whitebalance(px)[0])
 
 
-__all__ = ["Context", "Canvas", "load_cascade_blob", "cascade", "getWhitebalance", "ccv", "camshift", "facetrackr"]
+__all__ = ["Context", "Canvas", "load_cascade_blob", "cascade", "getWhitebalance", "ccv", "camshift", "facetrackr", "smoother", "headposition"]

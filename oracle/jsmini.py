@@ -156,6 +156,19 @@ class NativeFunction(JSObject):
         return self.fn(None, args)
 
 
+class JSDate(JSObject):
+    """`new Date()` — only what the reference uses: subtraction and getTime()."""
+    __slots__ = ("ms",)
+
+    def __init__(self, ms):
+        JSObject.__init__(self)
+        self.ms = float(ms)
+        self.props["getTime"] = NativeFunction(lambda this, a: self.ms)
+
+
+GLOBAL_THIS = JSObject()
+
+
 class ReturnEx(Exception):
     def __init__(self, v):
         self.v = v
@@ -195,6 +208,8 @@ class JSFunction(JSObject):
         self.props["prototype"] = JSObject()
 
     def call(self, this, args):
+        if this is undefined or this is None:
+            this = GLOBAL_THIS          # sloppy-mode functions see the global object as `this`
         env = Env(self.env, this)
         v = env.vars
         for n in self.hoisted:
@@ -231,6 +246,8 @@ def to_number(v):
         return math.nan
     if v is None:
         return 0.0
+    if c is JSDate:
+        return v.ms
     if c is str:
         try:
             return float(v) if v.strip() else 0.0
@@ -991,6 +1008,7 @@ def _math():
         "floor": fn(js_floor), "sqrt": fn(js_sqrt), "log": fn(js_log), "pow": fn(lambda a, b: math.pow(a, b)),
         "min": fn(js_min), "max": fn(js_max), "abs": fn(abs), "atan2": fn(math.atan2),
         "round": fn(lambda x: float(math.floor(x + 0.5))), "PI": math.pi,
+        "atan": fn(math.atan), "sin": fn(math.sin), "cos": fn(math.cos), "tan": fn(math.tan),
     })
     return m
 
@@ -1120,6 +1138,16 @@ class Interpreter:
         g["Infinity"] = math.inf
         doc = JSObject()
         doc.props["createElement"] = NativeFunction(lambda this, a: CanvasShim())
+        self.events = []                 # document.dispatchEvent log (facetrackingEvent / headtrackingEvent ...)
+        self.now_ms = 1.0e12             # `new Date()` clock (tests may advance it)
+
+        def create_event(this, a):
+            e = JSObject()
+            e.props["initEvent"] = NativeFunction(lambda th, aa: e.props.__setitem__("type", aa[0]) or undefined)
+            return e
+        doc.props["createEvent"] = NativeFunction(create_event)
+        doc.props["dispatchEvent"] = NativeFunction(lambda this, a: self.events.append(a[0]) or True)
+        g["Date"] = NativeFunction(lambda this, a: JSDate(self.now_ms))
         g["document"] = doc
         g["headtrackr"] = JSObject()
 
