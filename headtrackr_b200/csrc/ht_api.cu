@@ -679,7 +679,9 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
     // make this context's cascade the active __constant__ table (contexts with the same blob share it;
     // contexts with DIFFERENT cascades must not run concurrently on one device)
     if (g_loaded_cascade[ctx->cfg.device & 63] != ctx->hc.id) {
+      CK(cudaDeviceSynchronize());   // kernels of other contexts may still be reading the previous table
       CK(cudaMemcpyToSymbolAsync(c_casc, &ctx->hc.cc, sizeof(ConstCascade), 0, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st)); // ... and contexts sharing this cascade skip the upload, so it must have landed
       g_loaded_cascade[ctx->cfg.device & 63] = ctx->hc.id;
     }
     ctx->prof_begin(HT_PROF_CASCADE);

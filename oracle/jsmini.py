@@ -149,6 +149,12 @@ class NativeFunction(JSObject):
         JSObject.__init__(self)
         self.fn = fn
 
+    def get(self, key):
+        if key == "apply":        # Math.max.apply(null, array) — src/facetrackr.js:84-86
+            return NativeFunction(lambda this, a: self.call(a[0] if a else undefined,
+                                                            list(a[1].items) if len(a) > 1 else []))
+        return JSObject.get(self, key)
+
     def call(self, this, args):
         return self.fn(this, args)
 

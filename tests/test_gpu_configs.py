@@ -88,3 +88,11 @@ def test_config5_many_streams_in_one_batch(ctx, blob):
             w = trackers[s].track_obj()
             assert (objs[s]["x"], objs[s]["y"], objs[s]["width"], objs[s]["height"]) == (w["x"], w["y"], w["width"], w["height"])
             assert wins[s] == trackers[s].search_window()
+
+
+def test_facetrackr_on_cuda_matches_reference_js(ctx):
+    """The reference's own facetrackr.js event stream (tests/golden/reference_js_post.json) reproduced with the
+    CUDA library underneath the host state machine."""
+    from test_host_post import GOLD as POST, check_steps, run_facetrackr
+    for case in POST["facetrackr"]:
+        check_steps(run_facetrackr(case, facetrackr.CudaBackend(ctx)), case["steps"])

@@ -53,6 +53,36 @@ def main():
             r = jsmini.to_py(it.call(hp.get("track"), hp, obj(f)))
             outs.append([r["x"], r["y"], r["z"]])
         gold["headposition"].append(dict(params=params, fov=it.call(hp.get("getFOV"), hp), out=outs))
+    # ---- facetrackr state machine (src/facetrackr.js) over a short synthetic stream ----
+    import numpy as np
+    from headtrackr_b200 import synth
+    for f in ("ccv.js", "cascade.js", "camshift.js", "whitebalance.js", "facetrackr.js"):
+        it.run((REF / f).read_text())
+    gold["facetrackr"] = []
+    for name, wb, n_frames in [("vj_cs", False, 5), ("wb_vj_cs", True, 18)]:
+        base = synth.frame(3, 160, 120, n_faces=1)
+        frames = [np.roll(base, (t, 2 * t), axis=(0, 1)) for t in range(n_frames)]
+        if wb:   # whitebalance gate: identical frames until the 15-sample window is stable (src/facetrackr.js:79-95)
+            frames = [base] * 16 + frames[:2]
+        params = jsmini.JSObject()
+        params.props["whitebalancing"] = wb
+        canvas = jsmini.CanvasShim(frames[0].copy())
+        ft = it.get(["headtrackr", "facetrackr", "Tracker"]).construct([params])
+        it.call(ft.get("init"), ft, canvas)
+        it.events.clear()
+        steps = []
+        for fr in frames:
+            canvas.pix = fr.copy()
+            n_before = len(it.events)
+            it.call(ft.get("track"), ft)
+            o = jsmini.to_py(it.call(ft.get("getTrackingObject"), ft))
+            ev = [jsmini.to_py(e) for e in it.events[n_before:]]
+            for e in ev:
+                e.pop("time", None)
+            steps.append(dict(detection=o["detection"], x=o["x"], y=o["y"], width=o["width"], height=o["height"],
+                              confidence=o["confidence"], events=ev))
+        gold["facetrackr"].append(dict(name=name, whitebalancing=wb, n_frames=len(frames), steps=steps))
+        print(name, [s_["detection"] for s_ in steps])
     OUT.write_text(json.dumps(gold, indent=1))
     print("wrote", OUT)
 
