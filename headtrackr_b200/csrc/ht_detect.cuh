@@ -397,10 +397,29 @@ __global__ void __launch_bounds__(CASCADE_THREADS, MINB) k_cascade(DevPlan plan,
   }
     compact(run_dense(false, HT_GEN_PAIR(0, 1)));
     if (total_s == 0) return;
+#define HT_GEN_ONE(A)                                                       \
+  [&](const uint8_t *win, bool alive, double &sum) { return alive && gen_stage##A(win, sum); }
+#ifndef HT_SPLIT_GROUPS
+#define HT_SPLIT_GROUPS 1
+#endif
+#if HT_SPLIT_GROUPS >= 1   // stages 2 and 3 as separate groups: stage 3 (91 loads) runs on re-compacted lists
+    compact(run_lists(false, HT_GEN_ONE(2)));
+    if (total_s == 0) return;
+    compact(run_lists(false, HT_GEN_ONE(3)));
+    if (total_s == 0) return;
+#else
     compact(run_lists(false, HT_GEN_PAIR(2, 3)));
     if (total_s == 0) return;
+#endif
+#if HT_SPLIT_GROUPS >= 2
+    compact(run_lists(false, HT_GEN_ONE(4)));
+    if (total_s == 0) return;
+    compact(run_lists(false, HT_GEN_ONE(5)));
+    if (total_s == 0) return;
+#else
     compact(run_lists(false, HT_GEN_PAIR(4, 5)));
     if (total_s == 0) return;
+#endif
 #if HT_GEN_STAGES >= 8
     compact(run_lists(false, HT_GEN_PAIR(6, 7)));
     if (total_s == 0) return;
@@ -410,6 +429,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, MINB) k_cascade(DevPlan plan,
     if (total_s == 0) return;
 #endif
 #undef HT_GEN_PAIR
+#undef HT_GEN_ONE
     g = HT_GEN_STAGES / 2;
   }
   for (; g < c_casc.n_groups; ++g) {
