@@ -63,7 +63,7 @@ _lib = None
 
 EXPORTS = ["ht_version", "ht_create", "ht_destroy", "ht_last_error", "ht_sync", "ht_max_rects", "ht_detect",
            "ht_track_init", "ht_track_init_from_detect", "ht_track", "ht_detect_track", "ht_backprojection", "ht_whitebalance",
-           "ht_plan_info", "ht_debug_plane", "ht_debug_raw", "ht_debug_model_hist", "ht_debug_track_stats", "ht_launch_count",
+           "ht_plan_info", "ht_debug_plane", "ht_debug_raw", "ht_debug_model_hist", "ht_debug_track_stats", "ht_set_track_memo", "ht_debug_track_trace", "ht_launch_count",
            "ht_profile", "ht_profile_read"]
 
 PROF_CLASSES = ["gray", "pyramid", "cascade", "group", "hist", "track_init", "track"]
@@ -101,6 +101,8 @@ def lib():
     L.ht_debug_raw.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     L.ht_debug_model_hist.argtypes = [vp, C.c_int, vp]
     L.ht_debug_track_stats.argtypes = [vp, vp, C.c_int]
+    L.ht_debug_track_trace.argtypes = [vp, vp, C.c_int]
+    L.ht_set_track_memo.argtypes = [vp, C.c_int]
     L.ht_launch_count.argtypes = [vp]
     L.ht_launch_count.restype = C.c_uint64
     L.ht_profile.argtypes = [vp, C.c_int]

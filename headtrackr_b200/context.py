@@ -208,9 +208,20 @@ class Context:
         return [(r.x, r.y, r.width, r.height, r.confidence, r.neighbors) for r in out[: min(cnt.value, cap)]], cnt.value
 
     def debug_track_stats(self, reset=True):
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 5)()
         self._check(self._L.ht_debug_track_stats(self._h, C.addressof(out), int(bool(reset))))
-        return dict(passes=int(out[0]), serial_passes=int(out[1]), pixels=int(out[2]), calls=int(out[3]))
+        return dict(passes=int(out[0]), serial_passes=int(out[1]), pixels=int(out[2]), calls=int(out[3]),
+                    memo_hits=int(out[4]))
+
+    def set_track_memo(self, enable=True):
+        """Re-use the moments of windows already summed in the same launch (default on; results are identical)."""
+        self._check(self._L.ht_set_track_memo(self._h, int(bool(enable))))
+
+    def debug_track_trace(self, n):
+        """(n, 4) uint64: {start ns, end ns, SM id, passes} per stream (contexts created under HT_TRACK_TRACE=1)."""
+        out = np.zeros((n, 4), np.uint64)
+        self._check(self._L.ht_debug_track_trace(self._h, out.ctypes.data, n))
+        return out
 
     def debug_model_hist(self, slot):
         out = np.zeros(4096, np.uint32)

@@ -415,6 +415,16 @@ struct ht_ctx {
   std::vector<cudaEvent_t> chunk_events;
   int h2d_chunk = 64;                       // frames per pipelined upload chunk
   int track_cluster = 0;                    // >0: force single-phase k_track with that cluster size (A/B profiling)
+  bool track_memo = true;                   // k_track re-uses the moments of windows it has already summed in this
+                                            // launch (ht_set_track_memo / HT_TRACK_MEMO=0 for the strict A/B)
+  bool track_trace = false;                 // HT_TRACK_TRACE=1: k_track writes a per-stream timeline (ht_debug_track_trace)
+  DevBuf d_trace;
+  int track_nt = 256;                       // threads per k_track CTA (HT_TRACK_NT=128|256)
+  bool track_lpt = true;                    // longest-chain-first launch order (HT_TRACK_LPT=0 disables)
+  int track_heavy_div = 0;                  // >0: the n/div streams with the largest windows run on a cluster of
+  int track_heavy_cluster = 8;              //     track_heavy_cluster CTAs on sched_stream (HT_TRACK_HEAVY=div[,cluster])
+  cudaStream_t sched_stream = nullptr;
+  cudaEvent_t sched_ready = nullptr, sched_done = nullptr;
   bool use_tma = true;                      // stage level-0 tiles with cp.async.bulk.tensor (HT_TMA=0 disables)
   DevBuf d_tmaps;                           // one 128 B CUtensorMap per scale
   const void *tmap_arena = nullptr;
@@ -505,6 +515,7 @@ int ensure_tracker_buffers(ht_ctx *ctx) {
     CK(ctx->d_objs.reserve(mf * 6 * sizeof(int32_t)));
     CK(ctx->d_windows.reserve(mf * 4 * sizeof(int32_t)));
     CK(ctx->d_sched.reserve((2 * mf + 64) * sizeof(int32_t)));
+    if (ctx->track_trace) CK(ctx->d_trace.reserve(4 * mf * sizeof(unsigned long long)));
   }
   return HT_OK;
 }
@@ -526,11 +537,15 @@ int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_
 // outgrows bail_area stop and are queued.  Phase B: one 8-CTA cluster per queued stream finishes their calls.
 // Mean-shift is a serial chain of window passes per stream, so the few streams with large windows would
 // otherwise set the duration of the whole launch.
+// HT_TRACK_TRACE=1: timeline buffer of the context that is launching (debug; launches are made by one host thread)
+static unsigned long long *g_track_trace = nullptr;
+static int g_track_memo = 1;   // ht_ctx::track_memo of the context that is launching
+
 template <int C, int NT = 256>
 cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, int h, const int32_t *d_slots,
                            const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
                            int32_t *d_win, int32_t *flag, unsigned long long *stats, int bail_area, int32_t *calls_done,
-                           int32_t *bail_list, int32_t *bail_count, int use_list) {
+                           int32_t *bail_list, int32_t *bail_count, int use_list, int list_off = 0) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)n * C);
   cfg.blockDim = dim3(NT);
@@ -541,23 +556,46 @@ cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, 
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_track<C, NT>, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
-                            bail_area, calls_done, bail_list, bail_count, use_list);
+                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, g_track_trace, g_track_memo);
+}
+
+// cluster size x CTA size chosen at run time
+template <int NT>
+cudaError_t launch_track_nt(int c, cudaStream_t st, int n, const uint16_t *bins, int w, int h, const int32_t *d_slots,
+                            const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
+                            int32_t *d_win, int32_t *flag, unsigned long long *stats, int32_t *calls_done, int32_t *list,
+                            int32_t *count, int use_list, int list_off) {
+  switch (c) {
+    case 1: return launch_track_c<1, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off);
+    case 2: return launch_track_c<2, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off);
+    case 4: return launch_track_c<4, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off);
+    default: return launch_track_c<8, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off);
+  }
+}
+cudaError_t launch_track_any(int c, int nt, cudaStream_t st, int n, const uint16_t *bins, int w, int h, const int32_t *d_slots,
+                             const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
+                             int32_t *d_win, int32_t *flag, unsigned long long *stats, int32_t *calls_done, int32_t *list,
+                             int32_t *count, int use_list, int list_off) {
+  if (nt == 128)
+    return launch_track_nt<128>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off);
+  return launch_track_nt<256>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off);
 }
 
 int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h, const int32_t *d_slots, const uint32_t *mh,
                  const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs, int32_t *d_win, int32_t *flag) {
   unsigned long long *stats = ctx->d_flags.as<unsigned long long>() + 8;
   cudaStream_t st = ctx->stream;
-  // per-chunk scheduling scratch: [calls_done n][bail_list n][bail_count 1]
-  int32_t *sched = ctx->d_sched.as<int32_t>() + (size_t)f0 * 2 + (size_t)0;
+  g_track_memo = ctx->track_memo ? 1 : 0;
+  g_track_trace = ctx->track_trace ? ctx->d_trace.as<unsigned long long>() + 4 * (size_t)f0 : nullptr;
+  // per-chunk scheduling scratch: [calls_done | area n][bail_list | order n][bail_count 1]
   int32_t *calls_done = ctx->d_sched.as<int32_t>() + (size_t)f0;
   int32_t *bail_list = ctx->d_sched.as<int32_t>() + (size_t)ctx->cfg.max_frames + f0;
   int32_t *bail_count = ctx->d_sched.as<int32_t>() + 2 * (size_t)ctx->cfg.max_frames + (ctx->sched_seq++ & 63);
-  (void)sched;
-  cudaError_t e = cudaMemsetAsync(bail_count, 0, sizeof(int32_t), st);
-  if (e != cudaSuccess) return ctx->fail(HT_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  cudaError_t e = cudaSuccess;
   if (ctx->track_bail_area > 0) {
     // two-phase (HT_TRACK_BAIL=<px>): measured 8.1-8.9 ms per 1024x30 calls vs 7.2 ms for the single-phase cluster of 4
+    e = cudaMemsetAsync(bail_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return ctx->fail(HT_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
     e = launch_track_c<1>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, ctx->track_bail_area,
                           calls_done, bail_list, bail_count, 0);
     if (e == cudaSuccess)
@@ -565,18 +603,43 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
                             bail_list, bail_count, 1);
     ctx->launches += 2;
   } else {
-    // single phase: many streams -> 4 CTAs per stream (throughput); few streams -> 8 (latency of one stream)
+    // few streams -> 8 CTAs per stream (latency of one stream); many streams -> 2 (more streams resident).
+    // measured on 1024 streams x 30 calls in index order: 1 CTA 9.7 ms, 2 CTAs 6.1 ms, 4 CTAs 6.2 ms, 8 CTAs 10.1 ms
     int c = ctx->track_cluster;
-    // measured on 1024 streams x 30 calls: 1 CTA 9.7 ms, 2 CTAs 6.1 ms, 4 CTAs 6.2 ms, 8 CTAs 10.1 ms (512- and
-    // 1024-thread single CTAs: 8.8 ms)
     if (c <= 0) c = (n >= 256) ? 2 : (n >= 32 ? 4 : 8);
-    switch (c) {
-      case 1: e = launch_track_c<1>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, bail_list, bail_count, 0); break;
-      case 2: e = launch_track_c<2>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, bail_list, bail_count, 0); break;
-      case 4: e = launch_track_c<4>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, bail_list, bail_count, 0); break;
-      default: e = launch_track_c<8>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, bail_list, bail_count, 0); break;
+    const int nt = ctx->track_nt;
+    const bool lpt = ctx->track_lpt && n >= 128;     // below that every stream is resident from the start
+    if (!lpt) {
+      e = launch_track_any(c, nt, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done,
+                           bail_list, bail_count, 0, 0);
+      ++ctx->launches;
+    } else {
+      // longest chain first: order the streams by search-window area (k_track_area / k_track_rank); optionally the
+      // n / track_heavy_div largest get a cluster of 8 on a second stream, concurrently with the others
+      k_track_area<<<(n + 255) / 256, 256, 0, st>>>(state, d_slots, n, calls_done);
+      k_track_rank<<<(n + 255) / 256, 256, 0, st>>>(calls_done, n, bail_list);
+      ctx->launches += 2;
+      const int n_heavy = (ctx->track_heavy_div > 0) ? n / ctx->track_heavy_div : 0;
+      if (n_heavy > 0) {
+        if (!ctx->sched_stream) {
+          CK(cudaStreamCreateWithFlags(&ctx->sched_stream, cudaStreamNonBlocking));
+          CK(cudaEventCreateWithFlags(&ctx->sched_ready, cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&ctx->sched_done, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(ctx->sched_ready, st));
+        CK(cudaStreamWaitEvent(ctx->sched_stream, ctx->sched_ready, 0));
+        e = launch_track_any(ctx->track_heavy_cluster, 256, ctx->sched_stream, n_heavy, bins, w, h, d_slots, mh, ch, state,
+                             n_calls, d_objs, d_win, flag, stats, calls_done, bail_list, bail_count, 2, 0);
+        CK(cudaEventRecord(ctx->sched_done, ctx->sched_stream));
+        ++ctx->launches;
+      }
+      if (e == cudaSuccess && n > n_heavy) {
+        e = launch_track_any(c, nt, st, n - n_heavy, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
+                             calls_done, bail_list, bail_count, 2, n_heavy);
+        ++ctx->launches;
+      }
+      if (n_heavy > 0) CK(cudaStreamWaitEvent(st, ctx->sched_done, 0));
     }
-    ++ctx->launches;
   }
   if (e != cudaSuccess) return ctx->fail(HT_ERR_CUDA, "k_track launch: %s", cudaGetErrorString(e));
   return HT_OK;
@@ -788,6 +851,17 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
   }
   if (const char *tc = getenv("HT_TRACK_CLUSTER")) c->track_cluster = atoi(tc);
   if (const char *ba = getenv("HT_TRACK_BAIL")) c->track_bail_area = atoi(ba);
+  if (const char *tm2 = getenv("HT_TRACK_MEMO")) c->track_memo = atoi(tm2) != 0;
+  if (const char *tt = getenv("HT_TRACK_TRACE")) c->track_trace = atoi(tt) != 0;
+  if (const char *tn = getenv("HT_TRACK_NT")) c->track_nt = (atoi(tn) == 128) ? 128 : 256;
+  if (const char *tl = getenv("HT_TRACK_LPT")) c->track_lpt = atoi(tl) != 0;
+  if (const char *th = getenv("HT_TRACK_HEAVY")) {
+    c->track_heavy_div = std::max(0, atoi(th));
+    if (const char *comma = strchr(th, ',')) {
+      const int hc = atoi(comma + 1);
+      if (hc == 1 || hc == 2 || hc == 4 || hc == 8) c->track_heavy_cluster = hc;
+    }
+  }
   if (const char *mb = getenv("HT_CASC_MINB")) c->casc_minb = atoi(mb);
   if (const char *ov = getenv("HT_OVERLAP")) c->overlap_track = atoi(ov) != 0;
   if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
@@ -823,7 +897,7 @@ void ht_destroy(ht_ctx *ctx) {
   for (auto &kv : ctx->plans) kv.second->dev.release();
   DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
                     &ctx->labels, &ctx->seq2, &ctx->d_out_rects, &ctx->d_out_counts, &ctx->d_flags, &ctx->model_hist,
-                    &ctx->bins, &ctx->d_sched, &ctx->d_tmaps, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
+                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_tmaps, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
                     &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
   for (DevBuf *b : bufs) b->release();
   for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -831,6 +905,9 @@ void ht_destroy(ht_ctx *ctx) {
   for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
   if (ctx->compute_done) cudaEventDestroy(ctx->compute_done);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->sched_stream) cudaStreamDestroy(ctx->sched_stream);
+  if (ctx->sched_ready) cudaEventDestroy(ctx->sched_ready);
+  if (ctx->sched_done) cudaEventDestroy(ctx->sched_done);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->aux_done) cudaEventDestroy(ctx->aux_done);
   for (cudaEvent_t e : ctx->part_events) if (e) cudaEventDestroy(e);
@@ -1222,12 +1299,28 @@ int ht_debug_raw(ht_ctx *ctx, int frame, ht_rect *out, int cap, int32_t *count) 
   return HT_OK;
 }
 
-int ht_debug_track_stats(ht_ctx *ctx, uint64_t *out4, int reset) {
-  if (!ctx || !out4) return HT_ERR_ARG;
+int ht_set_track_memo(ht_ctx *ctx, int enable) {
+  if (!ctx) return HT_ERR_ARG;
+  ctx->track_memo = enable != 0;
+  return HT_OK;
+}
+
+int ht_debug_track_stats(ht_ctx *ctx, uint64_t *out5, int reset) {
+  if (!ctx || !out5) return HT_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy(out4, ctx->d_flags.as<unsigned long long>() + 8, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  if (reset) CK(cudaMemset(ctx->d_flags.as<unsigned long long>() + 8, 0, 4 * sizeof(uint64_t)));
+  CK(cudaMemcpy(out5, ctx->d_flags.as<unsigned long long>() + 8, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(ctx->d_flags.as<unsigned long long>() + 8, 0, 5 * sizeof(uint64_t)));
+  return HT_OK;
+}
+
+int ht_debug_track_trace(ht_ctx *ctx, uint64_t *out, int n) {
+  if (!ctx || !out) return HT_ERR_ARG;
+  if (!ctx->track_trace || !ctx->d_trace.p || n < 0 || n > ctx->cfg.max_frames)
+    return ctx->fail(HT_ERR_ARG, "track timeline is not enabled (HT_TRACK_TRACE=1 at ht_create) or n is out of range");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, ctx->d_trace.p, 4 * sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
   return HT_OK;
 }
 

@@ -173,6 +173,39 @@ __device__ __forceinline__ double warp_sum(double v) {
 // the chain of the streams with large windows, which otherwise set the kernel's duration.
 constexpr int TRACK_CLUSTER_MAX = 8;   // the cluster size is a launch-time choice (1, 2, 4 or 8 CTAs per stream)
 
+// Longest-chain-first launch order.  A stream's mean-shift passes form a serial chain whose length grows with its
+// search window, and a launch holds only a few hundred streams at a time, so the streams with the largest windows
+// are started first (and may be given a larger cluster): otherwise one of them starting in the last wave sets the
+// duration of the whole launch.  area[i] = search-window area of stream i; order = indices by descending area
+// (ties by index, so the order is deterministic).
+__global__ void k_track_area(const TrackState *__restrict__ state, const int32_t *__restrict__ slots, int n,
+                             int32_t *__restrict__ area) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const TrackState *s = state + (slots ? slots[i] : i);
+  long long a = s->initialised ? (long long)max(s->sw, 0) * (long long)max(s->sh, 0) : 0;
+  area[i] = (int32_t)min(a, (long long)0x7fffffff);
+}
+__global__ void k_track_rank(const int32_t *__restrict__ area, int n, int32_t *__restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t a = area[i];
+  int rank = 0;
+  for (int j = 0; j < n; ++j) {
+    const int32_t b = __ldg(area + j);
+    rank += (b > a || (b == a && j < i)) ? 1 : 0;
+  }
+  order[rank] = i;
+}
+
+// ld.shared.f64 from a 32-bit shared-window address (indexing the __shared__ array through its generic address
+// makes the compiler rebuild the cluster-window base, an S2R, for every access)
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+  return v;
+}
+
 __device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, const double *__restrict__ wsm, int lane,
                                             int wx, int xbeg, int xend, bool vec4, double &r0, double &r1, double &r2) {
   if (vec4) {
@@ -201,7 +234,7 @@ __device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, co
 }
 
 template <int TRACK_CLUSTER, int NT>
-__global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : (NT >= 512 ? 2 : 3))
+__global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : (NT >= 512 ? 2 : (NT >= 256 ? 3 : 6)))
 k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restrict__ slots,
         const uint32_t *__restrict__ model_hist, const uint32_t *__restrict__ cur_hist, TrackState *__restrict__ state,
         int n_calls, int32_t *__restrict__ out_objs /* 6 x i32 per frame */, int32_t *__restrict__ out_windows,
@@ -209,19 +242,34 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         // two-phase scheduling: phase A (one CTA per stream) hands streams whose search window outgrows
         // `bail_area` to phase B (a cluster per stream) through bail_list/calls_done
         int bail_area, int32_t *__restrict__ calls_done, int32_t *__restrict__ bail_list,
-        int32_t *__restrict__ bail_count, int use_list) {
+        int32_t *__restrict__ bail_count, int use_list,
+        // use_list == 2: the k-th cluster runs stream bail_list[list_off + k] (k_track_rank's order)
+        int list_off,
+        // optional timeline (HT_TRACK_TRACE=1): per stream {globaltimer at start, at end, SM id, passes}
+        unsigned long long *__restrict__ trace,
+        // memo != 0: moments are a pure function of (frame, weights, window) and all three are fixed for the calls of
+        // one launch, so the leader keeps the moments of the last windows it has seen and re-uses them when
+        // mean-shift returns to one of them (a converged stream, or one oscillating between two windows)
+        int memo) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  __shared__ double wsm[4096];
+  __shared__ double wsm[4096 + 1];   // [4096] = +0.0: the weight of pixels outside the window
   constexpr int NW = NT / 32;   // warps per CTA
   __shared__ double red[NW][6];
   __shared__ double cpart[TRACK_CLUSTER_MAX][6];  // used in rank 0: partial moments of every CTA of the cluster
   __shared__ int win[4];                          // wadx, wady, wadw, wadh (written by rank 0 into every CTA)
   __shared__ int ctrl;                            // 0 = run another pass over win[], 1 = this stream is finished
+  constexpr int MEMO_N = 8;
+  struct MemoEnt { int w[4]; int exact; int valid; Mom m; };
+  __shared__ MemoEnt memo_tab[MEMO_N];            // leader only
+  __shared__ int memo_next;
+  __shared__ unsigned long long st_memo_sh;
   const int crank = (int)cluster.block_rank();
   int k = blockIdx.x / TRACK_CLUSTER;
   int call0 = 0;
-  if (use_list) {                                 // phase B: k-th entry of the bail list (uniform over the cluster)
+  if (use_list == 2) {
+    k = bail_list[list_off + k];
+  } else if (use_list) {                          // phase B: k-th entry of the bail list (uniform over the cluster)
     if (k >= *bail_count) return;
     k = bail_list[k];
     call0 = calls_done[k];
@@ -229,7 +277,26 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   const int slot = slots ? slots[k] : k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool leader = (crank == 0 && tid == 0);
-  TrackState s = state[slot];
+  // The reference's loop state lives in shared memory: only the leader thread touches it after this point, and
+  // keeping it out of registers leaves them to the pipelined pass loop.
+  struct Lead { TrackState s; unsigned long long st_pass, st_serial, st_px; int call, it, prevx, prevy; bool bailed; };
+  __shared__ Lead lead_sh;
+  if (tid == 0) {
+    lead_sh.s = state[slot];
+    lead_sh.st_pass = lead_sh.st_serial = lead_sh.st_px = 0;
+    lead_sh.call = call0; lead_sh.it = 0; lead_sh.prevx = lead_sh.s.sx; lead_sh.prevy = lead_sh.s.sy;
+    lead_sh.bailed = false;
+    memo_next = 0; st_memo_sh = 0;
+    for (int i = 0; i < MEMO_N; ++i) memo_tab[i].valid = 0;
+  }
+  __syncthreads();
+  TrackState &s = lead_sh.s;
+  if (trace && leader) {
+    unsigned long long t; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace[4 * (size_t)k] = t; trace[4 * (size_t)k + 2] = smid;
+  }
   if (!s.initialised) {   // uniform over the cluster
     if (leader) {
       atomicOr(err_flag, 1);
@@ -248,15 +315,16 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
       if (c != 0) p = fmin((double)mh[i] / (double)c, 1.0);
       wsm[i] = p;
     }
+    if (tid == 0) wsm[4096] = 0.0;
   }
   const uint16_t *px = bins + (size_t)k * W * H;   // 12-bit colour bin of every pixel of this slot's frame (k_hist)
   const bool vec4 = (W & 3) == 0;
   double *cpart0 = cluster.map_shared_rank(&cpart[0][0], 0);
 
   // leader-only bookkeeping of the reference's loops (src/camshift.js:213-312)
-  unsigned long long st_pass = 0, st_serial = 0, st_px = 0;
-  int call = call0, it = 0, prevx = s.sx, prevy = s.sy;
-  bool bailed = false;
+  unsigned long long &st_pass = lead_sh.st_pass, &st_serial = lead_sh.st_serial, &st_px = lead_sh.st_px;
+  int &call = lead_sh.call, &it = lead_sh.it, &prevx = lead_sh.prevx, &prevy = lead_sh.prevy;
+  bool &bailed = lead_sh.bailed;
   auto publish = [&](int done) {   // leader: next window (or the finish flag) into every CTA of the cluster
     const int w0 = max(s.sx, 0), w1 = max(s.sy, 0);                // :286-289
     const int w2 = min(w0 + s.sw, W), w3 = min(w1 + s.sh, H);
@@ -279,55 +347,83 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   constexpr int ROW_STRIDE = NW * TRACK_CLUSTER;
   while (!ctrl) {
     const int wx = win[0], wy = win[1], ww = win[2] - win[0], wh = win[3] - win[1];
-    // Each lane reads 4 adjacent pixels (one 8 B load of 4 colour bins).  Per row: r0 = sum v,
-    // r1 = sum vx v, r2 = sum vx^2 v; the vy factors are applied once per row.  Rows are assigned by
-    // ABSOLUTE frame row (a CTA keeps hitting its own L1 lines when the window shifts between passes) and
-    // processed four at a time: four loads in flight feeding 12 independent accumulation chains.
+    // Each lane reads 4 adjacent pixels (one 8 B load of 4 colour bins) of 4 rows per step.  Rows are assigned by
+    // ABSOLUTE frame row (a CTA keeps hitting its own L1 lines when the window shifts between passes).  The steps of
+    // a pass (row group x 128-pixel column block) are software-pipelined: the four loads of step t+1 are issued
+    // before the arithmetic of step t, so a pass exposes one L2 latency instead of one per step (a pass is a short
+    // serial chain: 3-25 steps per thread).  Per step and row: r0 = sum v, r1 = sum vx v; the vy factors are
+    // applied once per row and step.
     double a00 = 0, a10 = 0, a01 = 0, a11 = 0, a20 = 0, a02 = 0;
     const int xbeg = wx & ~3, xend = wx + ww;
-    {
-      const int mine = crank * NW + warp;                        // rows with (wy+yy) % ROW_STRIDE == mine
-      int yy = (mine - (wy % ROW_STRIDE) + ROW_STRIDE) % ROW_STRIDE;
-      for (; yy < wh; yy += 4 * ROW_STRIDE) {
+    const int mine = crank * NW + warp;                          // rows with (wy+yy) % ROW_STRIDE == mine
+    const int yy0 = (mine - (wy % ROW_STRIDE) + ROW_STRIDE) % ROW_STRIDE;
+    if (vec4) {
+      const int n_x = (xend - xbeg + 127) >> 7;
+      const int n_rg = (yy0 < wh) ? (wh - yy0 + 4 * ROW_STRIDE - 1) / (4 * ROW_STRIDE) : 0;
+      const int total = n_rg * n_x;
+      const uint16_t *col = px + (size_t)wy * W + xbeg + 4 * lane;
+      const uint32_t wsm_base = (uint32_t)__cvta_generic_to_shared(wsm);
+      auto issue = [&](int rg, int xi, uint2 (&v)[4]) {
+        const int x4 = xbeg + 4 * lane + 128 * xi;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int y = yy0 + (4 * rg + j) * ROW_STRIDE;
+          v[j] = (y < wh && x4 < xend) ? __ldg(reinterpret_cast<const uint2 *>(col + (size_t)y * W + 128 * xi)) : make_uint2(0, 0);
+        }
+      };
+      auto consume = [&](int rg, int xi, const uint2 (&v)[4]) {
+        const int x4 = xbeg + 4 * lane + 128 * xi;
+        double vx[4], vx2[4];
+        bool in[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int x = x4 + i;
+          in[i] = (x >= wx && x < xend);
+          vx[i] = (double)(x - wx);
+          vx2[i] = vx[i] * vx[i];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int y = yy0 + (4 * rg + j) * ROW_STRIDE;
+          const bool rowok = y < wh;
+          const uint32_t b[4] = {v[j].x & 0xffffu, v[j].x >> 16, v[j].y & 0xffffu, v[j].y >> 16};
+          double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // pixels outside the window read the extra table entry wsm[4096] == +0.0, which leaves the sums unchanged
+            const double val = lds_f64(wsm_base + 8u * ((in[i] && rowok) ? b[i] : 4096u));
+            r0 += val;
+            r1 = fma(vx[i], val, r1);     // fused: this fast path is validated by trunc_ambiguous, the strict
+            r2 = fma(vx2[i], val, r2);    // reference order (separate multiply and add) is moments_serial
+          }
+          const double vy = (double)y;
+          a00 += r0; a10 += r1; a20 += r2;
+          a01 = fma(vy, r0, a01); a11 = fma(vy, r1, a11); a02 = fma(vy * vy, r0, a02);
+        }
+      };
+      uint2 va[4], vb[4];
+      int rg = 0, xi = 0;
+      if (total > 0) issue(0, 0, va);
+      for (int t = 0; t < total; t += 2) {
+        int rg1 = rg, xi1 = xi + 1;
+        if (xi1 == n_x) { xi1 = 0; ++rg1; }
+        if (t + 1 < total) issue(rg1, xi1, vb);
+        consume(rg, xi, va);
+        int rg2 = rg1, xi2 = xi1 + 1;
+        if (xi2 == n_x) { xi2 = 0; ++rg2; }
+        if (t + 2 < total) issue(rg2, xi2, va);
+        if (t + 1 < total) consume(rg1, xi1, vb);
+        rg = rg2; xi = xi2;
+      }
+    } else {
+      for (int yy = yy0; yy < wh; yy += 4 * ROW_STRIDE) {
         double r[4][3];
 #pragma unroll
         for (int j = 0; j < 4; ++j) r[j][0] = r[j][1] = r[j][2] = 0.0;
-        if (vec4) {
-          for (int x4 = xbeg + 4 * lane; x4 < xend; x4 += 128) {
-            uint2 v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int y = yy + j * ROW_STRIDE;
-              v[j] = (y < wh) ? __ldg(reinterpret_cast<const uint2 *>(px + (size_t)(wy + y) * W + x4)) : make_uint2(0, 0);
-            }
-            double vx[4], vx2[4];
-            bool in[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int x = x4 + i;
-              in[i] = (x >= wx && x < xend);
-              vx[i] = (double)(x - wx);
-              vx2[i] = vx[i] * vx[i];
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const bool rowok = (yy + j * ROW_STRIDE) < wh;
-              const uint32_t b[4] = {v[j].x & 0xffffu, v[j].x >> 16, v[j].y & 0xffffu, v[j].y >> 16};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const double val = (in[i] && rowok) ? wsm[b[i]] : 0.0;   // +0.0 terms leave the sums unchanged
-                r[j][0] += val;
-                r[j][1] += vx[i] * val;
-                r[j][2] += vx2[i] * val;
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int y = yy + j * ROW_STRIDE;
-            if (y < wh) row_partial(px + (size_t)(wy + y) * W, wsm, lane, wx, xbeg, xend, false, r[j][0], r[j][1], r[j][2]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int y = yy + j * ROW_STRIDE;
+          if (y < wh) row_partial(px + (size_t)(wy + y) * W, wsm, lane, wx, xbeg, xend, false, r[j][0], r[j][1], r[j][2]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -356,71 +452,98 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         m.m00 += cpart[r][0]; m.m10 += cpart[r][1]; m.m01 += cpart[r][2];
         m.m11 += cpart[r][3]; m.m20 += cpart[r][4]; m.m02 += cpart[r][5];
       }
-      bool exact = false;
+      bool exact = false;          // m is in the reference's strict summation order (moments_serial)
+      bool fresh = true;           // m was computed by this pass (false: taken from the memo)
+      int cw0 = win[0], cw1 = win[1], cw2 = win[2], cw3 = win[3];   // the window m belongs to
       ++st_pass;
       st_px += (unsigned long long)(max(ww, 0)) * (unsigned long long)(max(wh, 0));
-      double inv = 1.0 / m.m00;                                    // :109-111
-      double vxf = m.m10 * inv - s.sw / 2.0, vyf = m.m01 * inv - s.sh / 2.0;
-      if (trunc_ambiguous(vxf) || trunc_ambiguous(vyf)) {
-        m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm);
-        exact = true;
-        ++st_serial;
-        inv = 1.0 / m.m00;
-        vxf = m.m10 * inv - s.sw / 2.0;
-        vyf = m.m01 * inv - s.sh / 2.0;
-      }
-      s.sx += js_to_int32(vxf);                                    // :295-296
-      s.sy += js_to_int32(vyf);
-      const bool conv = (s.sx == prevx && s.sy == prevy);         // :299
-      bool done = false;
-      if (conv || it == 9) {
-        // final moments (second == true) are those of this window; make the <<2 truncations safe
-        if (!exact) {
-          const double xc = m.m10 * inv, yc = m.m01 * inv;
-          const double a = (m.m20 - m.m10 * xc) * inv, c = (m.m02 - m.m01 * yc) * inv;
-          bool amb;
-          if (s.calc_angles) {
-            const double b = (m.m11 - m.m01 * xc) * inv, d = a + c;
-            const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
-            amb = trunc_ambiguous(sqrt((d - e) * 0.5)) || trunc_ambiguous(sqrt((d + e) * 0.5));
-          } else {
-            amb = trunc_ambiguous(sqrt(a)) || trunc_ambiguous(sqrt(c));
+      for (;;) {
+        double inv = 1.0 / m.m00;                                    // :109-111
+        double vxf = m.m10 * inv - s.sw / 2.0, vyf = m.m01 * inv - s.sh / 2.0;
+        if (!exact && (trunc_ambiguous(vxf) || trunc_ambiguous(vyf))) {
+          m = moments_serial(px, W, cw0, cw1, cw2, cw3, wsm);
+          exact = true;
+          ++st_serial;
+          inv = 1.0 / m.m00;
+          vxf = m.m10 * inv - s.sw / 2.0;
+          vyf = m.m01 * inv - s.sh / 2.0;
+        }
+        s.sx += js_to_int32(vxf);                                    // :295-296
+        s.sy += js_to_int32(vyf);
+        const bool conv = (s.sx == prevx && s.sy == prevy);         // :299
+        bool done = false;
+        if (conv || it == 9) {
+          // final moments (second == true) are those of this window; make the <<2 truncations safe
+          if (!exact) {
+            const double xc = m.m10 * inv, yc = m.m01 * inv;
+            const double a = (m.m20 - m.m10 * xc) * inv, c = (m.m02 - m.m01 * yc) * inv;
+            bool amb;
+            if (s.calc_angles) {
+              const double b = (m.m11 - m.m01 * xc) * inv, d = a + c;
+              const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
+              amb = trunc_ambiguous(sqrt((d - e) * 0.5)) || trunc_ambiguous(sqrt((d + e) * 0.5));
+            } else {
+              amb = trunc_ambiguous(sqrt(a)) || trunc_ambiguous(sqrt(c));
+            }
+            if (amb) { m = moments_serial(px, W, cw0, cw1, cw2, cw3, wsm); exact = true; ++st_serial; }
           }
-          if (amb) { m = moments_serial(px, W, win[0], win[1], win[2], win[3], wsm); ++st_serial; }
-        }
-        s.sx = max(0, min(s.sx, W));                                   // :308-309
-        s.sy = max(0, min(s.sy, H));
-        // camShift epilogue — src/camshift.js:230-258
-        const double invM00 = 1.0 / m.m00;
-        const double xc = m.m10 * invM00, yc = m.m01 * invM00;
-        const double mu20 = m.m20 - m.m10 * xc, mu02 = m.m02 - m.m01 * yc, mu11 = m.m11 - m.m01 * xc;
-        const double a = mu20 * invM00, c = mu02 * invM00;
-        if (s.calc_angles) {
-          const double b = mu11 * invM00;
-          const double d = a + c;
-          const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
-          s.tw = (int32_t)((uint32_t)js_to_int32(sqrt((d - e) * 0.5)) << 2);
-          s.th = (int32_t)((uint32_t)js_to_int32(sqrt((d + e) * 0.5)) << 2);
-          double ang = atan2(2 * b, a - c + e);
-          if (ang < 0) ang = ang + 3.141592653589793;
-          s.angle = ang;
+          s.sx = max(0, min(s.sx, W));                                   // :308-309
+          s.sy = max(0, min(s.sy, H));
+          // camShift epilogue — src/camshift.js:230-258
+          const double invM00 = 1.0 / m.m00;
+          const double xc = m.m10 * invM00, yc = m.m01 * invM00;
+          const double mu20 = m.m20 - m.m10 * xc, mu02 = m.m02 - m.m01 * yc, mu11 = m.m11 - m.m01 * xc;
+          const double a = mu20 * invM00, c = mu02 * invM00;
+          if (s.calc_angles) {
+            const double b = mu11 * invM00;
+            const double d = a + c;
+            const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
+            s.tw = (int32_t)((uint32_t)js_to_int32(sqrt((d - e) * 0.5)) << 2);
+            s.th = (int32_t)((uint32_t)js_to_int32(sqrt((d + e) * 0.5)) << 2);
+            double ang = atan2(2 * b, a - c + e);
+            if (ang < 0) ang = ang + 3.141592653589793;
+            s.angle = ang;
+          } else {
+            s.tw = (int32_t)((uint32_t)js_to_int32(sqrt(a)) << 2);
+            s.th = (int32_t)((uint32_t)js_to_int32(sqrt(c)) << 2);
+            s.angle = 3.141592653589793 / 2;
+          }
+          s.tx = (int32_t)floor(fmax(0.0, fmin(s.sx + s.sw / 2.0, (double)W)));   // :253-254
+          s.ty = (int32_t)floor(fmax(0.0, fmin(s.sy + s.sh / 2.0, (double)H)));
+          s.sw = (int32_t)floor(1.1 * s.tw);                             // :257-258
+          s.sh = (int32_t)floor(1.1 * s.th);
+          ++call;
+          done = start_call();
         } else {
-          s.tw = (int32_t)((uint32_t)js_to_int32(sqrt(a)) << 2);
-          s.th = (int32_t)((uint32_t)js_to_int32(sqrt(c)) << 2);
-          s.angle = 3.141592653589793 / 2;
+          prevx = s.sx;
+          prevy = s.sy;
+          ++it;
         }
-        s.tx = (int32_t)floor(fmax(0.0, fmin(s.sx + s.sw / 2.0, (double)W)));   // :253-254
-        s.ty = (int32_t)floor(fmax(0.0, fmin(s.sy + s.sh / 2.0, (double)H)));
-        s.sw = (int32_t)floor(1.1 * s.tw);                             // :257-258
-        s.sh = (int32_t)floor(1.1 * s.th);
-        ++call;
-        done = start_call();
-      } else {
-        prevx = s.sx;
-        prevy = s.sy;
-        ++it;
+        if (memo && fresh) {        // remember this window's moments (the strict ones if they had to be computed)
+          MemoEnt &e = memo_tab[memo_next];
+          memo_next = (memo_next + 1) % MEMO_N;
+          e.w[0] = cw0; e.w[1] = cw1; e.w[2] = cw2; e.w[3] = cw3;
+          e.exact = exact ? 1 : 0; e.m = m; e.valid = 1;
+        }
+        if (done) { publish(1); break; }
+        if (memo) {                 // the next window (src/camshift.js:286-289) may be one whose moments are known
+          const int n0 = max(s.sx, 0), n1 = max(s.sy, 0);
+          const int n2 = min(n0 + s.sw, W), n3 = min(n1 + s.sh, H);
+          int hit = -1;
+          for (int i = 0; i < MEMO_N; ++i) {
+            const MemoEnt &e = memo_tab[i];
+            if (e.valid && e.w[0] == n0 && e.w[1] == n1 && e.w[2] == n2 && e.w[3] == n3) hit = i;
+          }
+          if (hit >= 0) {
+            m = memo_tab[hit].m; exact = memo_tab[hit].exact != 0; fresh = false;
+            cw0 = n0; cw1 = n1; cw2 = n2; cw3 = n3;
+            ++st_memo_sh;
+            continue;
+          }
+        }
+        publish(0);
+        break;
       }
-      publish(done ? 1 : 0);
     }
     if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
   }
@@ -428,8 +551,14 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
     if (stats) {
       atomicAdd(&stats[0], st_pass); atomicAdd(&stats[1], st_serial);
       atomicAdd(&stats[2], st_px); atomicAdd(&stats[3], (unsigned long long)(call - call0));
+      atomicAdd(&stats[4], st_memo_sh);
     }
     state[slot] = s;
+    if (trace) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace[4 * (size_t)k + 1] = t; trace[4 * (size_t)k + 3] = st_pass;
+    }
     if (bailed) {   // phase B continues this stream from call `call`
       calls_done[k] = call;
       bail_list[atomicAdd(bail_count, 1)] = k;

@@ -149,9 +149,19 @@ int ht_debug_plane(ht_ctx *ctx, int frame, int slot, int q, uint8_t *out, int ca
 int ht_debug_raw(ht_ctx *ctx, int frame, ht_rect *out, int cap, int32_t *count);
 /* tracker slot state: model histogram (4096 u32, optional) */
 int ht_debug_model_hist(ht_ctx *ctx, int slot, uint32_t *out4096);
-/* mean-shift counters since the last reset: {moment passes, passes redone in strict reference order,
- * window pixels visited, track() calls} */
-int ht_debug_track_stats(ht_ctx *ctx, uint64_t *out4, int reset);
+/* mean-shift counters since the last reset: {moment passes summed on the device, passes redone in strict reference
+ * order, window pixels visited, track() calls, passes answered from the per-launch window memo} */
+int ht_debug_track_stats(ht_ctx *ctx, uint64_t *out5, int reset);
+/* Window memo of ht_track / ht_detect_track (default on).  The moments of a search window depend only on the frame,
+ * the histogram weights and the window, and all three are fixed for the n_calls track() calls of one launch; the
+ * kernel therefore keeps the moments of the last 8 windows of a stream and re-uses them when mean-shift comes back
+ * to one of them (a converged stream; a stream oscillating between two windows - src/camshift.js:283-306 would
+ * re-sum them).  Results are identical either way; enable = 0 re-sums every pass like the reference. */
+int ht_set_track_memo(ht_ctx *ctx, int enable);
+/* per-stream timeline of the last ht_track / ht_detect_track launch, 4 x u64 per stream: {globaltimer ns at start,
+ * at end, SM id of the leading CTA, moment passes}.  Only for contexts created with HT_TRACK_TRACE=1 in the
+ * environment (tools/track_timeline.py); HT_ERR_ARG otherwise. */
+int ht_debug_track_trace(ht_ctx *ctx, uint64_t *out, int n_streams);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ht_launch_count(const ht_ctx *ctx);
 

@@ -180,3 +180,55 @@ def test_track_odd_width_scalar_path(ctx, blob):
     want = ot.track_obj()
     assert (objs[0]["x"], objs[0]["y"], objs[0]["width"], objs[0]["height"]) == (want["x"], want["y"], want["width"], want["height"])
     assert abs(objs[0]["angle"] - want["angle"]) <= 1e-4 and wins[0] == ot.search_window()
+
+
+@pytest.mark.parametrize("env", [{}, {"HT_TRACK_HEAVY": "8"}, {"HT_TRACK_NT": "128", "HT_TRACK_HEAVY": "4,4"},
+                                 {"HT_TRACK_LPT": "0"}, {"HT_TRACK_MEMO": "0"}])
+def test_scheduled_launch_orders_do_not_change_results(blob, env, monkeypatch):
+    """>= 128 streams: k_track runs the streams longest-window-first (optionally the largest ones on a bigger cluster
+    on a second stream).  The schedule must not change any stream's result."""
+    from headtrackr_b200 import Context
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    W, H, U, N = 320, 240, 16, 144
+    uniq = synth.batch(U, W, H, start=900)
+    want = [oracle.detect_track(uniq[i], blob, n_calls=6) for i in range(U)]
+    frames = np.stack([uniq[i % U] for i in range(N)])
+    c = Context(max_width=W, max_height=H, max_frames=N)
+    try:
+        for _ in range(2):
+            dets, found, objs, wins = c.detect_track(frames, 5, 1, calc_angles=False, n_calls=6)
+            for i in range(N):
+                n_det, fnd, obj = want[i % U]
+                assert len(dets[i]) == n_det and found[i] == fnd
+                if fnd:
+                    assert (objs[i]["x"], objs[i]["y"], objs[i]["width"], objs[i]["height"]) == \
+                        (obj["x"], obj["y"], obj["width"], obj["height"])
+    finally:
+        c.close()
+
+
+def test_window_memo_does_not_change_results(ctx, blob):
+    """30 track() calls on one frame: with the window memo the kernel sums far fewer passes, and every output is
+    identical to the strict run and to the oracle."""
+    frames = synth.batch(6, 640, 480, start=56)
+    want = [oracle.detect_track(frames[i], blob, n_calls=30) for i in range(6)]
+    runs = {}
+    try:
+        for memo in (False, True):
+            ctx.set_track_memo(memo)
+            ctx.debug_track_stats(reset=True)
+            dets, found, objs, wins = ctx.detect_track(frames, 5, 1, calc_angles=False, n_calls=30)
+            runs[memo] = (found, objs, wins, ctx.debug_track_stats(reset=True))
+    finally:
+        ctx.set_track_memo(True)
+    assert runs[False][:3] == runs[True][:3]
+    strict, memo = runs[False][3], runs[True][3]
+    assert strict["memo_hits"] == 0 and memo["memo_hits"] > 0
+    assert memo["passes"] + memo["memo_hits"] == strict["passes"] and memo["calls"] == strict["calls"]
+    for i in range(6):
+        n_det, fnd, obj = want[i]
+        assert runs[True][0][i] == fnd
+        if fnd:
+            o = runs[True][1][i]
+            assert (o["x"], o["y"], o["width"], o["height"]) == (obj["x"], obj["y"], obj["width"], obj["height"])
