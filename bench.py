@@ -196,6 +196,11 @@ def run_ours(args, W, H, track_calls, workload):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Headline = strict: every mean-shift pass of every track() call is summed on the device, as the reference does.
+    # The library's default additionally re-uses the moments of windows it has already summed within a launch
+    # (ht_set_track_memo) - identical results, far fewer passes when 30 calls hit one frame; that
+    # mode is measured separately below and reported under "memo", never as the headline.
+    ctx.set_track_memo(False)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -252,6 +257,44 @@ def run_ours(args, W, H, track_calls, workload):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * B * e2e_steps / e2e_s
+
+    # ---- library default (window memo on): same steps, device-resident and e2e ----
+    memo = None
+    if workload != "detect":
+        ctx.set_track_memo(True)
+        step()
+        barrier()
+        ctx.debug_track_stats(reset=True)
+        ctx.profile(True)
+        ctx.profile_read(reset=True)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        for _ in range(args.steps):
+            step()
+        m1.record(stream)
+        barrier()
+        memo_ms = m0.elapsed_time(m1)
+        memo_prof = ctx.profile_read(reset=True)
+        ctx.profile(False)
+        memo_stats = ctx.debug_track_stats(reset=True)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        memo_e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([memo_ms, memo_e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            memo_ms, memo_e2e_s = float(t[0].item()), float(t[1].item())
+        memo = {"value": world * B * args.steps / (memo_ms / 1e3), "ms_per_step": memo_ms / args.steps,
+                "e2e_value": world * B * e2e_steps / memo_e2e_s,
+                "track_ms_per_step": round(memo_prof["track"][0] / args.steps, 4),
+                "track_stats": memo_stats,
+                "note": "library default: moments of windows already summed in the same launch are re-used "
+                        "(identical results; the headline above re-sums every pass)"}
+        ctx.set_track_memo(False)
     h2d = B * H * W * 4
     d2h = h_rects.numel() * 8 + h_counts.numel() * 4 + (0 if workload == "detect" else (h_found.numel() + h_objs.numel() + h_wins.numel()) * 4)
 
@@ -268,7 +311,7 @@ def run_ours(args, W, H, track_calls, workload):
                 "config": {"workload": workload, "frame": f"{W}x{H}", "frames_per_gpu_per_step": B, "interval": 5,
                            "min_neighbors": 1, "track_calls_per_frame": track_calls, "sharding": f"frames dp{world}",
                            "l2": f"inputs larger than L2 ({B * W * H * 4 / 1e6:.0f} MB of frames per GPU per step)",
-                           "unique_frames": N_UNIQUE},
+                           "unique_frames": N_UNIQUE, "track_memo": "off (strict: every pass re-summed)"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps},
                 "gpu_launches": int(launches),
@@ -284,6 +327,8 @@ def run_ours(args, W, H, track_calls, workload):
                 "kernel_ms_per_step": kernel_ms,
                 "track_stats": track_stats,
                 "clocks": clocks}
+        if memo is not None:
+            line["memo"] = memo
         if world == 1 and not args.no_cpu_baseline:
             blob = synth.load_cascade_blob()
             sample = base if args.cpu_sample <= N_UNIQUE else make_base_frames(W, H, 0, args.cpu_sample)

@@ -82,23 +82,36 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
   }
   const uint32_t Dy = 2u * (uint32_t)dh;
   const uint8_t *src = frame + src_off;
-  uint8_t *dst = frame + dst_off + (size_t)Y0 * dst_pitch + X;
+  // All 16 source bytes of the thread's 4 rows are requested before any arithmetic (one exposed memory latency per
+  // thread instead of four); rows below the painted area read row taps {0, 0} and are zeroed afterwards, so the
+  // loads need no branches.  Offsets inside a plane fit 32 bits.
+  uint32_t oa[4], ob[4], wy1[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int Y = Y0 + r;
+    uint2 ry = make_uint2(0u, 0u);
+    if (Y < dh) ry = __ldg(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // warp-uniform
+    oa[r] = (ry.x & 0xffffu) * (uint32_t)src_pitch;
+    ob[r] = (ry.x >> 16) * (uint32_t)src_pitch;
+    wy1[r] = ry.y & 0xffffu;
+  }
+  uint32_t p[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    p[r][0] = src[oa[r] + xa]; p[r][1] = src[oa[r] + xb];
+    p[r][2] = src[ob[r] + xa]; p[r][3] = src[ob[r] + xb];
+  }
+  uint8_t *dst = frame + dst_off + (uint32_t)Y0 * (uint32_t)dst_pitch + (uint32_t)X;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int Y = Y0 + r;
     if (Y >= dst_h) break;
-    uint32_t q = 0;
-    if (col_ok && Y < dh) {
-      const uint2 ry = __ldg(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // warp-uniform
-      const uint8_t *ra = src + (size_t)(ry.x & 0xffffu) * src_pitch;
-      const uint8_t *rb = src + (size_t)(ry.x >> 16) * src_pitch;
-      const uint32_t wy1 = ry.y & 0xffffu, wy0 = Dy - wy1;
-      const uint32_t top = wx0 * ra[xa] + wx1 * ra[xb];   // <= 255 * 2dw
-      const uint32_t bot = wx0 * rb[xa] + wx1 * rb[xb];
-      const uint32_t num = top * wy0 + bot * wy1 + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
-      q = (uint32_t)(((uint64_t)num * magic) >> shift);
-    }
-    dst[(size_t)r * dst_pitch] = (uint8_t)q;              // unpainted columns / rows and the pitch padding are 0
+    const uint32_t top = wx0 * p[r][0] + wx1 * p[r][1];   // <= 255 * 2dw
+    const uint32_t bot = wx0 * p[r][2] + wx1 * p[r][3];
+    const uint32_t num = top * (Dy - wy1[r]) + bot * wy1[r] + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
+    uint32_t q = (uint32_t)(((uint64_t)num * magic) >> shift);
+    if (!col_ok || Y >= dh) q = 0;                        // unpainted columns / rows and the pitch padding are 0
+    dst[(uint32_t)r * (uint32_t)dst_pitch] = (uint8_t)q;
   }
 }
 

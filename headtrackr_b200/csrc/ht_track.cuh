@@ -18,7 +18,8 @@ __device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:6
 
 // ------------------------------------------------------------------------------------------------
 // K1'  4096-bin RGB histogram of whole frames — src/camshift.js:49-72 via :268 — plus the per-pixel
-// 12-bit bin plane (u16) that k_track's window passes read instead of re-decoding RGBA (half the bytes).
+// bin plane (u16) that k_track's window passes read instead of re-decoding RGBA (half the bytes).  The plane
+// holds 8 * bin: the byte offset of the pixel's weight in k_track's fp64 table (8 * 4095 < 2^16).
 // grid = (chunks, n_frames).  Shared-memory histogram per CTA, flushed to hist[frame][4096].
 __global__ void __launch_bounds__(256) k_hist(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_px,
                                               uint32_t *__restrict__ hist, uint16_t *__restrict__ bins, int chunks) {
@@ -37,11 +38,11 @@ __global__ void __launch_bounds__(256) k_hist(const uint8_t *__restrict__ rgba, 
       const uint32_t b0 = rgb_bin(v.x), b1 = rgb_bin(v.y);
       atomicAdd(&sh[b0], 1u);
       atomicAdd(&sh[b1], 1u);
-      if (bout) *reinterpret_cast<uint32_t *>(bout + p0) = b0 | (b1 << 16);
+      if (bout) *reinterpret_cast<uint32_t *>(bout + p0) = (b0 << 3) | (b1 << 19);
     } else {
       const uint32_t b0 = rgb_bin(__ldg(px + p0));
       atomicAdd(&sh[b0], 1u);
-      if (bout) bout[p0] = (uint16_t)b0;
+      if (bout) bout[p0] = (uint16_t)(b0 << 3);
     }
   }
   __syncthreads();
@@ -148,7 +149,7 @@ __device__ __noinline__ Mom moments_serial(const uint16_t *__restrict__ px, int 
   for (int i = x; i < w; ++i) {
     const double vx = (double)(i - x);
     for (int j = y; j < h; ++j) {
-      const double val = wsm[px[(size_t)j * W + i]];
+      const double val = wsm[px[(size_t)j * W + i] >> 3];
       const double vy = (double)(j - y);
       m.m00 += val;
       m.m01 += vy * val;
@@ -211,7 +212,7 @@ __device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, co
   if (vec4) {
     for (int x4 = xbeg + 4 * lane; x4 < xend; x4 += 128) {
       const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row + x4));
-      const uint32_t b[4] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16};
+      const uint32_t b[4] = {(v.x & 0xffffu) >> 3, v.x >> 19, (v.y & 0xffffu) >> 3, v.y >> 19};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int x = x4 + i;
@@ -224,7 +225,7 @@ __device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, co
     }
   } else {
     for (int x = wx + lane; x < xend; x += 32) {
-      const double val = wsm[row[x]];
+      const double val = wsm[row[x] >> 3];
       const double vx = (double)(x - wx);
       r0 += val;
       r1 += vx * val;
@@ -363,12 +364,14 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
       const int total = n_rg * n_x;
       const uint16_t *col = px + (size_t)wy * W + xbeg + 4 * lane;
       const uint32_t wsm_base = (uint32_t)__cvta_generic_to_shared(wsm);
+      constexpr uint32_t ZERO_W = 8u * 4096u;   // byte offset of wsm[4096]
       auto issue = [&](int rg, int xi, uint2 (&v)[4]) {
         const int x4 = xbeg + 4 * lane + 128 * xi;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int y = yy0 + (4 * rg + j) * ROW_STRIDE;
-          v[j] = (y < wh && x4 < xend) ? __ldg(reinterpret_cast<const uint2 *>(col + (size_t)y * W + 128 * xi)) : make_uint2(0, 0);
+          v[j] = (y < wh && x4 < xend) ? __ldg(reinterpret_cast<const uint2 *>(col + (size_t)y * W + 128 * xi))
+                                       : make_uint2(ZERO_W | (ZERO_W << 16), ZERO_W | (ZERO_W << 16));
         }
       };
       auto consume = [&](int rg, int xi, const uint2 (&v)[4]) {
@@ -385,13 +388,13 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int y = yy0 + (4 * rg + j) * ROW_STRIDE;
-          const bool rowok = y < wh;
+          // table offsets (the plane holds 8 * bin); rows below the window were "loaded" as ZERO_W by issue()
           const uint32_t b[4] = {v[j].x & 0xffffu, v[j].x >> 16, v[j].y & 0xffffu, v[j].y >> 16};
           double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             // pixels outside the window read the extra table entry wsm[4096] == +0.0, which leaves the sums unchanged
-            const double val = lds_f64(wsm_base + 8u * ((in[i] && rowok) ? b[i] : 4096u));
+            const double val = lds_f64(wsm_base + (in[i] ? b[i] : ZERO_W));
             r0 += val;
             r1 = fma(vx[i], val, r1);     // fused: this fast path is validated by trunc_ambiguous, the strict
             r2 = fma(vx2[i], val, r2);    // reference order (separate multiply and add) is moments_serial
