@@ -408,12 +408,21 @@ __global__ void __launch_bounds__(CASCADE_THREADS, MINB) k_cascade(DevPlan plan,
     if (__any_sync(0xffffffffu, alive)) alive = gen_stage##B(win, sum) && alive; \
     return alive;                                                           \
   }
-    compact(run_dense(false, HT_GEN_PAIR(0, 1)));
-    if (total_s == 0) return;
 #define HT_GEN_ONE(A)                                                       \
   [&](const uint8_t *win, bool alive, double &sum) { return alive && gen_stage##A(win, sum); }
 #ifndef HT_SPLIT_GROUPS
 #define HT_SPLIT_GROUPS 1
+#endif
+#if HT_SPLIT_GROUPS >= 3   // stage 1 on compacted lists (43 % of the windows survive stage 0): measured SLOWER, 12.0 vs
+                           // 11.4 ms per 1024 frames - the extra compaction of ~880 survivors per tile costs more
+                           // than the 16 % of shared-memory wavefronts it saves
+    compact(run_dense(false, HT_GEN_ONE(0)));
+    if (total_s == 0) return;
+    compact(run_lists(false, HT_GEN_ONE(1)));
+    if (total_s == 0) return;
+#else
+    compact(run_dense(false, HT_GEN_PAIR(0, 1)));
+    if (total_s == 0) return;
 #endif
 #if HT_SPLIT_GROUPS >= 1   // stages 2 and 3 as separate groups: stage 3 (91 loads) runs on re-compacted lists
     compact(run_lists(false, HT_GEN_ONE(2)));
