@@ -409,7 +409,12 @@ struct ht_ctx {
   cudaStream_t aux_stream = nullptr;        // tracking of part p overlaps the detection of part p+1 (ht_detect_track)
   cudaEvent_t aux_done = nullptr, part_events[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned part_seq = 0;
-  bool overlap_track = false;               // HT_OVERLAP=1 enables (measured slower: 24.4-26.7 vs 22.3 ms per step)
+  // Tracking of part p on a second stream while part p+1 is uploaded / detected (ht_detect_track).  Default (-1):
+  // only for HOST frames, where the batch arrives at PCIe speed and the GPU has idle time to fill - measured e2e
+  // 37.6k vs 33.0k frames/s with 4 parts (8 parts 36.8k, 16 parts 28.6k).  For device-resident frames it was
+  // measured slower (24.4-26.7 vs 22.3 ms per step) and stays off.  HT_OVERLAP=0 disables, HT_OVERLAP=<parts> forces.
+  int overlap_track = -1;
+  int overlap_parts = 0;
   cudaStream_t copy_stream = nullptr;       // H2D staging stream of ht_detect_track
   cudaEvent_t compute_done = nullptr;
   std::vector<cudaEvent_t> chunk_events;
@@ -863,7 +868,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
     }
   }
   if (const char *mb = getenv("HT_CASC_MINB")) c->casc_minb = atoi(mb);
-  if (const char *ov = getenv("HT_OVERLAP")) c->overlap_track = atoi(ov) != 0;
+  if (const char *ov = getenv("HT_OVERLAP")) { c->overlap_track = atoi(ov) != 0 ? 1 : 0; c->overlap_parts = atoi(ov); }
   if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
   if (const char *hc2 = getenv("HT_H2D_CHUNK")) c->h2d_chunk = std::max(1, atoi(hc2));
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
@@ -1082,8 +1087,9 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   // runs on a second stream while part p+1 is being detected.
   // (Tracking host-frame parts on the main stream as their chunks arrive was also measured: e2e 27.3k vs 33.6k fps
   // for one k_track over the whole batch — every k_track launch costs at least its slowest stream.)
-  const bool use_aux = (n_calls > 0 && ctx->overlap_track);
-  const int parts = use_aux ? ((n >= 512) ? 4 : (n >= 128 ? 2 : 1)) : 1;
+  const bool use_aux = n_calls > 0 && (ctx->overlap_track > 0 || (ctx->overlap_track < 0 && !is_device_ptr(rgba)));
+  int parts = use_aux ? ((n >= 512) ? 4 : (n >= 128 ? 2 : 1)) : 1;
+  if (use_aux && ctx->overlap_parts > 1) parts = std::min(ctx->overlap_parts, std::max(1, n / 32));
   auto part_begin = [&](int p) { return (int)(((long long)n * p) / parts); };
   if (use_aux && parts > 1 && !ctx->aux_stream) {
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
