@@ -811,6 +811,34 @@ int run_track_from_detect(ht_ctx *ctx, const uint8_t *d_rgba_batch, int w, int h
   return HT_OK;
 }
 
+// Host frames -> ctx->d_frames in chunks on the copy stream; chunk c is complete when ctx->chunk_events[c] fires.
+int upload_chunks(ht_ctx *ctx, const uint8_t *rgba, int n, size_t frame_bytes, int *chunk_out, int *n_chunks_out) {
+  CK(ctx->d_frames.reserve(frame_bytes * (size_t)n));
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  }
+  const int chunk = std::max(1, std::min(n, ctx->h2d_chunk));
+  const int n_chunks = (n + chunk - 1) / chunk;
+  while ((int)ctx->chunk_events.size() < n_chunks) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_events.push_back(e);
+  }
+  // the staging buffer may still be read by work enqueued earlier on the compute stream
+  CK(cudaEventRecord(ctx->compute_done, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done, 0));
+  uint8_t *d_frames = ctx->d_frames.as<uint8_t>();
+  for (int c = 0; c < n_chunks; ++c) {
+    const int f0 = c * chunk, nf = std::min(chunk, n - f0);
+    CK(cudaMemcpyAsync(d_frames + frame_bytes * f0, rgba + frame_bytes * f0, frame_bytes * nf, cudaMemcpyHostToDevice,
+                       ctx->copy_stream));
+    CK(cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
+  }
+  *chunk_out = chunk;
+  *n_chunks_out = n_chunks;
+  return HT_OK;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -944,16 +972,28 @@ int ht_detect(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interva
   Plan *P = nullptr;
   rc = get_plan(ctx, w, h, interval, &P);
   if (rc != HT_OK) return rc;
-  const uint8_t *d_rgba = nullptr;
-  rc = device_frames(ctx, rgba, n, w, h, &d_rgba);
-  if (rc != HT_OK) return rc;
+  if (!rgba) return ctx->fail(HT_ERR_ARG, "rgba is NULL");
+  if ((reinterpret_cast<uintptr_t>(rgba) & 3u) != 0) return ctx->fail(HT_ERR_ARG, "rgba must be 4-byte aligned");
   CK(ctx->arena.reserve(P->arena_stride * (size_t)n));
   cudaStream_t st = ctx->stream;
   const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
   Rect *d_rects = rects_dev ? reinterpret_cast<Rect *>(out_rects) : ctx->d_out_rects.as<Rect>();
   int32_t *d_counts = counts_dev ? out_counts : ctx->d_out_counts.as<int32_t>();
-  rc = run_detect(ctx, P, d_rgba, 0, n, min_neighbors, d_rects, d_counts);
-  if (rc != HT_OK) return rc;
+  if (is_device_ptr(rgba)) {
+    rc = run_detect(ctx, P, rgba, 0, n, min_neighbors, d_rects, d_counts);
+    if (rc != HT_OK) return rc;
+  } else {
+    // host frames: the H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c
+    int chunk = 0, n_chunks = 0;
+    rc = upload_chunks(ctx, rgba, n, (size_t)w * h * 4, &chunk, &n_chunks);
+    if (rc != HT_OK) return rc;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int f0 = c * chunk, nf = std::min(chunk, n - f0);
+      CK(cudaStreamWaitEvent(st, ctx->chunk_events[c], 0));
+      rc = run_detect(ctx, P, ctx->d_frames.as<uint8_t>(), f0, nf, min_neighbors, d_rects, d_counts);
+      if (rc != HT_OK) return rc;
+    }
+  }
   ctx->last_plan = P;
   ctx->last_n = n;
   if (!rects_dev) CK(cudaMemcpyAsync(out_rects, d_rects, sizeof(Rect) * (size_t)n * ctx->K, cudaMemcpyDeviceToHost, st));
@@ -1118,27 +1158,10 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
     }
   } else {
     // host frames: upload in chunks on a copy stream so the H2D of chunk c+1 overlaps the kernels of chunk c
-    CK(ctx->d_frames.reserve(frame_bytes * (size_t)n));
-    if (!ctx->copy_stream) {
-      CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    }
-    const int chunk = std::max(1, std::min(n, ctx->h2d_chunk));
-    const int n_chunks = (n + chunk - 1) / chunk;
-    while ((int)ctx->chunk_events.size() < n_chunks) {
-      cudaEvent_t e;
-      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      ctx->chunk_events.push_back(e);
-    }
-    // the staging buffer may still be read by work enqueued earlier on the compute stream
-    CK(cudaEventRecord(ctx->compute_done, st));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done, 0));
+    int chunk = 0, n_chunks = 0;
+    rc = upload_chunks(ctx, rgba, n, frame_bytes, &chunk, &n_chunks);
+    if (rc != HT_OK) return rc;
     uint8_t *d_frames = ctx->d_frames.as<uint8_t>();
-    for (int c = 0; c < n_chunks; ++c) {
-      const int f0 = c * chunk, nf = std::min(chunk, n - f0);
-      CK(cudaMemcpyAsync(d_frames + frame_bytes * f0, rgba + frame_bytes * f0, frame_bytes * nf, cudaMemcpyHostToDevice,
-                         ctx->copy_stream));
-      CK(cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
-    }
     // detect per uploaded chunk; tracking per PART (a k_track launch costs at least its slowest stream, so it is
     // not launched per chunk)
     int next_part = 0, tracked_to = 0;
