@@ -542,15 +542,17 @@ int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_
 // outgrows bail_area stop and are queued.  Phase B: one 8-CTA cluster per queued stream finishes their calls.
 // Mean-shift is a serial chain of window passes per stream, so the few streams with large windows would
 // otherwise set the duration of the whole launch.
-// HT_TRACK_TRACE=1: timeline buffer of the context that is launching (debug; launches are made by one host thread)
-static unsigned long long *g_track_trace = nullptr;
-static int g_track_memo = 1;   // ht_ctx::track_memo of the context that is launching
+// per-launch options of k_track that do not depend on the batch
+struct TrackOpts {
+  unsigned long long *trace;   // HT_TRACK_TRACE=1: per-stream timeline buffer (else NULL)
+  int memo;                    // ht_ctx::track_memo
+};
 
 template <int C, int NT = 256>
 cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, int h, const int32_t *d_slots,
                            const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
                            int32_t *d_win, int32_t *flag, unsigned long long *stats, int bail_area, int32_t *calls_done,
-                           int32_t *bail_list, int32_t *bail_count, int use_list, int list_off = 0) {
+                           int32_t *bail_list, int32_t *bail_count, int use_list, int list_off, TrackOpts opt) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)n * C);
   cfg.blockDim = dim3(NT);
@@ -561,7 +563,7 @@ cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, 
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_track<C, NT>, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
-                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, g_track_trace, g_track_memo);
+                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, opt.trace, opt.memo);
 }
 
 // cluster size x CTA size chosen at run time
@@ -569,29 +571,29 @@ template <int NT>
 cudaError_t launch_track_nt(int c, cudaStream_t st, int n, const uint16_t *bins, int w, int h, const int32_t *d_slots,
                             const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
                             int32_t *d_win, int32_t *flag, unsigned long long *stats, int32_t *calls_done, int32_t *list,
-                            int32_t *count, int use_list, int list_off) {
+                            int32_t *count, int use_list, int list_off, TrackOpts opt) {
   switch (c) {
-    case 1: return launch_track_c<1, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off);
-    case 2: return launch_track_c<2, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off);
-    case 4: return launch_track_c<4, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off);
-    default: return launch_track_c<8, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off);
+    case 1: return launch_track_c<1, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
+    case 2: return launch_track_c<2, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
+    case 4: return launch_track_c<4, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
+    default: return launch_track_c<8, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
   }
 }
 cudaError_t launch_track_any(int c, int nt, cudaStream_t st, int n, const uint16_t *bins, int w, int h, const int32_t *d_slots,
                              const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
                              int32_t *d_win, int32_t *flag, unsigned long long *stats, int32_t *calls_done, int32_t *list,
-                             int32_t *count, int use_list, int list_off) {
+                             int32_t *count, int use_list, int list_off, TrackOpts opt) {
   if (nt == 128)
-    return launch_track_nt<128>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off);
-  return launch_track_nt<256>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off);
+    return launch_track_nt<128>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off, opt);
+  return launch_track_nt<256>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off, opt);
 }
 
 int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h, const int32_t *d_slots, const uint32_t *mh,
                  const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs, int32_t *d_win, int32_t *flag) {
   unsigned long long *stats = ctx->d_flags.as<unsigned long long>() + 8;
   cudaStream_t st = ctx->stream;
-  g_track_memo = ctx->track_memo ? 1 : 0;
-  g_track_trace = ctx->track_trace ? ctx->d_trace.as<unsigned long long>() + 4 * (size_t)f0 : nullptr;
+  const TrackOpts opt{ctx->track_trace ? ctx->d_trace.as<unsigned long long>() + 4 * (size_t)f0 : nullptr,
+                      ctx->track_memo ? 1 : 0};
   // per-chunk scheduling scratch: [calls_done | area n][bail_list | order n][bail_count 1]
   int32_t *calls_done = ctx->d_sched.as<int32_t>() + (size_t)f0;
   int32_t *bail_list = ctx->d_sched.as<int32_t>() + (size_t)ctx->cfg.max_frames + f0;
@@ -602,10 +604,10 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
     e = cudaMemsetAsync(bail_count, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return ctx->fail(HT_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
     e = launch_track_c<1>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, ctx->track_bail_area,
-                          calls_done, bail_list, bail_count, 0);
+                          calls_done, bail_list, bail_count, 0, 0, opt);
     if (e == cudaSuccess)
       e = launch_track_c<8>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done,
-                            bail_list, bail_count, 1);
+                            bail_list, bail_count, 1, 0, opt);
     ctx->launches += 2;
   } else {
     // few streams -> 8 CTAs per stream (latency of one stream); many streams -> 2 (more streams resident).
@@ -616,7 +618,7 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
     const bool lpt = ctx->track_lpt && n >= 128;     // below that every stream is resident from the start
     if (!lpt) {
       e = launch_track_any(c, nt, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done,
-                           bail_list, bail_count, 0, 0);
+                           bail_list, bail_count, 0, 0, opt);
       ++ctx->launches;
     } else {
       // longest chain first: order the streams by search-window area (k_track_area / k_track_rank); optionally the
@@ -634,13 +636,13 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
         CK(cudaEventRecord(ctx->sched_ready, st));
         CK(cudaStreamWaitEvent(ctx->sched_stream, ctx->sched_ready, 0));
         e = launch_track_any(ctx->track_heavy_cluster, 256, ctx->sched_stream, n_heavy, bins, w, h, d_slots, mh, ch, state,
-                             n_calls, d_objs, d_win, flag, stats, calls_done, bail_list, bail_count, 2, 0);
+                             n_calls, d_objs, d_win, flag, stats, calls_done, bail_list, bail_count, 2, 0, opt);
         CK(cudaEventRecord(ctx->sched_done, ctx->sched_stream));
         ++ctx->launches;
       }
       if (e == cudaSuccess && n > n_heavy) {
         e = launch_track_any(c, nt, st, n - n_heavy, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
-                             calls_done, bail_list, bail_count, 2, n_heavy);
+                             calls_done, bail_list, bail_count, 2, n_heavy, opt);
         ++ctx->launches;
       }
       if (n_heavy > 0) CK(cudaStreamWaitEvent(st, ctx->sched_done, 0));

@@ -96,3 +96,51 @@ def test_facetrackr_on_cuda_matches_reference_js(ctx):
     from test_host_post import GOLD as POST, check_steps, run_facetrackr
     for case in POST["facetrackr"]:
         check_steps(run_facetrackr(case, facetrackr.CudaBackend(ctx)), case["steps"])
+
+
+def test_configs_2_and_3_full_batch_properties(blob):
+    """BASELINE configs 2/3 at their full size (1024 x 640x480 per launch), through size-independent properties:
+    the batch is 16 distinct frames in a scrambled order, so (a) every copy of a frame must give the same record
+    wherever it sits in the batch (idempotence / no cross-frame leakage), (b) each distinct frame must equal the
+    oracle, (c) the chunk-pipelined host path must equal the device-resident path, (d) the window memo must not
+    change a single output of the 30 track() calls."""
+    import torch
+    from headtrackr_b200 import Context
+    N, U, CALLS = 1024, 16, 30
+    uniq = synth.batch(U, 640, 480, start=40)
+    rng = np.random.default_rng(7)
+    which = rng.integers(0, U, size=N)
+    which[:U] = np.arange(U)
+    frames = uniq[which]                                            # 1.26 GB
+    want = [oracle.detect_track(uniq[u], blob, n_calls=CALLS) for u in range(U)]
+    want_rects = [oracle.detect(uniq[u], blob) for u in range(U)]
+    c = Context(max_width=640, max_height=480, max_frames=N)
+    try:
+        dev = torch.from_numpy(frames).cuda()
+        runs = {}
+        for name, src, memo in (("device_strict", dev, False), ("device_memo", dev, True), ("host_memo", frames, True)):
+            c.set_track_memo(memo)
+            runs[name] = c.detect_track(src, 5, 1, calc_angles=False, n_calls=CALLS)
+        del dev
+        ref = runs["device_strict"]
+        assert runs["device_memo"] == ref and runs["host_memo"] == ref            # (c), (d)
+        dets, found, objs, wins = ref
+        first = {}
+        for i in range(N):
+            u = int(which[i])
+            rec = ([tup(d) for d in dets[i]], found[i], objs[i], wins[i])
+            if u not in first:
+                first[u] = rec
+                n_det, fnd, obj = want[u]                                         # (b)
+                assert rec[0] == want_rects[u] and len(rec[0]) == n_det and rec[1] == fnd
+                if fnd:
+                    o = rec[2]
+                    assert (o["x"], o["y"], o["width"], o["height"]) == (obj["x"], obj["y"], obj["width"], obj["height"])
+                    assert abs(o["angle"] - obj["angle"]) <= 1e-4
+            else:
+                assert rec == first[u], f"frame {i} (copy of distinct frame {u}) differs from its first copy"   # (a)
+        # detect-only entry point on the same batch (config 2), host path
+        d2 = c.detect(frames, 5, 1)
+        assert all([tup(d) for d in d2[i]] == first[int(which[i])][0] for i in range(N))
+    finally:
+        c.close()
