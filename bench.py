@@ -114,15 +114,41 @@ def cpu_step(frames, blob, track_calls, threads):
     return time.perf_counter() - t0
 
 
+def usable_cores():
+    """Host cores this process may actually use: CPU affinity, capped by a cgroup CPU quota if there is one
+    (os.cpu_count() reports the machine, not the container)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]          # cgroup v2
+        if q != "max":
+            quota = float(q) / float(p)
+    except (OSError, ValueError):
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())           # cgroup v1
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and p > 0:
+                quota = q / p
+        except (OSError, ValueError):
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.999)))
+    return n
+
+
 def cpu_baseline(frames, blob, track_calls, steps=1, warmup=0):
     import oracle
     oracle.lib()
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     for _ in range(warmup):
         cpu_step(frames, blob, track_calls, threads)
     times = [cpu_step(frames, blob, track_calls, threads) for _ in range(steps)]
     total = sum(times)
-    return {"value": len(frames) * steps / total, "unit": "frames/s", "cores": threads, "kind": "port",
+    return {"value": len(frames) * steps / total, "unit": "frames/s", "cores": threads, "host_cpu_count": os.cpu_count(),
+            "kind": "port",
             "sample": f"{len(frames)} of the bench's synthetic frames per step, C restatement of the reference JS "
                       f"(oracle/ht_oracle.c, -O2, one thread per host core; not V8)"}, total / steps
 
@@ -350,7 +376,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=480)
-    ap.add_argument("--cpu-sample", type=int, default=max(64, 2 * (os.cpu_count() or 1)))
+    ap.add_argument("--cpu-sample", type=int, default=max(64, 2 * usable_cores()))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     track_calls = 30 if args.workload == "detect_track30" else 0
