@@ -8,6 +8,7 @@ import pytest
 
 from headtrackr_b200 import Canvas, camshift, ccv, facetrackr, synth
 from test_oracle_golden import GOLD, track_frames
+from test_oracle_golden_large import GOLD_L, large_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -30,6 +31,37 @@ def test_track_golden_cuda(ctx, case):
         assert [o["x"], o["y"], o["width"], o["height"]] == call["obj"][:4]
         assert abs(o["angle"] - call["obj"][4]) <= 1e-4          # north_star tolerance
         assert list(wins[0]) == call["window"]
+
+
+@pytest.mark.parametrize("case", GOLD_L["detect"], ids=lambda c: c["name"])
+def test_detect_large_golden_cuda(ctx, case):
+    """Benchmark-resolution frames (BASELINE configs 2 and 4) against the reference JS itself."""
+    got = ctx.detect(large_frame(case), case["interval"], case["min_neighbors"])[0]
+    got = [[d["x"], d["y"], d["width"], d["height"], d["confidence"], d["neighbors"]] for d in got]
+    assert got == case["rects"]
+
+
+@pytest.mark.parametrize("case", GOLD_L["track"], ids=lambda c: c["name"])
+@pytest.mark.parametrize("memo", [False, True], ids=["strict", "memo"])
+def test_track_large_golden_cuda(ctx, case, memo):
+    """BASELINE config 3: 30 track() calls on a 640x480 VJ frame, call by call and as one launch, against the JS."""
+    f = large_frame(case)
+    try:
+        ctx.set_track_memo(memo)
+        ctx.track_init(f, [case["rect"]], calc_angles=case["calc_angles"])
+        for call in case["calls"]:
+            objs, wins = ctx.track(f)
+            o = objs[0]
+            assert [o["x"], o["y"], o["width"], o["height"]] == call["obj"][:4]
+            assert abs(o["angle"] - call["obj"][4]) <= 1e-4
+            assert list(wins[0]) == call["window"]
+        ctx.track_init(f, [case["rect"]], calc_angles=case["calc_angles"])
+        objs, wins = ctx.track(f, n_calls=len(case["calls"]))
+        last = case["calls"][-1]
+        assert [objs[0]["x"], objs[0]["y"], objs[0]["width"], objs[0]["height"]] == last["obj"][:4]
+        assert list(wins[0]) == last["window"]
+    finally:
+        ctx.set_track_memo(True)
 
 
 def test_whitebalance_golden_cuda(ctx):
