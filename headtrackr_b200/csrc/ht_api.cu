@@ -413,6 +413,9 @@ struct ht_ctx {
   // only for HOST frames, where the batch arrives at PCIe speed and the GPU has idle time to fill - measured e2e
   // 37.6k vs 33.0k frames/s with 4 parts (8 parts 36.8k, 16 parts 28.6k).  For device-resident frames it was
   // measured slower (24.4-26.7 vs 22.3 ms per step) and stays off.  HT_OVERLAP=0 disables, HT_OVERLAP=<parts> forces.
+  int detect_pipe = 0;                      // HT_DETECT_PIPE=<parts> (experiment): see run_detect_piped
+  cudaStream_t pipe_stream = nullptr;
+  cudaEvent_t pipe_start = nullptr, pipe_events[16] = {};
   int overlap_track = -1;
   int overlap_parts = 0;
   cudaStream_t copy_stream = nullptr;       // H2D staging stream of ht_detect_track
@@ -713,8 +716,11 @@ int ensure_tensor_maps(ht_ctx *ctx, Plan *P) {
 
 // gray -> pyramid -> cascade -> sort+group for frames [f0, f0+n) of a device-resident batch.
 // Every per-frame buffer is indexed by absolute frame number so that chunks can be pipelined.
+// phase 0: everything (the default); phase 1: gray + pyramid only; phase 2: cascade + group only.  Phases 1 and 2 exist
+// for the opt-in HT_DETECT_PIPE experiment (the pyramid of part p+1 on a second stream under the cascade of part p:
+// k_resample is ALU/issue-bound, k_cascade LSU-bound).
 int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n, int min_neighbors, Rect *d_rects_batch,
-               int32_t *d_counts_batch) {
+               int32_t *d_counts_batch, int phase = 0) {
   cudaStream_t st = ctx->stream;
   const int w = P->w, h = P->h;
   const uint8_t *d_rgba = d_rgba_batch + (size_t)f0 * w * h * 4;
@@ -722,9 +728,9 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
   uint32_t *raw_keys = ctx->raw_keys.as<uint32_t>() + (size_t)f0 * ctx->raw_cap;
   double *raw_conf = ctx->raw_conf.as<double>() + (size_t)f0 * ctx->raw_cap;
   uint32_t *raw_count = ctx->raw_count.as<uint32_t>() + f0;
-  CK(cudaMemsetAsync(raw_count, 0, sizeof(uint32_t) * n, st));
+  if (phase != 1) CK(cudaMemsetAsync(raw_count, 0, sizeof(uint32_t) * n, st));
   // K1 grayscale -> plane 0
-  {
+  if (phase != 2) {
     const int qpr = (w + 3) / 4;
     const unsigned blocks = (unsigned)(((size_t)qpr * h + 255) / 256);
     const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgba) & 15u) == 0);
@@ -735,7 +741,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
     ++ctx->launches;
   }
   // K2 pyramid generations
-  for (size_t g = 1; g + 1 < P->gen_tile_begin.size(); ++g) {
+  for (size_t g = 1; phase != 2 && g + 1 < P->gen_tile_begin.size(); ++g) {
     const int t0 = P->gen_tile_begin[g], t1 = P->gen_tile_begin[g + 1];
     if (t1 > t0) {
       ctx->prof_begin(HT_PROF_PYRAMID);
@@ -744,6 +750,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       ++ctx->launches;
     }
   }
+  if (phase == 1) { CK(cudaGetLastError()); return HT_OK; }
   // K3 cascade
   if (!P->casc_tiles.empty()) {
     // make this context's cascade the active __constant__ table (contexts with the same blob share it;
@@ -781,6 +788,39 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
   ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
+  return HT_OK;
+}
+
+// HT_DETECT_PIPE=<parts> (experiment, default off): gray + pyramid of every part on a second stream, cascade + group
+// of part p on the context's stream as soon as its pyramid is complete.
+int run_detect_piped(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n, int min_neighbors,
+                     Rect *d_rects_batch, int32_t *d_counts_batch, int parts) {
+  parts = std::max(1, std::min(parts, std::min(n, 16)));
+  if (!ctx->pipe_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->pipe_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
+    for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&ctx->pipe_events[i], cudaEventDisableTiming));
+  }
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->pipe_start, st));                      // earlier work on the arena / frames is ordered first
+  CK(cudaStreamWaitEvent(ctx->pipe_stream, ctx->pipe_start, 0));
+  auto begin = [&](int p) { return f0 + (int)(((long long)n * p) / parts); };
+  for (int p = 0; p < parts; ++p) {
+    const int b = begin(p), e = begin(p + 1);
+    if (e <= b) continue;
+    ctx->stream = ctx->pipe_stream;
+    const int rc = run_detect(ctx, P, d_rgba_batch, b, e - b, min_neighbors, d_rects_batch, d_counts_batch, 1);
+    ctx->stream = st;
+    if (rc != HT_OK) return rc;
+    CK(cudaEventRecord(ctx->pipe_events[p], ctx->pipe_stream));
+  }
+  for (int p = 0; p < parts; ++p) {
+    const int b = begin(p), e = begin(p + 1);
+    if (e <= b) continue;
+    CK(cudaStreamWaitEvent(st, ctx->pipe_events[p], 0));
+    const int rc = run_detect(ctx, P, d_rgba_batch, b, e - b, min_neighbors, d_rects_batch, d_counts_batch, 2);
+    if (rc != HT_OK) return rc;
+  }
   return HT_OK;
 }
 
@@ -886,6 +926,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
   }
   if (const char *tc = getenv("HT_TRACK_CLUSTER")) c->track_cluster = atoi(tc);
   if (const char *ba = getenv("HT_TRACK_BAIL")) c->track_bail_area = atoi(ba);
+  if (const char *dp = getenv("HT_DETECT_PIPE")) c->detect_pipe = std::max(0, atoi(dp));
   if (const char *tm2 = getenv("HT_TRACK_MEMO")) c->track_memo = atoi(tm2) != 0;
   if (const char *tt = getenv("HT_TRACK_TRACE")) c->track_trace = atoi(tt) != 0;
   if (const char *tn = getenv("HT_TRACK_NT")) c->track_nt = (atoi(tn) == 128) ? 128 : 256;
@@ -940,6 +981,9 @@ void ht_destroy(ht_ctx *ctx) {
   for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
   if (ctx->compute_done) cudaEventDestroy(ctx->compute_done);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->pipe_stream) cudaStreamDestroy(ctx->pipe_stream);
+  if (ctx->pipe_start) cudaEventDestroy(ctx->pipe_start);
+  for (cudaEvent_t e : ctx->pipe_events) if (e) cudaEventDestroy(e);
   if (ctx->sched_stream) cudaStreamDestroy(ctx->sched_stream);
   if (ctx->sched_ready) cudaEventDestroy(ctx->sched_ready);
   if (ctx->sched_done) cudaEventDestroy(ctx->sched_done);
@@ -982,7 +1026,8 @@ int ht_detect(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interva
   Rect *d_rects = rects_dev ? reinterpret_cast<Rect *>(out_rects) : ctx->d_out_rects.as<Rect>();
   int32_t *d_counts = counts_dev ? out_counts : ctx->d_out_counts.as<int32_t>();
   if (is_device_ptr(rgba)) {
-    rc = run_detect(ctx, P, rgba, 0, n, min_neighbors, d_rects, d_counts);
+    rc = (ctx->detect_pipe > 1) ? run_detect_piped(ctx, P, rgba, 0, n, min_neighbors, d_rects, d_counts, ctx->detect_pipe)
+                                : run_detect(ctx, P, rgba, 0, n, min_neighbors, d_rects, d_counts);
     if (rc != HT_OK) return rc;
   } else {
     // host frames: the H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c
@@ -1153,7 +1198,9 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   if (is_device_ptr(rgba)) {
     for (int p = 0; p < parts; ++p) {
       const int f0 = part_begin(p), nf = part_begin(p + 1) - f0;
-      rc = run_detect(ctx, P, rgba, f0, nf, min_neighbors, d_rects, d_counts);
+      rc = (ctx->detect_pipe > 1 && parts == 1)
+               ? run_detect_piped(ctx, P, rgba, f0, nf, min_neighbors, d_rects, d_counts, ctx->detect_pipe)
+               : run_detect(ctx, P, rgba, f0, nf, min_neighbors, d_rects, d_counts);
       if (rc != HT_OK) return rc;
       rc = track_part(rgba, f0, nf);
       if (rc != HT_OK) return rc;
