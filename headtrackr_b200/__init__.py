@@ -10,7 +10,7 @@ Host-side mirror of the reference's L1 interface:
 All pixel work runs in libheadtrackr_b200.so (CUDA, C ABI in include/headtrackr_b200.h).
 """
 from . import _lib  # noqa: F401
-from . import camshift, ccv, facetrackr, headposition, smoother  # noqa: F401
+from . import camshift, ccv, facetrackr, headposition, main, smoother  # noqa: F401
 from .canvas import Canvas, as_pixels  # noqa: F401
 from .context import Context  # noqa: F401
 from .synth import load_cascade_blob  # noqa: F401

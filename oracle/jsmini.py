@@ -74,6 +74,8 @@ class JSArray(JSObject):
             return NativeFunction(lambda this, args: self.items.pop() if self.items else undefined)
         if key == "unshift":
             return NativeFunction(lambda this, args: self._unshift(args))
+        if key == "splice":        # headDiagonal.splice(0,1) - src/main.js:275
+            return NativeFunction(lambda this, args: self._splice(args))
         return JSObject.get(self, key)
 
     def _push(self, args):
@@ -83,6 +85,15 @@ class JSArray(JSObject):
     def _unshift(self, args):
         self.items[0:0] = list(args)
         return float(len(self.items))
+
+    def _splice(self, args):
+        n = len(self.items)
+        start = int(to_number(args[0])) if args else 0
+        start = max(n + start, 0) if start < 0 else min(start, n)
+        cnt = n - start if len(args) < 2 else max(0, min(int(to_number(args[1])), n - start))
+        removed = self.items[start:start + cnt]
+        self.items[start:start + cnt] = list(args[2:])
+        return JSArray(removed)
 
     def set(self, key, val):
         if key.__class__ is float or key.__class__ is int:
@@ -236,6 +247,17 @@ class JSFunction(JSObject):
         r = self.call(obj, args)
         return r if isinstance(r, JSObject) else obj
 
+    def get(self, key):
+        if key == "bind":          # function(){...}.bind(this) - src/main.js:77,305
+            return NativeFunction(lambda this, a: NativeFunction(
+                lambda this2, a2, f=self, bt=(a[0] if a else undefined), ba=list(a[1:]): f.call(bt, ba + list(a2))))
+        if key == "call":
+            return NativeFunction(lambda this, a: self.call(a[0] if a else undefined, list(a[1:])))
+        if key == "apply":
+            return NativeFunction(lambda this, a: self.call(a[0] if a else undefined,
+                                                            list(a[1].items) if len(a) > 1 and isinstance(a[1], JSArray) else []))
+        return JSObject.get(self, key)
+
 
 # ------------------------------------------------------------------------------------------------
 # conversions / operators
@@ -386,7 +408,7 @@ TOKEN_RE = re.compile(r"""
 """, re.X | re.S)
 
 KEYWORDS = {"var", "function", "if", "else", "for", "while", "do", "break", "continue", "return", "new", "this",
-            "true", "false", "null", "undefined", "typeof", "in"}
+            "true", "false", "null", "undefined", "typeof", "in", "try", "catch", "finally"}
 
 
 def tokenize(src):
@@ -524,6 +546,35 @@ class Parser:
                         except BreakEx:
                             break
                 return wh
+            if t == "try":                      # src/main.js:310-325 (starter)
+                self.next()
+                body = self.statement()
+                handler = param = finalizer = None
+                if self.at("catch"):
+                    self.next()
+                    self.expect("(")
+                    param = self.next()[1]
+                    self.expect(")")
+                    self.scopes[-1].add(param)
+                    handler = self.statement()
+                if self.at("finally"):
+                    self.next()
+                    finalizer = self.statement()
+
+                def tr(env, body=body, handler=handler, param=param, finalizer=finalizer):
+                    try:
+                        body(env)
+                    except (ReturnEx, BreakEx, ContinueEx):
+                        raise
+                    except Exception as ex:     # JS-level errors surface as Python exceptions in this interpreter
+                        if handler is None:
+                            raise
+                        env.vars[param] = str(ex)
+                        handler(env)
+                    finally:
+                        if finalizer is not None:
+                            finalizer(env)
+                return tr
             if t == "break":
                 self.next()
                 self.eat(";")
@@ -1152,7 +1203,32 @@ class Interpreter:
             e.props["initEvent"] = NativeFunction(lambda th, aa: e.props.__setitem__("type", aa[0]) or undefined)
             return e
         doc.props["createEvent"] = NativeFunction(create_event)
-        doc.props["dispatchEvent"] = NativeFunction(lambda this, a: self.events.append(a[0]) or True)
+        def dispatch(this, a):       # log a snapshot: src/main.js re-dispatches one mutated Event object
+            e = JSObject()
+            e.props.update(a[0].props)
+            self.events.append(e)
+            return True
+        doc.props["dispatchEvent"] = NativeFunction(dispatch)
+        self.timers = []                 # window.setTimeout log: [id, callback, ms, cleared]
+
+        def set_timeout(this, a):
+            self.timers.append([float(len(self.timers) + 1), a[0], to_number(a[1]) if len(a) > 1 else 0.0, False])
+            return self.timers[-1][0]
+
+        def clear_timeout(this, a):
+            for t in self.timers:
+                if a and t[0] == a[0]:
+                    t[3] = True
+            return undefined
+        win = JSObject()
+        win.props["setTimeout"] = NativeFunction(set_timeout)
+        win.props["clearTimeout"] = NativeFunction(clear_timeout)
+        g["window"] = win
+        fproto = JSObject()
+        fproto.props["bind"] = NativeFunction(lambda this, a: undefined)   # truthy: the bind polyfill of main.js is not needed
+        fn_global = JSObject()
+        fn_global.props["prototype"] = fproto
+        g["Function"] = fn_global
         g["Date"] = NativeFunction(lambda this, a: JSDate(self.now_ms))
         g["document"] = doc
         g["headtrackr"] = JSObject()

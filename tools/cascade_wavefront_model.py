@@ -204,6 +204,57 @@ def simulate(st, scales, v):
     return tot
 
 
+def simulate_quad(st, scales, groups, late_first=8, loads_per_point=1.75):
+    """What-if: phase-planar tile (level 0 in 4 planes by x mod 4, level 1 in 2, level 2 as is) where a LANE evaluates
+    the 4 x-adjacent windows (same ly, same phase) from 32-bit loads: a point costs 1 aligned or 2 unaligned LDS.32
+    per lane (1.75 on average) and serves 4 windows.  A quad stays in the lists while any of its windows is alive."""
+    n_loads = [len(s["points"]) * loads_per_point for s in st]
+    tot = dict(dense=0.0, lists=0.0, conflicts=0, late=0, overhead=0, iters=0)
+    n_tiles = 0
+    for (qw, qh, depth) in scales:
+        for ty in range((qh + TH - 1) // TH):
+            for tx in range((qw + TW - 1) // TW):
+                n_tiles += 1
+                ys = np.arange(ty * TH, min(qh, ty * TH + TH))
+                xs = np.arange(tx * TW, min(qw, tx * TW + TW))
+                d = np.zeros((4, TH, TW), np.int32) - 1
+                d[:, : len(ys), : len(xs)] = depth[:, ys[:, None], xs[None, :]]
+                dq = d.reshape(4, TH, TW // 4, 4).max(axis=3)                 # depth of a quad = its deepest window
+                qq, ly, g = np.meshgrid(np.arange(4), np.arange(TH), np.arange(TW // 4), indexing="ij")
+                qq, ly, g, dq = qq.ravel(), ly.ravel(), g.ravel(), dq.ravel()
+                valid = dq >= 0
+                alive = valid.copy()
+                first = True
+                for grp in groups:
+                    if first:
+                        key = (qq * TH + ly) // 4                              # a warp iteration = 4 rows x 8 quads
+                        for si, j in enumerate(grp):
+                            live = alive & (dq >= j) if si > 0 else alive
+                            tot["dense"] += len(np.unique(key[live])) * n_loads[j]
+                        first = False
+                    else:
+                        idx = np.nonzero(alive)[0]
+                        if idx.size == 0:
+                            break
+                        cls = (g[idx] + 8 * (ly[idx] & 3)) & 31                # bank of the quad's base word (pitch = 8 words mod 32)
+                        counts = np.bincount(cls, minlength=32)
+                        n_iter = counts.max()
+                        order = np.argsort(cls, kind="stable")
+                        idx, cls = idx[order], cls[order]
+                        start = np.concatenate([[0], np.cumsum(counts)[:-1]])
+                        pos = np.arange(idx.size) - start[cls]
+                        tot["iters"] += n_iter
+                        tot["overhead"] += n_iter
+                        for si, j in enumerate(grp):
+                            live = dq[idx] >= j if si > 0 else np.ones(idx.size, bool)
+                            tot["lists"] += len(np.unique(pos[live])) * n_loads[j]
+                    alive &= dq >= (grp[-1] + 1)
+                    tot["overhead"] += 2 * 16
+        # late stages: as in the current design (taken from the byte-layout model by the caller)
+    tot["tiles"] = n_tiles
+    return tot
+
+
 def main():
     idx = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (640, 480)
@@ -226,10 +277,19 @@ def main():
         Variant("lane-per-window up to stage 9", [[0, 1], [2], [3], [4, 5], [6, 7], [8, 9]], late_first=10),
     ]
     print(f"{'variant':52s} {'total':>9s} {'dense':>8s} {'lists':>8s} {'confl':>8s} {'late':>8s} {'ovh':>7s} {'iters':>7s}  per tile")
+    late_now = None
     for v in variants:
         t = simulate(st, scales, v)
+        if late_now is None:
+            late_now = t["late"]
         print(f"{v.name:52s} {t['total']:9d} {t['dense']:8d} {t['lists']:8d} {t['conflicts']:8d} {t['late']:8d} "
               f"{t['overhead']:7d} {t['iters']:7d}  {t['total'] / t['tiles']:.0f}")
+    for name, groups in (("QUAD lanes {0,1}{2}{3}{4,5}{6,7}", [[0, 1], [2], [3], [4, 5], [6, 7]]),
+                         ("QUAD lanes {0,1}{2,3}{4,5}{6,7}", [[0, 1], [2, 3], [4, 5], [6, 7]])):
+        t = simulate_quad(st, scales, groups)
+        total = t["dense"] + t["lists"] + late_now + t["overhead"]
+        print(f"{name:52s} {int(total):9d} {int(t['dense']):8d} {int(t['lists']):8d} {0:8d} {late_now:8d} "
+              f"{t['overhead']:7d} {t['iters']:7d}  {total / t['tiles']:.0f}")
 
 
 if __name__ == "__main__":
