@@ -64,6 +64,15 @@ def test_track_large_golden_cuda(ctx, case, memo):
         ctx.set_track_memo(True)
 
 
+@pytest.mark.parametrize("case", GOLD_L.get("backprojection", []), ids=lambda c: c["name"])
+def test_backprojection_golden_cuda(ctx, case):
+    import hashlib
+    f = synth.frame(case["index"], case["W"], case["H"], n_faces=case["n_faces"])
+    ctx.track_init(f, [case["rect"]], calc_angles=False)
+    img = ctx.backprojection(f, 0)
+    assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == case["image_sha256"]
+
+
 def test_whitebalance_golden_cuda(ctx):
     for c in GOLD["whitebalance"]:
         f = synth.frame(c["index"], c["W"], c["H"], kind=c["kind"])

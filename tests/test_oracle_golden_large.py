@@ -44,3 +44,16 @@ def test_track_large_golden_oracle(case):
         assert [o["x"], o["y"], o["width"], o["height"]] == call["obj"][:4]
         assert abs(o["angle"] - call["obj"][4]) <= 1e-12
         assert list(ot.search_window()) == call["window"]
+
+
+@pytest.mark.parametrize("case", GOLD_L.get("backprojection", []), ids=lambda c: c["name"])
+def test_backprojection_golden_oracle(case):
+    """getBackProjectionImg (src/camshift.js:177-196): the image the reference JS produced, by hash."""
+    f = synth.frame(case["index"], case["W"], case["H"], n_faces=case["n_faces"])
+    assert hashlib.sha256(np.ascontiguousarray(f).tobytes()).hexdigest() == case["frame_sha256"]
+    ot = oracle.CamshiftTracker(calc_angles=False)
+    ot.init_tracker(f, *case["rect"])
+    ot.track(f)
+    img = ot.backprojection_img(f)
+    assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == case["image_sha256"]
+    assert int((img[..., 0] > 0).sum()) == case["nonzero"]

@@ -107,6 +107,29 @@ def main():
                                   frame_sha256=mg.sha(frame), calls=calls))
         OUT.write_text(json.dumps(gold, indent=1))
         print(f"{name}: {n_calls} track() calls, JS == oracle  ({time.time() - t0:.0f}s)", flush=True)
+    if "backprojection" not in gold and not only:
+        # getBackProjectionImg (src/camshift.js:177-196) after initTracker + one track() on a 160x120 frame
+        W, H, idx = 160, 120, 3
+        frame = synth.frame(idx, W, H, n_faces=1)
+        best = max(oracle.detect(frame, blob), key=lambda r: r[4])
+        rect = [int(math.floor(v)) for v in best[:4]]
+        params = jsmini.JSObject()
+        params.props["calcAngles"] = False
+        trk = Tracker.construct([params])
+        canvas = jsmini.CanvasShim(frame.copy())
+        it.call(trk.get("initTracker"), trk, canvas, Rectangle.construct([float(v) for v in rect]))
+        it.call(trk.get("track"), trk, canvas)
+        img = it.call(trk.get("getBackProjectionImg"), trk)
+        arr = np.array(img.get("data").buf).reshape(H, W, 4).astype(np.uint8)
+        ot = oracle.CamshiftTracker(calc_angles=False)
+        ot.init_tracker(frame, *rect)
+        ot.track(frame)
+        assert np.array_equal(arr, ot.backprojection_img(frame)), "getBackProjectionImg: reference JS != C oracle"
+        gold["backprojection"] = [dict(name="backprojection_160x120", W=W, H=H, index=idx, n_faces=1, rect=rect,
+                                       frame_sha256=mg.sha(frame), image_sha256=mg.sha(arr),
+                                       nonzero=int((arr[..., 0] > 0).sum()))]
+        OUT.write_text(json.dumps(gold, indent=1))
+        print("backprojection_160x120: JS == oracle", flush=True)
     print(f"wrote {OUT} in {time.time() - t_start:.0f}s")
 
 
