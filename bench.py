@@ -327,7 +327,8 @@ def run_ours(args, W, H, track_calls, workload):
     if rank == 0:
         peak, peak_src = measured_peaks()
         casc_ms, casc_n = prof["cascade"]
-        alg_bytes = B * W * H * 4                      # one read of the RGBA frame, x frames per launch
+        # one read of the RGBA frame per frame; a k_cascade launch covers one L2 wave of frames
+        alg_bytes = B * W * H * 4 * args.steps / casc_n if casc_n else None
         achieved = (alg_bytes / 1e9) / (casc_ms / casc_n / 1e3) if casc_n else None
         kernel_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
         line = {"metric": "frames/sec @640x480 (detect+CAMShift)", "value": value, "unit": "frames/s",

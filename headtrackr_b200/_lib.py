@@ -4,11 +4,13 @@ There is no CPU fallback: if the shared library is missing it is built with nvcc
 is impossible the import fails loudly.  Nothing here imports the oracle.
 """
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-SO_PATH = _PKG / "libheadtrackr_b200.so"
+# HT_LIB selects another build of the same library (A/B variants of compile-time knobs, tools/build_variants.sh)
+SO_PATH = Path(os.environ["HT_LIB"]).resolve() if os.environ.get("HT_LIB") else _PKG / "libheadtrackr_b200.so"
 CSRC = _PKG / "csrc"
 
 HT_OK, HT_WARN_OVERFLOW = 0, 1
@@ -63,7 +65,7 @@ _lib = None
 
 EXPORTS = ["ht_version", "ht_create", "ht_destroy", "ht_last_error", "ht_sync", "ht_max_rects", "ht_detect",
            "ht_track_init", "ht_track_init_from_detect", "ht_track", "ht_detect_track", "ht_backprojection", "ht_whitebalance",
-           "ht_plan_info", "ht_debug_plane", "ht_debug_raw", "ht_debug_model_hist", "ht_debug_track_stats", "ht_set_track_memo", "ht_debug_track_trace", "ht_launch_count",
+           "ht_plan_info", "ht_debug_plane", "ht_debug_raw", "ht_debug_model_hist", "ht_debug_track_stats", "ht_set_track_memo", "ht_debug_set_exactness", "ht_debug_track_trace", "ht_launch_count",
            "ht_profile", "ht_profile_read"]
 
 PROF_CLASSES = ["gray", "pyramid", "cascade", "group", "hist", "track_init", "track"]
@@ -103,6 +105,7 @@ def lib():
     L.ht_debug_track_stats.argtypes = [vp, vp, C.c_int]
     L.ht_debug_track_trace.argtypes = [vp, vp, C.c_int]
     L.ht_set_track_memo.argtypes = [vp, C.c_int]
+    L.ht_debug_set_exactness.argtypes = [vp, C.c_int]
     L.ht_launch_count.argtypes = [vp]
     L.ht_launch_count.restype = C.c_uint64
     L.ht_profile.argtypes = [vp, C.c_int]

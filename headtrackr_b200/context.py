@@ -217,6 +217,10 @@ class Context:
         """Re-use the moments of windows already summed in the same launch (default on; results are identical)."""
         self._check(self._L.ht_set_track_memo(self._h, int(bool(enable))))
 
+    def debug_set_exactness(self, flags):
+        """Force the exactness fallbacks (bit 0: generated cascade stages, 1: late stages, 2: mean-shift moments)."""
+        self._check(self._L.ht_debug_set_exactness(self._h, int(flags)))
+
     def debug_track_trace(self, n):
         """(n, 4) uint64: {start ns, end ns, SM id, passes} per stream (contexts created under HT_TRACK_TRACE=1)."""
         out = np.zeros((n, 4), np.uint64)

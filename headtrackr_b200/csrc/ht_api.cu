@@ -65,7 +65,7 @@ struct Plan {
   std::vector<int> gen_tile_begin;      // size n_gens+1
   std::vector<DevScale> scales;
   std::vector<DevCascTile> casc_tiles;
-  size_t arena_stride = 0;
+  size_t arena_stride = 0;              // WORDS per frame quad (4 frames interleaved)
   uint32_t windows_per_frame = 0;
   DevBuf dev;
   DevPlan dplan{};
@@ -99,8 +99,8 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
   auto add_plane = [&](int slot, int q) {
     DevPlane pl;
     pl.w = P.slot_w[slot]; pl.h = P.slot_h[slot];
-    pl.pitch = align_up(pl.w, 16);
-    off = align_up(off, (size_t)256);
+    pl.pitch = align_up(pl.w, 4);             // words (one word = the pixel in the 4 frames of a quad)
+    off = align_up(off, (size_t)64);          // 256 B
     pl.off = (uint32_t)off;
     off += (size_t)pl.pitch * pl.h;
     P.plane_id[(size_t)slot * 4 + q] = (int)P.planes.size();
@@ -110,8 +110,8 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
     add_plane(s, 0);
     if (s >= 2 * P.next) for (int q = 1; q < 4; ++q) add_plane(s, q);
   }
-  if (off > 0xF0000000ull) { err = "frame too large"; return HT_ERR_SIZE; }
-  P.arena_stride = align_up(off, (size_t)256);
+  if (off > 0x3C000000ull) { err = "frame too large"; return HT_ERR_SIZE; }
+  P.arena_stride = align_up(off, (size_t)64);   // words per frame quad
   // ---- resample jobs, by generation ----
   std::vector<int> gen(P.n_slots, 0);
   int n_gens = 1;
@@ -247,7 +247,9 @@ struct HostCascade {
   ConstCascade cc;      // image of the __constant__ table
   uint64_t id = 0;      // FNV-1a of cc: identical cascades share the loaded constants
   bool fast = false;    // blob == the cascade the generated stages were specialised for
-  std::vector<LateFeat> late;  // per-feature records for the warp-per-window late stages
+  std::vector<LateFeat> late;          // late-stage records in scheduled order, 32 per chunk
+  std::vector<int32_t> late_chunk0;    // [n_stages + 1] first chunk of every stage
+  int late_conflicts = 0;              // bank conflicts the schedule could not avoid (diagnostic)
 };
 
 // which cascade image is currently in c_casc, per device
@@ -280,9 +282,7 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   auto point_off = [&](int z, int x, int y, bool &ok) -> uint16_t {
     const int lim = (24 >> z) - 1;
     if (z < 0 || z > 2 || x < 0 || y < 0 || x > lim || y > lim) { ok = false; return 0; }
-    if (z == 0) return (uint16_t)(y * TP + x);
-    if (z == 1) return (uint16_t)(REGION + TP + 2 * x + 2 * y * TP);
-    return (uint16_t)(REGION + 4 * x + 4 * y * TP);
+    return (uint16_t)(point_word(z, x, y) | (z > 0 ? 0x8000 : 0));   // bit 15: relative to baseB
   };
   for (int k = 0; k < hc.n_features; ++k) {
     const uint8_t *r = pf + (size_t)k * 32;
@@ -310,35 +310,39 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   }
   // exact integer images of alpha / threshold (see LateFeat in ht_common.cuh)
   bool ints_ok = true;
-  hc.late.assign((size_t)hc.n_features, LateFeat{});
+  std::vector<long long> a_int((size_t)hc.n_features, 0);
   auto to_int = [&](double v, long long &out) {
     const double scaled = v * 1e8;
     const long long r = llround(scaled);
     out = r;
     return std::fabs(scaled - (double)r) < 1e-3 && ((double)r / 1e8) == v && std::llabs(r) < (1ll << 40);
   };
-  for (int k = 0; k < hc.n_features; ++k) {
-    long long ai = 0;
-    if (!to_int(cc.alpha[k], ai) || std::llabs(ai) > 0x7fffffffll) ints_ok = false;
-    LateFeat &lf = hc.late[k];
-    for (int q = 0; q < 10; ++q) lf.off[q] = cc.off[k][q];
-    lf.a_int = (int32_t)ai;
-    lf.np = cc.np_nn[k] & 15; lf.nn = cc.np_nn[k] >> 4;
-  }
+  for (int k = 0; k < hc.n_features; ++k)
+    if (!to_int(cc.alpha[k], a_int[k]) || std::llabs(a_int[k]) > 0x7fffffffll) ints_ok = false;
   for (int j = 0; j < hc.n_stages; ++j) {
     long long ti = 0;
     if (!to_int(cc.stage[j].threshold, ti)) ints_ok = false;
     cc.thr_int[j] = ti;
   }
-  // lane-per-window groups {0,1} {2,3} {4,5}; then either warp-per-window late stages (exact integers)
-  // or, when the cascade's numbers are not 8-digit decimals, two more lane-per-window groups.
+  uint64_t bh = 1469598103934665603ull;
+  for (size_t i = 0; i < len; ++i) { bh ^= b[i]; bh *= 1099511628211ull; }
+  hc.fast = (bh == HT_GEN_BLOB_ID) && (len == need) && ints_ok && hc.n_stages >= HT_GEN_STAGES && !getenv("HT_NO_LATE");
+  if (getenv("HT_NO_FAST")) hc.fast = false;  // A/B switch for profiling: table-driven stages only
+  // lane-per-window groups, then either warp-per-window late stages (exact integers) or, when the cascade's
+  // numbers are not 8-digit decimals, lane-per-window groups to the end.
   {
     int g = 0;
+    const int cuts_fast[] = {0, 2, 3, 4, 6};      // {0,1} {2} {3} {4,5} {6,7}: the generated stages
+    const int cuts_int[] = {0, 2, 4, 6};
     const int cuts_fp[] = {0, 2, 4, 6, 9};
-    if (ints_ok && !getenv("HT_NO_LATE")) {
-      // lane-per-window pairs up to the last generated stage, then warp-per-window
-      for (int cpos = 0; cpos < HT_GEN_STAGES && cpos < hc.n_stages; cpos += 2) cc.group_first[g++] = cpos;
-      cc.group_first[g] = std::min((int)HT_GEN_STAGES, hc.n_stages);
+    static_assert(HT_GEN_STAGES == 8, "cuts_fast assumes 8 generated stages");
+    if (hc.fast) {
+      for (int cpos : cuts_fast) cc.group_first[g++] = cpos;
+      cc.group_first[g] = HT_GEN_STAGES;
+      cc.late_int = 1;
+    } else if (ints_ok && !getenv("HT_NO_LATE")) {
+      for (int cpos : cuts_int) if (cpos < hc.n_stages) cc.group_first[g++] = cpos;
+      cc.group_first[g] = std::min(8, hc.n_stages);
       cc.late_int = 1;
     } else {
       for (int cpos : cuts_fp) if (cpos < hc.n_stages) cc.group_first[g++] = cpos;
@@ -347,15 +351,77 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
     }
     cc.n_groups = g;
   }
+  // ---- late-stage schedule: chunks of 32 records with bank-conflict-free load slots (LateFeat) ----
+  hc.late.clear();
+  hc.late_chunk0.assign((size_t)hc.n_stages + 1, 0);
+  hc.late_conflicts = 0;
+  for (int j = 0; j < hc.n_stages; ++j) {
+    hc.late_chunk0[j] = (int32_t)(hc.late.size() / 32);
+    if (j < cc.group_first[cc.n_groups]) continue;
+    std::vector<int> rem;
+    for (int k = cc.stage[j].first; k < cc.stage[j].first + cc.stage[j].count; ++k) rem.push_back(k);
+    std::stable_sort(rem.begin(), rem.end(), [&](int x, int y) {   // features with many points first
+      const int sx = (cc.np_nn[x] & 15) + (cc.np_nn[x] >> 4), sy = (cc.np_nn[y] & 15) + (cc.np_nn[y] >> 4);
+      return sx > sy;
+    });
+    while (!rem.empty()) {
+      int bank_word[10][32];                       // word offset that occupies (slot, bank), or -1
+      for (auto &row : bank_word) for (int &v : row) v = -1;
+      // place one side (p: slots 0-4, n: slots 5-9) of feature k; returns the conflicts it adds (dry = do not commit)
+      auto place_side = [&](int k, int side, uint16_t *out, bool allow_conflicts, bool dry) -> int {
+        const int cnt = side ? (cc.np_nn[k] >> 4) : (cc.np_nn[k] & 15);
+        const uint16_t *pt = &cc.off[k][side ? 5 : 0];
+        int order[5] = {0, 1, 2, 3, 4}, best_cost = 1 << 30, best[5] = {0, 1, 2, 3, 4};
+        do {   // slot of point i = order[i]; <= 120 permutations
+          int cost = 0;
+          for (int i = 0; i < cnt; ++i) {
+            const int slot = side * 5 + order[i], word = pt[i] & 0x7fff, bw = bank_word[slot][word & 31];
+            if (bw >= 0 && bw != word) cost += 1 << 10;   // a bank conflict
+            cost += order[i];                              // prefer the low slots: a slot nobody uses costs no wavefront
+          }
+          if (cost < best_cost) { best_cost = cost; for (int i = 0; i < 5; ++i) best[i] = order[i]; }
+        } while (std::next_permutation(order, order + 5));
+        const int conflicts = best_cost >> 10;
+        if (conflicts && !allow_conflicts) return -1;
+        if (!dry) {
+          for (int i = 0; i < cnt; ++i) {
+            const int slot = side * 5 + best[i], word = pt[i] & 0x7fff;
+            if (bank_word[slot][word & 31] < 0) bank_word[slot][word & 31] = word;
+            out[slot] = pt[i];
+          }
+        }
+        return conflicts;
+      };
+      for (int lane = 0; lane < 32; ++lane) {
+        LateFeat lf{};
+        for (int q = 0; q < 10; ++q) lf.off[q] = 0xFFFF;
+        lf.a_int = 0;
+        if (!rem.empty()) {
+          size_t pick = rem.size();
+          for (size_t i = 0; i < rem.size() && pick == rem.size(); ++i)
+            if (place_side(rem[i], 0, lf.off, false, true) == 0 && place_side(rem[i], 1, lf.off, false, true) == 0) pick = i;
+          if (pick == rem.size()) {   // nothing fits conflict-free: take the feature that adds the fewest conflicts
+            int best_c = 1 << 30;
+            for (size_t i = 0; i < rem.size(); ++i) {
+              const int cfl = place_side(rem[i], 0, lf.off, true, true) + place_side(rem[i], 1, lf.off, true, true);
+              if (cfl < best_c) { best_c = cfl; pick = i; }
+            }
+          }
+          const int k = rem[pick];
+          hc.late_conflicts += place_side(k, 0, lf.off, true, false) + place_side(k, 1, lf.off, true, false);
+          lf.a_int = (int32_t)a_int[k];
+          rem.erase(rem.begin() + (long)pick);
+        }
+        hc.late.push_back(lf);
+      }
+    }
+  }
+  hc.late_chunk0[hc.n_stages] = (int32_t)(hc.late.size() / 32);
+  if (hc.late.empty()) hc.late.resize(32);
   uint64_t hsh = 1469598103934665603ull;
   const uint8_t *cb = reinterpret_cast<const uint8_t *>(&cc);
   for (size_t i = 0; i < sizeof(cc); ++i) { hsh ^= cb[i]; hsh *= 1099511628211ull; }
   hc.id = hsh ? hsh : 1;
-  uint64_t bh = 1469598103934665603ull;
-  for (size_t i = 0; i < len; ++i) { bh ^= b[i]; bh *= 1099511628211ull; }
-  hc.fast = (bh == HT_GEN_BLOB_ID) && (len == need) && cc.late_int && cc.n_groups == HT_GEN_STAGES / 2 &&
-            cc.group_first[cc.n_groups] == HT_GEN_STAGES;
-  if (getenv("HT_NO_FAST")) hc.fast = false;  // A/B switch for profiling: table-driven stages only
   return HT_OK;
 }
 
@@ -413,9 +479,14 @@ struct ht_ctx {
   // only for HOST frames, where the batch arrives at PCIe speed and the GPU has idle time to fill - measured e2e
   // 37.6k vs 33.0k frames/s with 4 parts (8 parts 36.8k, 16 parts 28.6k).  For device-resident frames it was
   // measured slower (24.4-26.7 vs 22.3 ms per step) and stays off.  HT_OVERLAP=0 disables, HT_OVERLAP=<parts> forces.
-  int detect_pipe = 0;                      // HT_DETECT_PIPE=<parts> (experiment): see run_detect_piped
+  int detect_pipe = 0;                      // HT_DETECT_PIPE=1: gray + pyramid of wave w+1 on a second stream under the cascade of wave w
+  int wave_frames = 32;                     // frames per L2-resident wave of run_detect (HT_WAVE)
+  int force_ties = 0;                       // ht_debug_set_exactness: force the exactness fallbacks (tests)
   cudaStream_t pipe_stream = nullptr;
-  cudaEvent_t pipe_start = nullptr, pipe_events[16] = {};
+  cudaEvent_t pipe_start = nullptr, pipe_events[4] = {};
+  int last_wave_f0 = 0, last_wave_n = 0;    // frames whose pyramid is still in the arena (ht_debug_plane)
+  const uint32_t *last_wave_arena = nullptr;
+  DevBuf d_late_chunk0;
   int overlap_track = -1;
   int overlap_parts = 0;
   cudaStream_t copy_stream = nullptr;       // H2D staging stream of ht_detect_track
@@ -433,11 +504,6 @@ struct ht_ctx {
   int track_heavy_cluster = 8;              //     track_heavy_cluster CTAs on sched_stream (HT_TRACK_HEAVY=div[,cluster])
   cudaStream_t sched_stream = nullptr;
   cudaEvent_t sched_ready = nullptr, sched_done = nullptr;
-  bool use_tma = true;                      // stage level-0 tiles with cp.async.bulk.tensor (HT_TMA=0 disables)
-  DevBuf d_tmaps;                           // one 128 B CUtensorMap per scale
-  const void *tmap_arena = nullptr;
-  const void *tmap_plan = nullptr;
-  int casc_minb = 6;                        // CTAs per SM the cascade kernel is compiled for (register cap)
   int track_bail_area = 0;                  // >0: two-phase k_track; phase A hands streams with a larger window (px) to phase B
   DevBuf d_sched;                           // k_track two-phase scheduling scratch
   unsigned sched_seq = 0;
@@ -549,6 +615,7 @@ int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_
 struct TrackOpts {
   unsigned long long *trace;   // HT_TRACK_TRACE=1: per-stream timeline buffer (else NULL)
   int memo;                    // ht_ctx::track_memo
+  int force_serial;            // ht_ctx::force_ties & 4
 };
 
 template <int C, int NT = 256>
@@ -566,7 +633,7 @@ cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, 
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_track<C, NT>, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
-                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, opt.trace, opt.memo);
+                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, opt.trace, opt.memo, opt.force_serial);
 }
 
 // cluster size x CTA size chosen at run time
@@ -596,7 +663,7 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
   unsigned long long *stats = ctx->d_flags.as<unsigned long long>() + 8;
   cudaStream_t st = ctx->stream;
   const TrackOpts opt{ctx->track_trace ? ctx->d_trace.as<unsigned long long>() + 4 * (size_t)f0 : nullptr,
-                      ctx->track_memo ? 1 : 0};
+                      ctx->track_memo ? 1 : 0, (ctx->force_ties & 4) ? 1 : 0};
   // per-chunk scheduling scratch: [calls_done | area n][bail_list | order n][bail_count 1]
   int32_t *calls_done = ctx->d_sched.as<int32_t>() + (size_t)f0;
   int32_t *bail_list = ctx->d_sched.as<int32_t>() + (size_t)ctx->cfg.max_frames + f0;
@@ -675,111 +742,126 @@ int track_init_common(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *d
   return HT_OK;
 }
 
-// Tensor maps for the TMA staging of level-0 cascade tiles: one 3-D map (column, row, frame) per scale over the
-// pyramid arena.  Re-encoded whenever the arena allocation or the plan changes.
-int ensure_tensor_maps(ht_ctx *ctx, Plan *P) {
-  if (ctx->tmap_arena == ctx->arena.p && ctx->tmap_plan == P) return HT_OK;
-  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn encode = nullptr;
-  if (!encode) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
-      return ctx->fail(HT_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
-    encode = reinterpret_cast<encode_fn>(fn);
-  }
-  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
-  std::vector<CUtensorMap> maps(P->scales.size());
-  memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
-  for (size_t i = 0; i < P->scales.size(); ++i) {
-    const DevScale &sc = P->scales[i];
-    if (sc.qw <= 0 || sc.qh <= 0) continue;
-    const DevPlane &pl = P->planes[sc.p0];
-    cuuint64_t dims[3] = {(cuuint64_t)pl.pitch, (cuuint64_t)pl.h, (cuuint64_t)ctx->cfg.max_frames};
-    cuuint64_t strides[2] = {(cuuint64_t)pl.pitch, (cuuint64_t)P->arena_stride};
-    cuuint32_t box[3] = {(cuuint32_t)TP, (cuuint32_t)TILE_ROWS, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->arena.as<uint8_t>() + pl.off, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return ctx->fail(HT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for scale %d", (int)r, (int)i);
-  }
-  CK(ctx->d_tmaps.reserve(maps.size() * sizeof(CUtensorMap)));
-  CK(cudaMemcpyAsync(ctx->d_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));   // `maps` is a local; re-encoding only happens when buffers change
-  ctx->tmap_arena = ctx->arena.p;
-  ctx->tmap_plan = P;
+// Shared memory of one k_cascade CTA: the staged tile, two survivor-list buffers, the list lengths of every phase.
+constexpr size_t CASC_SMEM = (size_t)TILE_WORDS * 4 + 2 * (size_t)NWIN * sizeof(uint16_t) + (size_t)(MAX_GROUPS + 2) * 32 * sizeof(int);
+constexpr size_t GRAY_HIST_SMEM = 4 * 4096 * sizeof(uint32_t);
+
+int set_kernel_attributes(ht_ctx *ctx) {
+  CK(cudaFuncSetAttribute(k_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CASC_SMEM));
+  CK(cudaFuncSetAttribute(k_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CASC_SMEM));
+  CK(cudaFuncSetAttribute(k_cascade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(k_cascade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(k_gray<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAY_HIST_SMEM));
+  CK(cudaFuncSetAttribute(k_gray<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAY_HIST_SMEM));
   return HT_OK;
 }
 
+// what camshift needs from the frame, produced by the gray pass of the same read (src/camshift.js:268)
+struct HistOut {
+  uint32_t *hist;   // [n][4096] current-frame histograms (frame f0 first), or NULL
+  uint16_t *bins;   // [n][h*w]  weight-table offsets, or NULL
+};
+
 // gray -> pyramid -> cascade -> sort+group for frames [f0, f0+n) of a device-resident batch.
 // Every per-frame buffer is indexed by absolute frame number so that chunks can be pipelined.
-// phase 0: everything (the default); phase 1: gray + pyramid only; phase 2: cascade + group only.  Phases 1 and 2 exist
-// for the opt-in HT_DETECT_PIPE experiment (the pyramid of part p+1 on a second stream under the cascade of part p:
-// k_resample is ALU/issue-bound, k_cascade LSU-bound).
+//
+// The frames are processed in WAVES of ctx->wave_frames (whole frame quads): the pyramid arena holds one wave
+// (8 MB per 640x480 quad) and is re-used by the next one, so that it lives in the 126 MB L2 instead of making a
+// round trip through HBM for the whole batch (round 1: 1.86 GB read by k_cascade per 1024 frames).  With
+// ctx->detect_pipe the gray + pyramid kernels of wave w+1 run on a second stream (and a second arena) under the
+// cascade of wave w.
 int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n, int min_neighbors, Rect *d_rects_batch,
-               int32_t *d_counts_batch, int phase = 0) {
+               int32_t *d_counts_batch, HistOut ho = HistOut{nullptr, nullptr}) {
   cudaStream_t st = ctx->stream;
   const int w = P->w, h = P->h;
-  const uint8_t *d_rgba = d_rgba_batch + (size_t)f0 * w * h * 4;
-  uint8_t *arena = ctx->arena.as<uint8_t>() + (size_t)f0 * P->arena_stride;
-  uint32_t *raw_keys = ctx->raw_keys.as<uint32_t>() + (size_t)f0 * ctx->raw_cap;
-  double *raw_conf = ctx->raw_conf.as<double>() + (size_t)f0 * ctx->raw_cap;
-  uint32_t *raw_count = ctx->raw_count.as<uint32_t>() + f0;
-  if (phase != 1) CK(cudaMemsetAsync(raw_count, 0, sizeof(uint32_t) * n, st));
-  // K1 grayscale -> plane 0
-  if (phase != 2) {
-    const int qpr = (w + 3) / 4;
-    const unsigned blocks = (unsigned)(((size_t)qpr * h + 255) / 256);
-    const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgba) & 15u) == 0);
-    ctx->prof_begin(HT_PROF_GRAY);
-    if (vec) k_gray<true><<<dim3(blocks, n), 256, 0, st>>>(d_rgba, (size_t)w * h * 4, arena, P->arena_stride, w, h, P->planes[0].pitch, qpr);
-    else k_gray<false><<<dim3(blocks, n), 256, 0, st>>>(d_rgba, (size_t)w * h * 4, arena, P->arena_stride, w, h, P->planes[0].pitch, qpr);
-    ctx->prof_end();
-    ++ctx->launches;
+  const size_t frame_bytes = (size_t)w * h * 4;
+  const int wave = std::max(4, ctx->wave_frames & ~3);
+  const size_t wave_words = P->arena_stride * (size_t)(wave / 4);
+  const bool piped = ctx->detect_pipe > 0 && n > wave;
+  CK(ctx->arena.reserve(wave_words * 4 * (piped ? 2 : 1)));
+  CK(cudaMemsetAsync(ctx->raw_count.as<uint32_t>() + f0, 0, sizeof(uint32_t) * n, st));
+  if (ho.hist) CK(cudaMemsetAsync(ho.hist, 0, (size_t)n * 4096 * sizeof(uint32_t), st));
+  // make this context's cascade the active __constant__ table (contexts with the same blob share it;
+  // contexts with DIFFERENT cascades must not run concurrently on one device)
+  if (g_loaded_cascade[ctx->cfg.device & 63] != ctx->hc.id) {
+    CK(cudaDeviceSynchronize());   // kernels of other contexts may still be reading the previous table
+    CK(cudaMemcpyToSymbolAsync(c_casc, &ctx->hc.cc, sizeof(ConstCascade), 0, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st)); // ... and contexts sharing this cascade skip the upload, so it must have landed
+    g_loaded_cascade[ctx->cfg.device & 63] = ctx->hc.id;
   }
-  // K2 pyramid generations
-  for (size_t g = 1; phase != 2 && g + 1 < P->gen_tile_begin.size(); ++g) {
-    const int t0 = P->gen_tile_begin[g], t1 = P->gen_tile_begin[g + 1];
-    if (t1 > t0) {
-      ctx->prof_begin(HT_PROF_PYRAMID);
-      k_resample<<<dim3(t1 - t0, n), 256, 0, st>>>(P->dplan, t0, arena, P->arena_stride);
+  if (piped && !ctx->pipe_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->pipe_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->pipe_events[i], cudaEventDisableTiming));
+  }
+  if (piped) {   // earlier work on the arena / frames is ordered before the first pyramid
+    CK(cudaEventRecord(ctx->pipe_start, st));
+    CK(cudaStreamWaitEvent(ctx->pipe_stream, ctx->pipe_start, 0));
+  }
+  const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgba_batch) & 15u) == 0);
+  int wi = 0;
+  for (int w0 = 0; w0 < n; w0 += wave, ++wi) {
+    const int nw = std::min(wave, n - w0), fa = f0 + w0, quads = (nw + 3) / 4;
+    uint32_t *arena = ctx->arena.as<uint32_t>() + (piped ? (size_t)(wi & 1) * wave_words : 0);
+    const uint8_t *d_rgba = d_rgba_batch + (size_t)fa * frame_bytes;
+    cudaStream_t ps = piped ? ctx->pipe_stream : st;
+    if (piped && wi >= 2) CK(cudaStreamWaitEvent(ps, ctx->pipe_events[2 + (wi & 1)], 0));   // cascade of wave wi-2 is done with this arena
+    ctx->stream = ps;
+    // K1 grayscale (+ histogram + bin plane) -> plane 0
+    {
+      const bool hist = ho.hist != nullptr;
+      const int target = hist ? 444 : 1184;      // CTAs: 3 (64 KB of histograms each) or 8 per SM
+      const int chunks = std::max(1, std::min(h, (target + quads - 1) / quads));
+      uint32_t *hp = hist ? ho.hist + (size_t)w0 * 4096 : nullptr;
+      uint16_t *bp = ho.bins ? ho.bins + (size_t)w0 * w * h : nullptr;
+      ctx->prof_begin(HT_PROF_GRAY);
+      const dim3 grid((unsigned)chunks, (unsigned)quads);
+      if (hist) {
+        if (vec) k_gray<true, true><<<grid, 256, GRAY_HIST_SMEM, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, hp, bp, chunks);
+        else k_gray<false, true><<<grid, 256, GRAY_HIST_SMEM, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, hp, bp, chunks);
+      } else {
+        if (vec) k_gray<true, false><<<grid, 256, 0, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, nullptr, nullptr, chunks);
+        else k_gray<false, false><<<grid, 256, 0, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, nullptr, nullptr, chunks);
+      }
       ctx->prof_end();
       ++ctx->launches;
     }
-  }
-  if (phase == 1) { CK(cudaGetLastError()); return HT_OK; }
-  // K3 cascade
-  if (!P->casc_tiles.empty()) {
-    // make this context's cascade the active __constant__ table (contexts with the same blob share it;
-    // contexts with DIFFERENT cascades must not run concurrently on one device)
-    if (g_loaded_cascade[ctx->cfg.device & 63] != ctx->hc.id) {
-      CK(cudaDeviceSynchronize());   // kernels of other contexts may still be reading the previous table
-      CK(cudaMemcpyToSymbolAsync(c_casc, &ctx->hc.cc, sizeof(ConstCascade), 0, cudaMemcpyHostToDevice, st));
-      CK(cudaStreamSynchronize(st)); // ... and contexts sharing this cascade skip the upload, so it must have landed
-      g_loaded_cascade[ctx->cfg.device & 63] = ctx->hc.id;
+    // K2 pyramid generations
+    for (size_t g = 1; g + 1 < P->gen_tile_begin.size(); ++g) {
+      const int t0 = P->gen_tile_begin[g], t1 = P->gen_tile_begin[g + 1];
+      if (t1 > t0) {
+        ctx->prof_begin(HT_PROF_PYRAMID);
+        k_resample<<<dim3(t1 - t0, quads), 256, 0, ps>>>(P->dplan, t0, arena, P->arena_stride);
+        ctx->prof_end();
+        ++ctx->launches;
+      }
     }
-    ctx->prof_begin(HT_PROF_CASCADE);
-    auto kern = ctx->hc.fast ? k_cascade<true, 4> : k_cascade<false, 4>;
-    if (ctx->hc.fast && ctx->casc_minb == 5) kern = k_cascade<true, 5>;   // experiment: HT_CASC_MINB
-    if (ctx->hc.fast && ctx->casc_minb == 6) kern = k_cascade<true, 6>;
-    if (ctx->hc.fast && ctx->casc_minb == 3) kern = k_cascade<true, 3>;
-    const void *tmaps = nullptr;
-    if (ctx->use_tma && TP == TILE_FILL_COLS) {   // the TMA box is TP bytes wide: needs a 16-byte multiple
-      int trc = ensure_tensor_maps(ctx, P);
-      if (trc != HT_OK) return trc;
-      tmaps = ctx->d_tmaps.p;
+    ctx->stream = st;
+    if (piped) {
+      CK(cudaEventRecord(ctx->pipe_events[wi & 1], ps));
+      CK(cudaStreamWaitEvent(st, ctx->pipe_events[wi & 1], 0));
     }
-    kern<<<dim3((unsigned)P->casc_tiles.size(), n), CASCADE_THREADS, 0, st>>>(
-        P->dplan, ctx->d_casc.as<LateFeat>(), tmaps, f0, arena, P->arena_stride, raw_keys, raw_conf, raw_count, ctx->raw_cap);
-    ctx->prof_end();
-    ++ctx->launches;
+    // K3 cascade
+    if (!P->casc_tiles.empty()) {
+      ctx->prof_begin(HT_PROF_CASCADE);
+      auto kern = ctx->hc.fast ? k_cascade<true> : k_cascade<false>;
+      kern<<<dim3((unsigned)P->casc_tiles.size(), quads), CASCADE_THREADS, CASC_SMEM, st>>>(
+          P->dplan, ctx->d_casc.as<LateFeat>(), ctx->d_late_chunk0.as<int32_t>(), arena, P->arena_stride, nw,
+          ctx->raw_keys.as<uint32_t>() + (size_t)fa * ctx->raw_cap, ctx->raw_conf.as<double>() + (size_t)fa * ctx->raw_cap,
+          ctx->raw_count.as<uint32_t>() + fa, ctx->raw_cap, ctx->force_ties);
+      ctx->prof_end();
+      ++ctx->launches;
+    }
+    if (piped) CK(cudaEventRecord(ctx->pipe_events[2 + (wi & 1)], st));
+    ctx->last_wave_f0 = fa;
+    ctx->last_wave_n = nw;
+    ctx->last_wave_arena = arena;
   }
   // K4 sort + group
   ctx->prof_begin(HT_PROF_GROUP);
-  k_group<<<(n + 3) / 4, 128, 0, st>>>(P->dplan, n, raw_keys, raw_conf, raw_count, ctx->raw_cap,
+  k_group<<<(n + 3) / 4, 128, 0, st>>>(P->dplan, n, ctx->raw_keys.as<uint32_t>() + (size_t)f0 * ctx->raw_cap,
+                                       ctx->raw_conf.as<double>() + (size_t)f0 * ctx->raw_cap,
+                                       ctx->raw_count.as<uint32_t>() + f0, ctx->raw_cap,
                                        ctx->sorted.as<Rect>() + (size_t)f0 * ctx->raw_cap,
                                        ctx->labels.as<int>() + (size_t)f0 * ctx->raw_cap,
                                        ctx->seq2.as<Rect>() + (size_t)f0 * ctx->raw_cap, min_neighbors,
@@ -788,39 +870,6 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
   ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
-  return HT_OK;
-}
-
-// HT_DETECT_PIPE=<parts> (experiment, default off): gray + pyramid of every part on a second stream, cascade + group
-// of part p on the context's stream as soon as its pyramid is complete.
-int run_detect_piped(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n, int min_neighbors,
-                     Rect *d_rects_batch, int32_t *d_counts_batch, int parts) {
-  parts = std::max(1, std::min(parts, std::min(n, 16)));
-  if (!ctx->pipe_stream) {
-    CK(cudaStreamCreateWithFlags(&ctx->pipe_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
-    for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&ctx->pipe_events[i], cudaEventDisableTiming));
-  }
-  cudaStream_t st = ctx->stream;
-  CK(cudaEventRecord(ctx->pipe_start, st));                      // earlier work on the arena / frames is ordered first
-  CK(cudaStreamWaitEvent(ctx->pipe_stream, ctx->pipe_start, 0));
-  auto begin = [&](int p) { return f0 + (int)(((long long)n * p) / parts); };
-  for (int p = 0; p < parts; ++p) {
-    const int b = begin(p), e = begin(p + 1);
-    if (e <= b) continue;
-    ctx->stream = ctx->pipe_stream;
-    const int rc = run_detect(ctx, P, d_rgba_batch, b, e - b, min_neighbors, d_rects_batch, d_counts_batch, 1);
-    ctx->stream = st;
-    if (rc != HT_OK) return rc;
-    CK(cudaEventRecord(ctx->pipe_events[p], ctx->pipe_stream));
-  }
-  for (int p = 0; p < parts; ++p) {
-    const int b = begin(p), e = begin(p + 1);
-    if (e <= b) continue;
-    CK(cudaStreamWaitEvent(st, ctx->pipe_events[p], 0));
-    const int rc = run_detect(ctx, P, d_rgba_batch, b, e - b, min_neighbors, d_rects_batch, d_counts_batch, 2);
-    if (rc != HT_OK) return rc;
-  }
   return HT_OK;
 }
 
@@ -839,11 +888,10 @@ int run_track_from_detect(ht_ctx *ctx, const uint8_t *d_rgba_batch, int w, int h
   ctx->prof_end();
   ctx->launches += 2;
   if (n_calls > 0) {
+    // the current-frame histograms and the bin plane were produced by the gray pass of run_detect (one frame read)
     uint16_t *bins = ctx->bins.as<uint16_t>() + (size_t)f0 * w * h;
-    int rc = launch_hist(ctx, d_rgba, n, w, h, ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096, bins);
-    if (rc != HT_OK) return rc;
     ctx->prof_begin(HT_PROF_TRACK);
-    rc = launch_track(ctx, n, f0, bins, w, h, nullptr, ctx->model_hist.as<uint32_t>() + (size_t)f0 * 4096,
+    int rc = launch_track(ctx, n, f0, bins, w, h, nullptr, ctx->model_hist.as<uint32_t>() + (size_t)f0 * 4096,
                       ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096, ctx->track_state.as<TrackState>() + f0, n_calls,
                       d_objs + 6 * (size_t)f0, d_win ? d_win + 4 * (size_t)f0 : nullptr, ctx->d_flags.as<int32_t>() + 2);
     if (rc != HT_OK) return rc;
@@ -938,16 +986,18 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
       if (hc == 1 || hc == 2 || hc == 4 || hc == 8) c->track_heavy_cluster = hc;
     }
   }
-  if (const char *mb = getenv("HT_CASC_MINB")) c->casc_minb = atoi(mb);
+  if (const char *wv = getenv("HT_WAVE")) c->wave_frames = std::max(4, atoi(wv));
   if (const char *ov = getenv("HT_OVERLAP")) { c->overlap_track = atoi(ov) != 0 ? 1 : 0; c->overlap_parts = atoi(ov); }
-  if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
   if (const char *hc2 = getenv("HT_H2D_CHUNK")) c->h2d_chunk = std::max(1, atoi(hc2));
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
   // the cascade image is copied into __constant__ memory lazily by run_detect; the late-stage table lives in HBM
   if (c->d_casc.reserve(c->hc.late.size() * sizeof(LateFeat)) != cudaSuccess ||
-      cudaMemcpy(c->d_casc.p, c->hc.late.data(), c->hc.late.size() * sizeof(LateFeat), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaMemcpy(c->d_casc.p, c->hc.late.data(), c->hc.late.size() * sizeof(LateFeat), cudaMemcpyHostToDevice) != cudaSuccess ||
+      c->d_late_chunk0.reserve(c->hc.late_chunk0.size() * sizeof(int32_t)) != cudaSuccess ||
+      cudaMemcpy(c->d_late_chunk0.p, c->hc.late_chunk0.data(), c->hc.late_chunk0.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
     g_create_error = "ht_create: cascade upload failed"; return HT_ERR_CUDA;
   }
+  if (set_kernel_attributes(c.get()) != HT_OK) { g_create_error = "ht_create: " + c->err; return HT_ERR_CUDA; }
   // per-frame result buffers
   const size_t mf = (size_t)cfg->max_frames;
   bool ok = c->raw_keys.reserve(mf * c->raw_cap * sizeof(uint32_t)) == cudaSuccess &&
@@ -973,7 +1023,7 @@ void ht_destroy(ht_ctx *ctx) {
   for (auto &kv : ctx->plans) kv.second->dev.release();
   DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
                     &ctx->labels, &ctx->seq2, &ctx->d_out_rects, &ctx->d_out_counts, &ctx->d_flags, &ctx->model_hist,
-                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_tmaps, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
+                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_late_chunk0, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
                     &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
   for (DevBuf *b : bufs) b->release();
   for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -1020,14 +1070,12 @@ int ht_detect(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interva
   if (rc != HT_OK) return rc;
   if (!rgba) return ctx->fail(HT_ERR_ARG, "rgba is NULL");
   if ((reinterpret_cast<uintptr_t>(rgba) & 3u) != 0) return ctx->fail(HT_ERR_ARG, "rgba must be 4-byte aligned");
-  CK(ctx->arena.reserve(P->arena_stride * (size_t)n));
   cudaStream_t st = ctx->stream;
   const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
   Rect *d_rects = rects_dev ? reinterpret_cast<Rect *>(out_rects) : ctx->d_out_rects.as<Rect>();
   int32_t *d_counts = counts_dev ? out_counts : ctx->d_out_counts.as<int32_t>();
   if (is_device_ptr(rgba)) {
-    rc = (ctx->detect_pipe > 1) ? run_detect_piped(ctx, P, rgba, 0, n, min_neighbors, d_rects, d_counts, ctx->detect_pipe)
-                                : run_detect(ctx, P, rgba, 0, n, min_neighbors, d_rects, d_counts);
+    rc = run_detect(ctx, P, rgba, 0, n, min_neighbors, d_rects, d_counts);
     if (rc != HT_OK) return rc;
   } else {
     // host frames: the H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c
@@ -1154,7 +1202,6 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   if (rc != HT_OK) return rc;
   rc = ensure_tracker_buffers(ctx);
   if (rc != HT_OK) return rc;
-  CK(ctx->arena.reserve(P->arena_stride * (size_t)n));
   if (n_calls > 0) CK(ctx->bins.reserve((size_t)n * w * h * sizeof(uint16_t)));
   cudaStream_t st = ctx->stream;
   const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
@@ -1178,6 +1225,10 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   int parts = use_aux ? ((n >= 512) ? 4 : (n >= 128 ? 2 : 1)) : 1;
   if (use_aux && ctx->overlap_parts > 1) parts = std::min(ctx->overlap_parts, std::max(1, n / 32));
   auto part_begin = [&](int p) { return (int)(((long long)n * p) / parts); };
+  auto hist_out = [&](int f0) {
+    return n_calls > 0 ? HistOut{ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096, ctx->bins.as<uint16_t>() + (size_t)f0 * w * h}
+                       : HistOut{nullptr, nullptr};
+  };
   if (use_aux && parts > 1 && !ctx->aux_stream) {
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->aux_done, cudaEventDisableTiming));
@@ -1198,9 +1249,7 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   if (is_device_ptr(rgba)) {
     for (int p = 0; p < parts; ++p) {
       const int f0 = part_begin(p), nf = part_begin(p + 1) - f0;
-      rc = (ctx->detect_pipe > 1 && parts == 1)
-               ? run_detect_piped(ctx, P, rgba, f0, nf, min_neighbors, d_rects, d_counts, ctx->detect_pipe)
-               : run_detect(ctx, P, rgba, f0, nf, min_neighbors, d_rects, d_counts);
+      rc = run_detect(ctx, P, rgba, f0, nf, min_neighbors, d_rects, d_counts, hist_out(f0));
       if (rc != HT_OK) return rc;
       rc = track_part(rgba, f0, nf);
       if (rc != HT_OK) return rc;
@@ -1217,7 +1266,7 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
     for (int c = 0; c < n_chunks; ++c) {
       const int f0 = c * chunk, nf = std::min(chunk, n - f0);
       CK(cudaStreamWaitEvent(st, ctx->chunk_events[c], 0));
-      rc = run_detect(ctx, P, d_frames, f0, nf, min_neighbors, d_rects, d_counts);
+      rc = run_detect(ctx, P, d_frames, f0, nf, min_neighbors, d_rects, d_counts, hist_out(f0));
       if (rc != HT_OK) return rc;
       const int done_to = f0 + nf;
       while (next_part < parts && part_begin(next_part + 1) <= done_to) {
@@ -1356,10 +1405,18 @@ int ht_debug_plane(ht_ctx *ctx, int frame, int slot, int q, uint8_t *out, int ca
   if (w) *w = pl.w;
   if (h) *h = pl.h;
   if (!out || cap_bytes < pl.w * pl.h) return ctx->fail(HT_ERR_ARG, "output too small");
+  if (frame < ctx->last_wave_f0 || frame >= ctx->last_wave_f0 + ctx->last_wave_n || !ctx->last_wave_arena)
+    return ctx->fail(HT_ERR_STATE, "the pyramid of frame %d is no longer resident (only the last wave of %d frames is; see HT_WAVE)",
+                     frame, ctx->wave_frames);
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy2D(out, pl.w, ctx->arena.as<uint8_t>() + (size_t)frame * P->arena_stride + pl.off, pl.pitch, pl.w, pl.h,
-                  cudaMemcpyDeviceToHost));
+  // the arena is frame-quad-interleaved: one word per pixel, byte f = frame within its quad
+  const int rel = frame - ctx->last_wave_f0;
+  std::vector<uint32_t> words((size_t)pl.pitch * pl.h);
+  CK(cudaMemcpy(words.data(), ctx->last_wave_arena + (size_t)(rel / 4) * P->arena_stride + pl.off, words.size() * 4,
+                cudaMemcpyDeviceToHost));
+  for (int y = 0; y < pl.h; ++y)
+    for (int x = 0; x < pl.w; ++x) out[(size_t)y * pl.w + x] = (uint8_t)(words[(size_t)y * pl.pitch + x] >> (8 * (rel & 3)));
   return HT_OK;
 }
 
@@ -1374,6 +1431,12 @@ int ht_debug_raw(ht_ctx *ctx, int frame, ht_rect *out, int cap, int32_t *count) 
   const int ncopy = std::min<int>(std::min<uint32_t>(c, (uint32_t)ctx->raw_cap), cap);
   if (out && ncopy > 0)
     CK(cudaMemcpy(out, ctx->sorted.as<Rect>() + (size_t)frame * ctx->raw_cap, sizeof(Rect) * ncopy, cudaMemcpyDeviceToHost));
+  return HT_OK;
+}
+
+int ht_debug_set_exactness(ht_ctx *ctx, int flags) {
+  if (!ctx) return HT_ERR_ARG;
+  ctx->force_ties = flags;
   return HT_OK;
 }
 
@@ -1412,3 +1475,69 @@ int ht_debug_model_hist(ht_ctx *ctx, int slot, uint32_t *out4096) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Host-only self-test of the cascade parser and the late-stage schedule (no device needed):
+//   nvcc -DHT_HOST_SELFTEST -o ht_selftest ht_api.cu && ./ht_selftest ../data/cascade_face.bin
+// Prints one JSON line; tests/test_late_schedule.py checks it.
+#ifdef HT_HOST_SELFTEST
+int main(int argc, char **argv) {
+  if (argc < 2) { fprintf(stderr, "usage: %s cascade.bin\n", argv[0]); return 2; }
+  FILE *f = fopen(argv[1], "rb");
+  if (!f) { perror("open"); return 2; }
+  std::vector<uint8_t> blob;
+  uint8_t buf[4096];
+  size_t got;
+  while ((got = fread(buf, 1, sizeof(buf), f)) > 0) blob.insert(blob.end(), buf, buf + got);
+  fclose(f);
+  HostCascade hc;
+  std::string err;
+  const int rc = parse_cascade(blob.data(), blob.size(), hc, err);
+  if (rc != HT_OK) { fprintf(stderr, "parse_cascade: %s\n", err.c_str()); return 1; }
+  const ConstCascade &cc = hc.cc;
+  const int late_first = cc.group_first[cc.n_groups];
+  // every feature of a late stage appears exactly once, with its points and its alpha
+  long long bad = 0, used_slots = 0, used_instr = 0, conflicts = 0;
+  for (int j = late_first; j < hc.n_stages; ++j) {
+    std::vector<int> seen((size_t)cc.stage[j].count, 0);
+    for (int ch = hc.late_chunk0[j]; ch < hc.late_chunk0[j + 1]; ++ch) {
+      for (int s = 0; s < 10; ++s) {
+        int bank_word[32];
+        for (int &v : bank_word) v = -1;
+        bool any = false;
+        for (int lane = 0; lane < 32; ++lane) {
+          const uint16_t o = hc.late[(size_t)ch * 32 + lane].off[s];
+          if (o == 0xFFFF) continue;
+          any = true; ++used_slots;
+          const int word = o & 0x7fff;
+          if (bank_word[word & 31] >= 0 && bank_word[word & 31] != word) ++conflicts;
+          bank_word[word & 31] = word;
+        }
+        used_instr += any ? 1 : 0;
+      }
+      for (int lane = 0; lane < 32; ++lane) {
+        const LateFeat &lf = hc.late[(size_t)ch * 32 + lane];
+        std::vector<uint16_t> p, n;
+        for (int s = 0; s < 5; ++s) if (lf.off[s] != 0xFFFF) p.push_back(lf.off[s]);
+        for (int s = 5; s < 10; ++s) if (lf.off[s] != 0xFFFF) n.push_back(lf.off[s]);
+        if (p.empty() && n.empty()) { if (lf.a_int != 0) ++bad; continue; }
+        std::sort(p.begin(), p.end()); std::sort(n.begin(), n.end());
+        int match = -1;
+        for (int k = cc.stage[j].first; k < cc.stage[j].first + cc.stage[j].count && match < 0; ++k) {
+          if (seen[(size_t)(k - cc.stage[j].first)]) continue;
+          std::vector<uint16_t> kp(cc.off[k], cc.off[k] + (cc.np_nn[k] & 15)), kn(cc.off[k] + 5, cc.off[k] + 5 + (cc.np_nn[k] >> 4));
+          std::sort(kp.begin(), kp.end()); std::sort(kn.begin(), kn.end());
+          if (kp == p && kn == n && llround(cc.alpha[k] * 1e8) == lf.a_int) match = k;
+        }
+        if (match < 0) ++bad; else seen[(size_t)(match - cc.stage[j].first)] = 1;
+      }
+    }
+    for (int v : seen) if (!v) ++bad;
+  }
+  printf("{\"n_stages\": %d, \"n_features\": %d, \"fast\": %d, \"n_groups\": %d, \"late_first\": %d, \"chunks\": %d, "
+         "\"bad\": %lld, \"point_loads\": %lld, \"load_instr_with_traffic\": %lld, \"bank_conflicts\": %lld, \"late_conflicts\": %d}\n",
+         hc.n_stages, hc.n_features, hc.fast ? 1 : 0, cc.n_groups, late_first, hc.late_chunk0[hc.n_stages], bad, used_slots,
+         used_instr, conflicts, hc.late_conflicts);
+  return bad ? 1 : 0;
+}
+#endif

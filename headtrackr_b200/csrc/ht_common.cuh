@@ -16,40 +16,58 @@
 namespace ht {
 
 // ------------------------------------------------------------------------------------------------
-// Cascade-tile geometry (k_cascade).  A tile is TW x TH quarter-resolution window positions x 4
-// phases.  All three pyramid levels a window reads are staged in shared memory in an "expanded"
-// layout so that EVERY feature point of window (lx,ly,q) sits at  a0 + constant  with the single
-// per-window base  a0 = (4*lx + 2*dx) + (4*ly + 2*dy) * TP :
-//   region A, level 0 (full res)  pixel (X,Y)            at  A + Y*TP + X
-//   region B, level 1 (half res)  pixel (X,Y)            at  B + (2*Y+1)*TP + 2*X
-//   region B, level 2 (quarter res, phase copy q)        at  B + (4*Y + 2*dy)*TP + 4*X + 2*dx
-// A window's level-1 origin is (2lx+dx, 2ly+dy) and its level-2 origin is (lx,ly) in copy q
-// (src/ccv.js:179-180,235-241), which makes the three address forms collapse onto a0.
-// Adjacent lanes (lx, lx+1) are 4 bytes apart in every level -> conflict-free shared-memory reads.
+// Frame quads.  The pyramid arena is stored FRAME-QUAD-INTERLEAVED: one 32-bit word per pixel holds the gray
+// value of that pixel in four consecutive frames of the batch (byte f = frame & 3).  One LDS.32 / LDG.32 therefore
+// serves the same window of four frames, the resampler's tap arithmetic is shared by four frames, and a window's
+// base address never splits a bank word (round 1 lost 23 % of its shared-memory wavefronts to that).
+// Arena of quad g starts at g * quad_stride words; plane offsets and pitches are in WORDS (pitch % 4 == 0).
+//
+// Cascade-tile geometry (k_cascade).  A tile is TW x TH quarter-resolution window positions x 4 phases x 4 frames.
+// With u = 2*lx + dx in [0, 2*TW) and v = 2*ly + dy in [0, 2*TH) the three pyramid levels a window reads are staged
+// in shared memory so that EVERY feature point is  base + constant  with two per-window bases
+//     baseA = v * (2*P0) + u          (level 0)            baseB = v * P1 + u      (levels 1 and 2)
+//   level 0 (full res), pixel (X,Y)      : word  Y*P0 + (X&1)*H0 + (X>>1)            (columns split by parity, so that
+//                                           the 32 windows u..u+31 of a warp read 32 consecutive words)
+//   level 1 (half res), pixel (X,Y)      : word  W1 + Y*P1 + X
+//   level 2 (quarter res), phase copy q  : word  W2 + (2*Y + dy)*P2 + 2*X + dx       (the four copies interleaved)
+// A window's level-0 origin is (2u, 2v), its level-1 origin (u, v), its level-2 origin (lx, ly) in copy q
+// (src/ccv.js:179-180,235-241).  2*P0 == P1 == P2 (mod 32), so bank(baseA) == bank(baseB) == (u + 12 v) & 31: the
+// "bank class" of the window.  Lane L only ever evaluates class-L windows -> conflict-free loads in every stage.
 constexpr int TW = 32;
 constexpr int TH = 16;
-#ifndef HT_TILE_PITCH
-#define HT_TILE_PITCH 160
-#endif
-constexpr int TP = HT_TILE_PITCH;             // tile pitch in bytes (>= 4*TW+22, multiple of 4; TMA staging needs % 16)
-constexpr int TILE_FILL_COLS = 160;           // level-0 columns staged per row (ten 16 B vectors)
-constexpr int TILE_ROWS = 4 * TH + 22;        // 86 level-0 rows: 4*(TH-1)+2+23+1
-constexpr int REGION = TILE_ROWS * TP;        // bytes per region
+constexpr int L0_COLS = 4 * TW + 22;          // 150 level-0 columns
+constexpr int L0_ROWS = 4 * TH + 22;          // 86
+constexpr int H0 = L0_COLS / 2;               // 75: word offset of the odd-column half of a level-0 row
+constexpr int P0 = L0_COLS;                   // 150 words per level-0 row
 constexpr int L1_ROWS = 2 * TH + 11;          // 43
 constexpr int L1_COLS = 2 * TW + 11;          // 75
-constexpr int L2_ROWS = TH + 5;               // 21
-constexpr int L2_COLS = TW + 5;               // 37
-constexpr int NWIN = TW * TH * 4;             // windows per tile
-// shared-memory bank of a window's base a0 = 4lx + 2dx + (4ly + 2dy) * TP  (bank = word index mod 32)
-__host__ __device__ constexpr int bank_class(int lx, int ly, int dy) { return (lx + (4 * ly + 2 * dy) * (TP / 4)) & 31; }
-constexpr int CASCADE_THREADS = 256;
+constexpr int P1 = 76;
+constexpr int L2_ROWS = TH + 5;               // 21 per copy
+constexpr int L2_COLS = TW + 5;               // 37 per copy
+constexpr int P2 = 76;
+constexpr int W1 = L0_ROWS * P0;              // 12900
+constexpr int W2 = W1 + L1_ROWS * P1;         // 16168
+constexpr int TILE_WORDS = W2 + 2 * L2_ROWS * P2;   // 19360 words = 77,440 B
+static_assert((2 * P0 - P1) % 32 == 0 && P1 == P2, "bank classes of the two bases must coincide");
+static_assert(2 * L2_COLS <= P2 && L1_COLS <= P1, "tile pitches");
+constexpr int NQUADWIN = TW * TH * 4;         // window positions per tile (each x 4 frames)
+constexpr int NWIN = NQUADWIN * 4;            // windows per tile
+constexpr int CLASS_CAP = NWIN / 32;          // 256: windows of one bank class in a tile
+constexpr int CASCADE_THREADS = 512;
+constexpr int CASCADE_WARPS = CASCADE_THREADS / 32;
+// shared-memory WORD offset of point (z, x, y) of the 24x24 window relative to baseA (z == 0) or baseB (z > 0)
+__host__ __device__ constexpr int point_word(int z, int x, int y) {
+  return z == 0 ? y * P0 + (x & 1) * H0 + (x >> 1) : z == 1 ? W1 + y * P1 + x : W2 + 2 * y * P2 + 2 * x;
+}
+__host__ __device__ constexpr int bank_class(int u, int v) { return (u + 12 * v) & 31; }
+static_assert((2 * P0) % 32 == 12 && P1 % 32 == 12, "bank_class assumes v * 12");
 
 constexpr int MAX_STAGES = 64;
 constexpr int MAX_GROUPS = 16;
 
 struct DevPlane {
-  uint32_t off;   // byte offset inside the per-frame arena
-  int32_t pitch;  // bytes per row (multiple of 16)
+  uint32_t off;   // WORD offset inside the per-quad arena (one word = the pixel in 4 frames)
+  int32_t pitch;  // words per row (multiple of 4 -> rows are 16 B aligned)
   int32_t w, h;
 };
 
@@ -101,14 +119,14 @@ struct DevStage {
 };
 
 struct ConstCascade {
-  // shared-memory byte offsets relative to a0; valid p points first (np of them), then repeats of
-  // slot 0; same for n.  Layout [feature][p0..p4, n0..n4].
+  // shared-memory WORD offsets (point_word) relative to baseA, or to baseB when bit 15 is set; valid p points first
+  // (np of them), then repeats of slot 0; same for n.  Layout [feature][p0..p4, n0..n4].
   uint16_t off[MAX_FEATS][10];
   double alpha[MAX_FEATS];     // alpha[2k+1] (pass); alpha[2k] == -alpha[2k+1] is checked on the host
   uint8_t np_nn[MAX_FEATS];    // np | nn << 4   (1..5 each)
   DevStage stage[MAX_STAGES];
   int32_t n_stages;
-  int32_t n_groups;                     // lane-per-window stage groups (queue compaction between them)
+  int32_t n_groups;                     // lane-per-window stage groups (survivor lists between them)
   int32_t group_first[MAX_GROUPS + 1];  // their stage boundaries; stages >= group_first[n_groups] are "late"
   int32_t late_int;                     // 1: late stages run warp-per-window with exact integer sums
   int64_t thr_int[MAX_STAGES];          // stage thresholds x 1e8 (exact, see LateFeat)
@@ -121,11 +139,15 @@ struct ConstCascade {
 // distinct decimal sums differ by >= 1e-8: `sum < threshold` (src/ccv.js:222) is therefore decided
 // exactly by the integers unless they are EQUAL, in which case the stage is re-evaluated with the
 // reference's ordered fp64 adds.  The confidence of a surviving window is always the ordered fp64 sum.
+//
+// Because an exact integer sum may be taken in any order, the features of a late stage are re-arranged on the
+// host (build_late_schedule) into chunks of 32 records - lane L of the warp takes record L of every chunk - such
+// that within a chunk the 32 offsets of each load slot fall into different shared-memory banks (all lanes add the
+// same per-window base, so conflicts depend only on the offsets).  Unused slots hold 0xFFFF and cost no access.
 struct alignas(16) LateFeat {
-  uint16_t off[10];  // p0..p4, n0..n4 (compacted, as ConstCascade::off)
-  int32_t a_int;     // alpha[2k+1] * 1e8
-  uint8_t np, nn;
-  uint8_t pad_[6];
+  uint16_t off[10];  // slots 0-4: p points, 5-9: n points (ConstCascade::off encoding); 0xFFFF = unused
+  int32_t a_int;     // alpha[2k+1] * 1e8 (0 for the padding records of a stage's last chunk)
+  uint32_t pad_[2];
 };
 static_assert(sizeof(LateFeat) == 32, "LateFeat is two 16-byte loads");
 static_assert(sizeof(ConstCascade) <= 65536 - 1024, "cascade must fit the constant bank");

@@ -2,77 +2,152 @@
 // (/root/reference/src/ccv.js:22-32, 109-333).  No tensor cores: byte compares + ordered fp64 adds.
 // The whole library is compiled with -fmad=false so that every a*b+c below is two IEEE roundings,
 // as in JavaScript.
+//
+// Everything between the caller's RGBA frames and the raw detection list works on FRAME QUADS: the pyramid arena
+// holds one 32-bit word per pixel = that pixel in four consecutive frames (ht_common.cuh).
 #pragma once
 #include "ht_common.cuh"
 
 namespace ht {
 
-// ------------------------------------------------------------------------------------------------
-// K1  grayscale — src/ccv.js:28-29:  gray = ToUint8Clamp(r*0.3 + g*0.59 + b*0.11)  (fp64, RN-even)
-// One thread per 4 horizontally adjacent pixels: one 16 B load, one 4 B store into plane 0.
-// HBM-bound: 4 B read + 1 B written per pixel.
-__device__ __forceinline__ uint32_t gray_of(uint32_t px) {
-  const double r = (double)(px & 0xffu), g = (double)((px >> 8) & 0xffu), b = (double)((px >> 16) & 0xffu);
-  const double v = __dadd_rn(__dadd_rn(__dmul_rn(r, 0.3), __dmul_rn(g, 0.59)), __dmul_rn(b, 0.11));
-  int iv = __double2int_rn(v);  // round half to even == Uint8ClampedArray store
-  return (uint32_t)min(iv, 255);
+__device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:63-66, 345-348
+  return ((px & 0xf0u) << 4) | ((px >> 8) & 0xf0u) | ((px >> 20) & 0xfu);
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, size_t frame_bytes,
-                                              uint8_t *__restrict__ arena, size_t arena_stride,
-                                              int w, int h, int pitch0, int quads_per_row) {
-  const int frame = blockIdx.y;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t row = t / (uint32_t)quads_per_row;
-  if (row >= (uint32_t)h) return;
-  const int col = (int)(t - row * (uint32_t)quads_per_row) * 4;
-  const uint8_t *src = rgba + (size_t)frame * frame_bytes + ((size_t)row * w + col) * 4;
-  uint32_t px[4] = {0, 0, 0, 0};
-  if (VEC) {  // w % 4 == 0 and 16 B aligned base
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
-    px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (col + i < w) px[i] = (uint32_t)src[4 * i] | ((uint32_t)src[4 * i + 1] << 8) | ((uint32_t)src[4 * i + 2] << 16);
+// ------------------------------------------------------------------------------------------------
+// K1  grayscale — src/ccv.js:28-29:  gray = ToUint8Clamp(r*0.3 + g*0.59 + b*0.11)  (fp64, left to right, RN-even)
+//
+// No integer formula reproduces this: with q = 30r + 59g + 11b the exact value is q/100, and for the 167,836 of the
+// 2^24 triples with q % 100 == 50 the fp64 sum lands on either side of k + 0.5 (226 of the 253 tie values of q go
+// BOTH ways depending on (r,g,b): tests/test_gray_formula.py), so the three products and two sums are kept in fp64.
+// What round 1 paid for were the int<->fp64 CONVERSIONS (I2F.F64 / F2I.F64 run at a quarter of the fp64 rate): here
+// a byte becomes a double by planting it in the mantissa of 2^52 and subtracting 2^52 (exact), and the round-half-
+// even store is `v + 2^52` read back from the low mantissa bits (exact for 0 <= v < 2^31; proven equal to
+// rint() for every triple in the same test).  9 fp64 pipe operations per pixel, no conversions.
+__device__ __forceinline__ uint32_t gray_of(uint32_t px) {
+  const double M = 4503599627370496.0;   // 2^52
+  const double r = __dsub_rn(__hiloint2double(0x43300000, (int)(px & 0xffu)), M);
+  const double g = __dsub_rn(__hiloint2double(0x43300000, (int)((px >> 8) & 0xffu)), M);
+  const double b = __dsub_rn(__hiloint2double(0x43300000, (int)((px >> 16) & 0xffu)), M);
+  const double v = __dadd_rn(__dadd_rn(__dmul_rn(r, 0.3), __dmul_rn(g, 0.59)), __dmul_rn(b, 0.11));
+  const uint32_t iv = (uint32_t)__double2loint(__dadd_rn(v, M));   // round half to even == Uint8ClampedArray store
+  return min(iv, 255u);
+}
+
+// One thread = 4 horizontally adjacent pixels of the 4 frames of a quad: four 16 B loads (one per frame), sixteen
+// gray values, one 16 B store of 4 interleaved words into plane 0.  HIST additionally builds what camshift needs
+// from the same read of the frame (src/camshift.js:49-72 via :268): the 4096-bin RGB histogram of each frame
+// (shared-memory atomics, flushed per CTA) and the u16 plane of weight-table offsets (8 * bin) that k_track reads.
+// grid = (chunks, quads).  HBM-bound: 4 B read + 1 B (+ 2 B) written per pixel.
+template <bool VEC, bool HIST>
+__global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_frames,
+                                              uint32_t *__restrict__ arena, size_t quad_stride, int w, int h,
+                                              int pitch0, uint32_t *__restrict__ hist, uint16_t *__restrict__ bins,
+                                              int chunks) {
+  extern __shared__ uint32_t sh_hist[];   // HIST: [4][4096]
+  const int quad = blockIdx.y;
+  if (HIST) {
+    for (int i = threadIdx.x; i < 4 * 4096; i += 256) sh_hist[i] = 0;
+    __syncthreads();
   }
-  uint32_t out = 0;
+  const int gpr = pitch0 >> 2;                        // groups of 4 pixels per plane row (pad columns included)
+  const int n_groups = gpr * h;
+  const int per = (n_groups + chunks - 1) / chunks;
+  const int beg = blockIdx.x * per, end = min(n_groups, beg + per);
+  const int n_px = w * h;
+  uint32_t *dst_plane = arena + (size_t)quad * quad_stride;
+  const int f_valid = min(4, n_frames - 4 * quad);    // frames of this quad that exist
+  for (int it = beg + threadIdx.x; it < end; it += 256) {
+    const int row = it / gpr, col = (it - row * gpr) * 4;
+    uint32_t px[4][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t gv = (col + i < w) ? gray_of(px[i]) : 0u;  // pad columns are written as 0
-    out |= gv << (8 * i);
+    for (int f = 0; f < 4; ++f) {
+      px[f][0] = px[f][1] = px[f][2] = px[f][3] = 0;
+      if (f < f_valid && col < w) {
+        const uint8_t *src = rgba + (size_t)(4 * quad + f) * frame_bytes + ((size_t)row * w + col) * 4;
+        if (VEC) {  // w % 4 == 0 and 16 B aligned frames
+          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+          px[f][0] = v.x; px[f][1] = v.y; px[f][2] = v.z; px[f][3] = v.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (col + i < w) px[f][i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
+        }
+      }
+    }
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      out[i] = 0;
+      if (col + i < w) {            // pad columns and missing frames are written as 0
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          if (f < f_valid) out[i] |= gray_of(px[f][i]) << (8 * f);
+      }
+    }
+    *reinterpret_cast<uint4 *>(dst_plane + (size_t)row * pitch0 + col) = make_uint4(out[0], out[1], out[2], out[3]);
+    if (HIST) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        if (f >= f_valid || col >= w) continue;
+        uint32_t b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          b[i] = rgb_bin(px[f][i]);
+          if (col + i < w) atomicAdd(&sh_hist[f * 4096 + b[i]], 1u);
+        }
+        if (bins) {
+          uint16_t *bo = bins + (size_t)(4 * quad + f) * n_px + (size_t)row * w + col;
+          if (VEC) {
+            *reinterpret_cast<uint2 *>(bo) = make_uint2((b[0] << 3) | (b[1] << 19), (b[2] << 3) | (b[3] << 19));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (col + i < w) bo[i] = (uint16_t)(b[i] << 3);
+          }
+        }
+      }
+    }
   }
-  *reinterpret_cast<uint32_t *>(arena + (size_t)frame * arena_stride + (size_t)row * pitch0 + col) = out;
+  if (HIST) {
+    __syncthreads();
+    for (int f = 0; f < f_valid; ++f) {
+      uint32_t *out = hist + (size_t)(4 * quad + f) * 4096;
+      if (chunks == 1) {
+        for (int i = threadIdx.x; i < 4096; i += 256) out[i] = sh_hist[f * 4096 + i];
+      } else {
+        for (int i = threadIdx.x; i < 4096; i += 256)
+          if (sh_hist[f * 4096 + i]) atomicAdd(&out[i], sh_hist[f * 4096 + i]);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2  pyramid level = canvas-shim drawImage (exact integer bilinear, see oracle/ht_oracle.h and
 // src/ccv.js:121,128,135,140,145).  One launch per pyramid "generation" (levels whose sources are
-// complete).  Block = 32 x 32 pixels of one destination plane; thread = one column x 4 rows.
-// Tap positions / weights come from per-job tables read with 16 B loads (computing them on the fly with magic
-// divisions was measured slower: 4.04 vs 3.89 ms per 1024 frames).
-__global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8_t *__restrict__ arena,
-                                                  size_t arena_stride) {
+// complete).  Block = 32 x 32 pixels of one destination plane of one frame quad; thread = one column x 4 rows.
+// Every load and store is a whole word (4 frames): the tap positions, weights and addresses - most of round 1's
+// 43 instructions per output pixel - are computed once for four frames.
+__global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint32_t *__restrict__ arena,
+                                                  size_t quad_stride) {
   // per-block metadata: one 8 B tile record and one 64 B job record, fetched with vector loads
   const uint2 tl = __ldg(reinterpret_cast<const uint2 *>(plan.pyr_tiles + tile0 + blockIdx.x));
   const int job_id = (int)(tl.x & 0xffffu), tx = (int)(tl.x >> 16), ty = (int)(tl.y & 0xffffu);
   const uint4 *jp = reinterpret_cast<const uint4 *>(plan.jobs + job_id);
-  const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1), j2 = __ldg(jp + 2), j3 = __ldg(jp + 3);
+  const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1), j2 = __ldg(jp + 2);
   // DevJob: {src_off, dst_off, src_pitch, dst_pitch} {dst_h, dw, dh, col_off} {row_off, magic, shift, half} {..}
   const uint32_t src_off = j0.x, dst_off = j0.y;
   const int src_pitch = (int)j0.z, dst_pitch = (int)j0.w;
   const int dst_h = (int)j1.x, dw = (int)j1.y, dh = (int)j1.z;
   const uint32_t col_off = j1.w, row_off = j2.x, magic = j2.y, shift = j2.z, half = j2.w;
-  (void)j3;
-  // Block = 32 columns x 32 rows: lane = column (adjacent lanes read adjacent-ish source bytes, so one
-  // warp-wide byte load touches one or two 128 B lines), each thread produces 4 consecutive rows and reuses
-  // its column taps for all of them.
+  // lane = column (adjacent lanes read adjacent-ish source words), each thread produces 4 consecutive rows and
+  // reuses its column taps for all of them.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int X = tx * 32 + lane;
   const int Y0 = ty * 32 + warp * 4;
   if (Y0 >= dst_h || X >= dst_pitch) return;
-  uint8_t *frame = arena + (size_t)blockIdx.y * arena_stride;
+  uint32_t *quad = arena + (size_t)blockIdx.y * quad_stride;
   uint32_t xa = 0, xb = 0, wx0 = 0, wx1 = 0;
   const bool col_ok = X < dw;
   if (col_ok) {
@@ -81,10 +156,9 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
     wx1 = cx.y & 0xffffu; wx0 = 2u * (uint32_t)dw - wx1;
   }
   const uint32_t Dy = 2u * (uint32_t)dh;
-  const uint8_t *src = frame + src_off;
-  // All 16 source bytes of the thread's 4 rows are requested before any arithmetic (one exposed memory latency per
-  // thread instead of four); rows below the painted area read row taps {0, 0} and are zeroed afterwards, so the
-  // loads need no branches.  Offsets inside a plane fit 32 bits.
+  const uint32_t *src = quad + src_off;
+  // All 16 source words of the thread's 4 rows are requested before any arithmetic; rows below the painted area
+  // read row taps {0, 0} and are zeroed afterwards, so the loads need no branches.
   uint32_t oa[4], ob[4], wy1[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -101,62 +175,101 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint8
     p[r][0] = src[oa[r] + xa]; p[r][1] = src[oa[r] + xb];
     p[r][2] = src[ob[r] + xa]; p[r][3] = src[ob[r] + xb];
   }
-  uint8_t *dst = frame + dst_off + (uint32_t)Y0 * (uint32_t)dst_pitch + (uint32_t)X;
+  uint32_t *dst = quad + dst_off + (uint32_t)Y0 * (uint32_t)dst_pitch + (uint32_t)X;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int Y = Y0 + r;
     if (Y >= dst_h) break;
-    const uint32_t top = wx0 * p[r][0] + wx1 * p[r][1];   // <= 255 * 2dw
-    const uint32_t bot = wx0 * p[r][2] + wx1 * p[r][3];
-    const uint32_t num = top * (Dy - wy1[r]) + bot * wy1[r] + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
-    uint32_t q = (uint32_t)(((uint64_t)num * magic) >> shift);
-    if (!col_ok || Y >= dh) q = 0;                        // unpainted columns / rows and the pitch padding are 0
-    dst[(uint32_t)r * (uint32_t)dst_pitch] = (uint8_t)q;
+    uint32_t out = 0;
+    if (col_ok && Y < dh) {                                  // unpainted columns / rows and the pitch padding are 0
+      const uint32_t wy0 = Dy - wy1[r];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const uint32_t a = (p[r][0] >> (8 * f)) & 0xffu, b = (p[r][1] >> (8 * f)) & 0xffu;
+        const uint32_t c = (p[r][2] >> (8 * f)) & 0xffu, d = (p[r][3] >> (8 * f)) & 0xffu;
+        const uint32_t top = wx0 * a + wx1 * b;              // <= 255 * 2dw
+        const uint32_t bot = wx0 * c + wx1 * d;
+        const uint32_t num = top * wy0 + bot * wy1[r] + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
+        out |= (uint32_t)(((uint64_t)num * magic) >> shift) << (8 * f);
+      }
+    }
+    dst[(uint32_t)r * (uint32_t)dst_pitch] = out;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3  BBF cascade over all windows of one (frame, scale, tile) — src/ccv.js:178-243.
+// K3  BBF cascade over all windows of one (frame quad, scale, tile) — src/ccv.js:178-243.
 //
 // Feature test: min over the p-points > max over the n-points.  The reference's early-outs
 // (src/ccv.js:193-218) break exactly when a running min(p) <= running max(n); since min is
 // non-increasing and max non-decreasing this is equivalent to the final comparison.
-// Stage sum: sequential fp64 adds of alpha in feature order (bit-exact with the JS).
-//
-// Windows are evaluated in stage groups; survivors of a group are compacted (ballot + prefix) into
-// a shared-memory queue so that later, longer stages run on dense warps.
+// Stage sum: sequential fp64 adds of alpha in feature order (bit-exact with the JS) wherever a sum is PRODUCED
+// (the confidence of a detection) or a decision is a tie; everywhere else the decision `!(sum < threshold)` is
+// taken on exact integers or truth tables (tools/gen_cascade_code.py, LateFeat in ht_common.cuh).
 
 __constant__ ConstCascade c_casc;
 
 // ---- stages specialised at build time (tools/gen_cascade_code.py) ----
-__host__ __device__ constexpr unsigned gen_off(int z, int x, int y) {
-  return z == 0 ? (unsigned)(y * TP + x) : z == 1 ? (unsigned)(REGION + TP + 2 * x + 2 * y * TP) : (unsigned)(REGION + 4 * x + 4 * y * TP);
-}
-// sum += (pmin > nmax) ? alpha[2k+1] : alpha[2k]  with alpha[2k] == -alpha[2k+1] (src/ccv.js:194,219):
-// add `a` with its sign bit flipped unless pm > nm.  d = nm - pm is negative exactly when the feature
-// fires, so the flip mask is ~d & 0x80000000 — one IADD + one LOP3 instead of a compare and two selects.
-__device__ __forceinline__ double bbf_accumulate(double s, unsigned pm, unsigned nm, double a) {
-  const int d = (int)nm - (int)pm;
-  const int hi = __double2hiint(a) ^ (~d & (int)0x80000000);
-  return s + __hiloint2double(hi, __double2loint(a));
-}
-#define HT_W(z, x, y) ((unsigned)win[gen_off(z, x, y)])
 #define HT_MIN2(a, b) __vimin3_u32(a, b, b)      /* VIMNMX3.U32 (plain min() is turned into U16x2 + masks) */
 #define HT_MIN3(a, b, c) __vimin3_u32(a, b, c)
 #define HT_MAX2(a, b) __vimax3_u32(a, b, b)
 #define HT_MAX3(a, b, c) __vimax3_u32(a, b, c)
-#define HT_ACC(s, pm, nm, k) bbf_accumulate(s, pm, nm, c_casc.alpha[k])
-#define HT_THRESHOLD(j) (c_casc.stage[j].threshold)
+#define HT_LO(w) __byte_perm(w, 0u, 0x4240)      /* frames 0 and 2 as u16x2 */
+#define HT_HI(w) __byte_perm(w, 0u, 0x4341)      /* frames 1 and 3 as u16x2 */
+#define HT_QMIN2(a, b) __vimin3_u16x2(a, b, b)   /* VIMNMX3.U16x2 */
+#define HT_QMIN3(a, b, c) __vimin3_u16x2(a, b, c)
+#define HT_QMAX2(a, b) __vimax3_u16x2(a, b, b)
+#define HT_QMAX3(a, b, c) __vimax3_u16x2(a, b, c)
+#define HT_QCMP(nm, pm) ((nm) - (pm) + 0x80008000u)   /* bit 15 / 31 clear <=> min(p) > max(n) in that frame */
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+  return d;
+}
+// stage decision as a truth table of the four "feature did not fire" bits: x3 ? B(x0,x1,x2) : A(x0,x1,x2)
+#define HT_LUT4(x0, x1, x2, x3, A, B) lop3<0xCA>(x3, lop3<B>(x0, x1, x2), lop3<A>(x0, x1, x2))
 #include "cascade_face_gen.inc"
-#undef HT_W
+#ifndef HT_QUAD_STAGES
+#define HT_QUAD_STAGES 2   // stages the dense group evaluates in quad form (2: {0,1}; 3: {0,1,2})
+#endif
 #undef HT_MIN2
 #undef HT_MIN3
 #undef HT_MAX2
 #undef HT_MAX3
-#undef HT_ACC
-#undef HT_THRESHOLD
+#undef HT_LO
+#undef HT_HI
+#undef HT_QMIN2
+#undef HT_QMIN3
+#undef HT_QMAX2
+#undef HT_QMAX3
+#undef HT_QCMP
+#undef HT_LUT4
 
-__device__ __forceinline__ unsigned ldpx(const uint8_t *__restrict__ win, unsigned off) { return win[off]; }
+// byte address of a table offset (ConstCascade::off / LateFeat::off): bit 15 selects baseB
+__device__ __forceinline__ unsigned px_at(const uint8_t *__restrict__ tA, const uint8_t *__restrict__ tB, unsigned o) {
+  return (o & 0x8000u) ? tB[4u * (o & 0x7fffu)] : tA[4u * o];
+}
+
+// The reference's stage sum for one window: ordered fp64 adds, src/ccv.js:186-221.  All table reads are uniform.
+__device__ __noinline__ double stage_sum_ordered(const uint8_t *__restrict__ tA, const uint8_t *__restrict__ tB, int j) {
+  const int first = c_casc.stage[j].first, last = first + c_casc.stage[j].count;
+  double sum = 0.0;
+  for (int k = first; k < last; ++k) {
+    const unsigned kind = c_casc.np_nn[k];
+    const unsigned np = kind & 15u, nn = kind >> 4;
+    unsigned pmin = px_at(tA, tB, c_casc.off[k][0]);
+    unsigned nmax = px_at(tA, tB, c_casc.off[k][5]);
+    for (unsigned i = 1; i < np; ++i) pmin = min(pmin, px_at(tA, tB, c_casc.off[k][i]));
+    for (unsigned i = 1; i < nn; ++i) nmax = max(nmax, px_at(tA, tB, c_casc.off[k][5 + i]));
+    const double a = c_casc.alpha[k];
+    sum += (pmin > nmax) ? a : -a;   // src/ccv.js:194,219 (alpha[2k] == -alpha[2k+1], checked on the host)
+  }
+  return sum;
+}
+__device__ __forceinline__ bool stage_pass_ordered(const uint8_t *tA, const uint8_t *tB, int j) {
+  return !(stage_sum_ordered(tA, tB, j) < c_casc.stage[j].threshold);   // src/ccv.js:222
+}
 
 // predicated ld.shared.u8: lanes with p == false issue no shared-memory access and return dflt
 __device__ __forceinline__ unsigned lds_u8_if(unsigned saddr, bool p, unsigned dflt) {
@@ -165,354 +278,267 @@ __device__ __forceinline__ unsigned lds_u8_if(unsigned saddr, bool p, unsigned d
   return v;
 }
 
-// one stage for one window per lane; all control flow is warp-uniform (table reads are uniform)
-__device__ __forceinline__ bool stage_pass(const uint8_t *__restrict__ win, int j, bool alive, double &sum_out) {
-  const int first = c_casc.stage[j].first, last = first + c_casc.stage[j].count;
-  double sum = 0.0;
-  for (int k = first; k < last; ++k) {
-    const unsigned kind = c_casc.np_nn[k];
-    const unsigned np = kind & 15u, nn = kind >> 4;
-    unsigned pmin = ldpx(win, c_casc.off[k][0]);
-    unsigned nmax = ldpx(win, c_casc.off[k][5]);
-    if (np > 1) {
-      pmin = min(pmin, ldpx(win, c_casc.off[k][1]));
-      if (np > 2) {
-        pmin = min(pmin, ldpx(win, c_casc.off[k][2]));
-        if (np > 3) {
-          pmin = min(pmin, ldpx(win, c_casc.off[k][3]));
-          if (np > 4) pmin = min(pmin, ldpx(win, c_casc.off[k][4]));
-        }
-      }
-    }
-    if (nn > 1) {
-      nmax = max(nmax, ldpx(win, c_casc.off[k][6]));
-      if (nn > 2) {
-        nmax = max(nmax, ldpx(win, c_casc.off[k][7]));
-        if (nn > 3) {
-          nmax = max(nmax, ldpx(win, c_casc.off[k][8]));
-          if (nn > 4) nmax = max(nmax, ldpx(win, c_casc.off[k][9]));
-        }
-      }
-    }
-    sum = bbf_accumulate(sum, pmin, nmax, c_casc.alpha[k]);   // src/ccv.js:194,219
-  }
-  sum_out = sum;
-  return alive && !(sum < c_casc.stage[j].threshold);  // src/ccv.js:222
+__device__ __forceinline__ void cp_async4(unsigned saddr, const void *g, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(valid ? 4u : 0u) : "memory");
 }
 
-template <bool FAST, int MINB>
-__global__ void __launch_bounds__(CASCADE_THREADS, MINB) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
-                                                              const void *__restrict__ tmaps, int tma_frame0,
-                                                              const uint8_t *__restrict__ arena, size_t arena_stride,
-                                                              uint32_t *__restrict__ raw_keys,
-                                                              double *__restrict__ raw_conf,
-                                                              uint32_t *__restrict__ raw_count, int raw_cap) {
-  __shared__ __align__(128) uint8_t tile[2 * REGION];
-  __shared__ __align__(8) unsigned long long tma_bar;
-  __shared__ uint16_t raw[NWIN];   // [slot][class] survivor cells of the group that just ran
-  __shared__ uint16_t cl[NWIN];    // [entry][class] compacted per-bank-class lists
-  __shared__ int cnt[8][32];
-  __shared__ int len_s[32], pre_s[32];
-  __shared__ int maxlen_s, total_s;
+// Debug switches of the exactness fallbacks (ht_debug_set_exactness): bit 0 = treat every generated byte-stage
+// decision as a tie, bit 1 = treat every late-stage integer decision as a tie.  Ties are decided by
+// stage_pass_ordered, so results must not change (tests/test_gpu_fallbacks.py).
+template <bool FAST>
+__global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
+                                                                const int32_t *__restrict__ late_chunk0,
+                                                                const uint32_t *__restrict__ arena, size_t quad_stride,
+                                                                int n_frames, uint32_t *__restrict__ raw_keys,
+                                                                double *__restrict__ raw_conf,
+                                                                uint32_t *__restrict__ raw_count, int raw_cap,
+                                                                int force_ties) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t *tile = smem;                                                   // TILE_WORDS
+  uint16_t *cl0 = reinterpret_cast<uint16_t *>(smem + TILE_WORDS);         // [CLASS_CAP][32] survivor lists (ping)
+  uint16_t *cl1 = cl0 + NWIN;                                              // (pong)
+  int *cnt = reinterpret_cast<int *>(cl1 + NWIN);                          // [MAX_GROUPS + 2][32] list lengths per phase
 
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int frame = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int quad = blockIdx.y;
   const DevCascTile tl = plan.casc_tiles[blockIdx.x];
   const DevScale sc = plan.scales[tl.scale];
-  const uint8_t *fr = arena + (size_t)frame * arena_stride;
+  const uint32_t *qa = arena + (size_t)quad * quad_stride;
   const int x0 = tl.tx * TW, y0 = tl.ty * TH;  // quarter-res origin of the tile
+  const int f_valid = min(4, n_frames - 4 * quad);
 
-  // ---- stage the three levels in shared memory (layout in ht_common.cuh) ----
-  // Level 0 (13.8 KB, a plain 2-D box of the plane) is staged by the TMA engine when tensor maps are
-  // available: one elected thread issues cp.async.bulk.tensor (3-D map: column, row, frame; out-of-bounds
-  // elements are zero-filled) and the CTA waits on an mbarrier after it has scattered levels 1 and 2 itself.
-  const bool use_tma = (tmaps != nullptr) && (TP == TILE_FILL_COLS);
-  if (use_tma) {
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();   // nobody may poll the barrier before it is initialised
-    if (tid == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)REGION) : "memory");
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(tile);
-      const unsigned long long map = (unsigned long long)(reinterpret_cast<const uint8_t *>(tmaps) + 128 * (size_t)tl.scale);
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"(dst), "l"(map), "r"(4 * x0), "r"(4 * y0), "r"(tma_frame0 + frame), "r"(bar)
-          : "memory");
-    }
-  } else {
-    const DevPlane pl = plan.planes[sc.p0];
-    const uint8_t *src = fr + pl.off;
-    const int X0 = 4 * x0, Y0 = 4 * y0;
-    for (int i = tid; i < TILE_ROWS * (TILE_FILL_COLS / 16); i += CASCADE_THREADS) {
-      const int r = i / (TILE_FILL_COLS / 16), c = (i % (TILE_FILL_COLS / 16)) * 16;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (Y0 + r < pl.h && X0 + c < pl.pitch)
-        v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(Y0 + r) * pl.pitch + X0 + c));
-      if (TP % 16 == 0) {
-        *reinterpret_cast<uint4 *>(tile + r * TP + c) = v;
-      } else {   // rows are only 4 B aligned
-        uint32_t *d = reinterpret_cast<uint32_t *>(tile + r * TP + c);
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  for (int i = tid; i < (MAX_GROUPS + 2) * 32; i += CASCADE_THREADS) cnt[i] = 0;
+
+  // ---- stage the three levels in shared memory (layout in ht_common.cuh): 4-byte cp.async with the layout
+  //      permutation in the destination address; words outside a plane are zero-filled ----
+  {
+    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+    {  // level 0: parity-split columns
+      const DevPlane pl = plan.planes[sc.p0];
+      const uint32_t *src = qa + pl.off;
+      const int X0 = 4 * x0, Y0 = 4 * y0;
+      for (int i = tid; i < L0_ROWS * P0; i += CASCADE_THREADS) {
+        const int r = i / P0, c = i - r * P0;
+        const int X = (c < H0) ? 2 * c : 2 * (c - H0) + 1;
+        const bool ok = (Y0 + r < pl.h) && (X0 + X < pl.pitch);
+        cp_async4(tile_s + 4u * (unsigned)i, ok ? src + (size_t)(Y0 + r) * pl.pitch + X0 + X : src, ok);
       }
     }
-  }
-  {
-    const DevPlane pl = plan.planes[sc.p1];
-    const uint8_t *src = fr + pl.off;
-    const int X0 = 2 * x0, Y0 = 2 * y0;
-    constexpr int QC = (L1_COLS + 3) / 4;
-    for (int i = tid; i < L1_ROWS * QC; i += CASCADE_THREADS) {
-      const int r = i / QC, c = (i % QC) * 4;
-      uint32_t v = 0;
-      if (Y0 + r < pl.h && X0 + c < pl.pitch)
-        v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(Y0 + r) * pl.pitch + X0 + c));
-      uint8_t *d = tile + REGION + (2 * r + 1) * TP + 2 * c;
-      d[0] = (uint8_t)v; d[2] = (uint8_t)(v >> 8); d[4] = (uint8_t)(v >> 16); d[6] = (uint8_t)(v >> 24);
+    {  // level 1
+      const DevPlane pl = plan.planes[sc.p1];
+      const uint32_t *src = qa + pl.off;
+      const int X0 = 2 * x0, Y0 = 2 * y0;
+      for (int i = tid; i < L1_ROWS * P1; i += CASCADE_THREADS) {
+        const int r = i / P1, c = i - r * P1;
+        const bool ok = (Y0 + r < pl.h) && (X0 + c < pl.pitch);
+        cp_async4(tile_s + 4u * (unsigned)(W1 + i), ok ? src + (size_t)(Y0 + r) * pl.pitch + X0 + c : src, ok);
+      }
     }
-  }
-  {
-    constexpr int QC = (L2_COLS + 3) / 4;
-    for (int i = tid; i < 4 * L2_ROWS * QC; i += CASCADE_THREADS) {
-      const int q = i / (L2_ROWS * QC), rem = i % (L2_ROWS * QC);
-      const int r = rem / QC, c = (rem % QC) * 4;
-      const DevPlane pl = plan.planes[plan.scales[tl.scale].p2[q]];  // (indexing the register copy `sc` would spill it)
-      uint32_t v = 0;
-      if (y0 + r < pl.h && x0 + c < pl.pitch)
-        v = __ldg(reinterpret_cast<const uint32_t *>(fr + pl.off + (size_t)(y0 + r) * pl.pitch + x0 + c));
-      uint8_t *d = tile + REGION + (4 * r + 2 * (q >> 1)) * TP + 4 * c + 2 * (q & 1);
-      d[0] = (uint8_t)v; d[4] = (uint8_t)(v >> 8); d[8] = (uint8_t)(v >> 16); d[12] = (uint8_t)(v >> 24);
+    {  // level 2: the four phase copies interleaved (row 2Y+dy, column 2X+dx)
+      for (int i = tid; i < 2 * L2_ROWS * P2; i += CASCADE_THREADS) {
+        const int rr = i / P2, cc = i - rr * P2;
+        const int q = (cc & 1) | ((rr & 1) << 1), r = rr >> 1, c = cc >> 1;
+        const DevPlane pl = plan.planes[plan.scales[tl.scale].p2[q]];  // (indexing the register copy `sc` would spill it)
+        const uint32_t *src = qa + pl.off;
+        const bool ok = (y0 + r < pl.h) && (x0 + c < pl.pitch);
+        cp_async4(tile_s + 4u * (unsigned)(W2 + i), ok ? src + (size_t)(y0 + r) * pl.pitch + x0 + c : src, ok);
+      }
     }
-  }
-  if (use_tma) {   // every thread observes the completion of the bulk copy (phase 0 of the barrier)
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
-    unsigned done = 0;
-    while (!done) {
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(done) : "r"(bar) : "memory");
-    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 
-  // ---- stage groups ----
-  // Survivors of a group are kept in 32 per-BANK-CLASS lists: class(window) = (lx + 16*dy) & 31 is the shared-
-  // memory bank of the window's base a0 (TP = 160: four tile rows are a multiple of 128 B).  Lane L of every warp
-  // only ever evaluates windows of class L, so a warp's 32 pixel loads hit 32 different banks in the compacted
-  // groups too (ballot compaction of arbitrary survivors measured ~2.7 wavefronts per load).
-  //   raw[slot][class] : one writer per cell (window id or 0xFFFF), slot-major so a warp's stores are contiguous
-  //   cl[entry][class] : compacted per-class lists; len_s[class], maxlen_s, pre_s[class] (exclusive scan), total_s
-  const int warp = tid >> 5;
-  auto decode = [&](int wid, int &lx, int &ly, int &q) {
-    lx = wid & (TW - 1); ly = (wid / TW) & (TH - 1); q = wid / (TW * TH);
-    return tile + (4 * lx + 2 * (q & 1)) + (4 * ly + 2 * (q >> 1)) * TP;
-  };
-  auto emit = [&](int lx, int ly, int q, double sum) {  // src/ccv.js:227-234: (window id in reference order, last stage sum)
+  // A window of the tile is (u, v, f): u = 2 lx + dx, v = 2 ly + dy, f = frame in the quad; list entries are
+  // f << 11 | v << 6 | u.  cl[e * 32 + c] is entry e of bank class c; lane L evaluates class L.
+  const uint8_t *tile_b = reinterpret_cast<const uint8_t *>(tile);
+  auto emit = [&](int e, double sum) {  // src/ccv.js:227-234: (window id in reference order, last stage sum)
+    const int u = e & 63, v = (e >> 6) & 31, f = e >> 11;
+    const int lx = u >> 1, ly = v >> 1, q = (u & 1) | ((v & 1) << 1);
     const uint32_t key = sc.win_base + (uint32_t)((q * sc.qh + (y0 + ly)) * sc.qw + (x0 + lx));
+    const int frame = 4 * quad + f;
     const uint32_t pos = atomicAdd(&raw_count[frame], 1u);
     if (pos < (uint32_t)raw_cap) {
       raw_keys[(size_t)frame * raw_cap + pos] = key;
       raw_conf[(size_t)frame * raw_cap + pos] = sum;
     }
   };
-  // compaction of raw[0..n_slots) into the class lists; every thread calls it
-  auto compact = [&](int n_slots) {
-    __syncthreads();
-    uint16_t v[8];
-    int c = 0;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const int slot = warp * 8 + s;
-      v[s] = (slot < n_slots) ? raw[slot * 32 + lane] : (uint16_t)0xFFFFu;
-      c += (v[s] != 0xFFFFu) ? 1 : 0;
-    }
-    cnt[warp][lane] = c;
-    __syncthreads();
-    int off = 0, tot = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < 8; ++w2) {
-      const int x = cnt[w2][lane];
-      off += (w2 < warp) ? x : 0;
-      tot += x;
-    }
-#pragma unroll
-    for (int s = 0; s < 8; ++s)
-      if (v[s] != 0xFFFFu) cl[(off++) * 32 + lane] = v[s];
-    if (warp == 0) {
-      len_s[lane] = tot;
-      int mx = tot, incl = tot;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      pre_s[lane] = incl - tot;
-      if (lane == 31) total_s = incl;
-      if (lane == 0) maxlen_s = mx;
-    }
-    __syncthreads();
-  };
-  // dense first group: thread (warp, lane) owns lx = lane; iteration `it` -> q = it >> 1, ly = (it & 1) * 8 + warp
-  auto run_dense = [&](bool emit_here, auto eval) {
-    for (int it = 0; it < NWIN / CASCADE_THREADS; ++it) {
-      const int wid = it * CASCADE_THREADS + tid;
-      int lx, ly, q;
-      const uint8_t *win = decode(wid, lx, ly, q);
-      bool alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh);
-      double sum = 0.0;
-      alive = eval(win, alive, sum);
-      if (emit_here) { if (alive) emit(lx, ly, q, sum); }
-      else raw[(warp * 8 + it) * 32 + bank_class(lx, ly, q >> 1)] = alive ? (uint16_t)wid : (uint16_t)0xFFFFu;
-    }
-    return NWIN / 32;
-  };
-  // later groups: lane L takes entries warp, warp+8, ... of class L
-  auto run_lists = [&](bool emit_here, auto eval) {
-    const int ml = maxlen_s, mylen = len_s[lane];
-    for (int e = warp; e < ml; e += 8) {
-      bool alive = e < mylen;
-      const int wid = alive ? cl[e * 32 + lane] : 0;
-      int lx, ly, q;
-      const uint8_t *win = decode(wid, lx, ly, q);
-      double sum = 0.0;
-      alive = eval(win, alive, sum);
-      if (emit_here) { if (alive) emit(lx, ly, q, sum); }
-      else raw[e * 32 + lane] = alive ? (uint16_t)wid : (uint16_t)0xFFFFu;
-    }
-    return ml;
-  };
-  auto table_stages = [&](const int jb, const int je) {
-    return [=](const uint8_t *win, bool alive, double &sum) {
-      for (int j = jb; j < je; ++j) {
-        if (!__any_sync(0xffffffffu, alive)) break;
-        alive = stage_pass(win, j, alive, sum);
-      }
-      return alive;
-    };
+  auto bases = [&](int e, const uint8_t *&tA, const uint8_t *&tB) {
+    const int u = e & 63, v = (e >> 6) & 31, f = e >> 11;
+    tA = tile_b + 4 * (v * (2 * P0) + u) + f;
+    tB = tile_b + 4 * (v * P1 + u) + f;
   };
   const int late_first = c_casc.group_first[c_casc.n_groups];
   const bool has_late = late_first < c_casc.n_stages;
+  int phase = 0;   // cnt[phase] = lengths of the lists the next group reads
+  uint16_t *cl_in = cl0, *cl_out = cl1;
   int g = 0;
+
+  // ---- dense group: every window of the tile ----
   if (FAST) {
-    // specialised groups {0,1} {2,3} {4,5} {6,7} {8,9}: straight-line code generated from the cascade
-    // (cascade_face_gen.inc).  Lane-per-window stays cheaper than warp-per-window while a warp iteration still
-    // carries >~2 live windows, i.e. up to stage 9 for this cascade (stage-10 entrants: ~2 per tile).
-    static_assert(HT_GEN_STAGES == 6 || HT_GEN_STAGES == 8 || HT_GEN_STAGES == 10, "generated stages come in pairs");
-#define HT_GEN_PAIR(A, B)                                                   \
-  [&](const uint8_t *win, bool alive, double &sum) {                        \
-    alive = alive && gen_stage##A(win, sum);                                \
-    if (__any_sync(0xffffffffu, alive)) alive = gen_stage##B(win, sum) && alive; \
-    return alive;                                                           \
+    // quad form (cascade_face_gen.inc): warp iteration = one v and 32 consecutive u, lane = u & 31, 4 frames per lane
+    constexpr int NQ = HT_QUAD_STAGES < HT_GEN_QUAD_STAGES ? HT_QUAD_STAGES : HT_GEN_QUAD_STAGES;
+    static_assert(NQ == 2 || NQ == 3, "the dense group is {0,1} or {0,1,2}");
+    for (int it = warp; it < 4 * TH; it += CASCADE_WARPS) {
+      const int v = it >> 1, u = ((it & 1) << 5) | lane;
+      const int lx = u >> 1, ly = v >> 1;
+      const uint32_t *tA = tile + v * (2 * P0) + u, *tB = tile + v * P1 + u;
+      uint32_t a_lo = 0, a_hi = 0;   // alive bits: frame 0 -> lo bit 15, 2 -> lo bit 31, 1 -> hi bit 15, 3 -> hi bit 31
+      if (x0 + lx < sc.qw && y0 + ly < sc.qh) {
+        a_lo = (f_valid > 0 ? 0x8000u : 0u) | (f_valid > 2 ? 0x80000000u : 0u);
+        a_hi = (f_valid > 1 ? 0x8000u : 0u) | (f_valid > 3 ? 0x80000000u : 0u);
+      }
+#define HT_QSTAGE(J)                                                                                        \
+  if (NQ > J && __any_sync(0xffffffffu, (a_lo | a_hi) != 0u)) {                                              \
+    uint32_t p_lo, p_hi, t_lo, t_hi;                                                                         \
+    gen_q_stage##J(tA, tB, p_lo, p_hi, t_lo, t_hi);                                                          \
+    t_lo &= a_lo; t_hi &= a_hi;                                                                              \
+    if (t_lo | t_hi) { /* exact decimal tie (never seen in practice): the reference's ordered adds decide */ \
+      for (int f = 0; f < 4; ++f) {                                                                          \
+        const uint32_t bit = (f & 2) ? 0x80000000u : 0x8000u;                                                \
+        uint32_t &tt = (f & 1) ? t_hi : t_lo, &pp = (f & 1) ? p_hi : p_lo;                                   \
+        if (tt & bit) {                                                                                      \
+          const uint8_t *bA = reinterpret_cast<const uint8_t *>(tA) + f, *bB = reinterpret_cast<const uint8_t *>(tB) + f; \
+          if (!stage_pass_ordered(bA, bB, J)) pp &= ~bit;                                                    \
+        }                                                                                                    \
+      }                                                                                                      \
+    }                                                                                                        \
+    a_lo &= p_lo; a_hi &= p_hi;                                                                              \
   }
-#define HT_GEN_ONE(A)                                                       \
-  [&](const uint8_t *win, bool alive, double &sum) { return alive && gen_stage##A(win, sum); }
-#ifndef HT_SPLIT_GROUPS
-#define HT_SPLIT_GROUPS 1
+      HT_QSTAGE(0)
+      HT_QSTAGE(1)
+#if HT_GEN_QUAD_STAGES >= 3
+      HT_QSTAGE(2)
 #endif
-#if HT_SPLIT_GROUPS >= 3   // stage 1 on compacted lists (43 % of the windows survive stage 0): measured SLOWER, 12.0 vs
-                           // 11.4 ms per 1024 frames - the extra compaction of ~880 survivors per tile costs more
-                           // than the 16 % of shared-memory wavefronts it saves
-    compact(run_dense(false, HT_GEN_ONE(0)));
-    if (total_s == 0) return;
-    compact(run_lists(false, HT_GEN_ONE(1)));
-    if (total_s == 0) return;
-#else
-    compact(run_dense(false, HT_GEN_PAIR(0, 1)));
-    if (total_s == 0) return;
-#endif
-#if HT_SPLIT_GROUPS >= 1   // stages 2 and 3 as separate groups: stage 3 (91 loads) runs on re-compacted lists
-    compact(run_lists(false, HT_GEN_ONE(2)));
-    if (total_s == 0) return;
-    compact(run_lists(false, HT_GEN_ONE(3)));
-    if (total_s == 0) return;
-#else
-    compact(run_lists(false, HT_GEN_PAIR(2, 3)));
-    if (total_s == 0) return;
-#endif
-#if HT_SPLIT_GROUPS >= 2
-    compact(run_lists(false, HT_GEN_ONE(4)));
-    if (total_s == 0) return;
-    compact(run_lists(false, HT_GEN_ONE(5)));
-    if (total_s == 0) return;
-#else
-    compact(run_lists(false, HT_GEN_PAIR(4, 5)));
-    if (total_s == 0) return;
-#endif
-#if HT_GEN_STAGES >= 8
-    compact(run_lists(false, HT_GEN_PAIR(6, 7)));
-    if (total_s == 0) return;
-#endif
-#if HT_GEN_STAGES >= 10
-    compact(run_lists(false, HT_GEN_PAIR(8, 9)));
-    if (total_s == 0) return;
-#endif
-#undef HT_GEN_PAIR
-#undef HT_GEN_ONE
-    g = HT_GEN_STAGES / 2;
+#undef HT_QSTAGE
+      const uint32_t m = ((a_lo >> 15) & 1u) | ((a_hi >> 14) & 2u) | ((a_lo >> 29) & 4u) | ((a_hi >> 28) & 8u);
+      if (m) {
+        const int c = bank_class(u, v);
+        int pos = atomicAdd(&cnt[c], __popc(m));
+        const int e0 = (v << 6) | u;
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          if (m & (1u << f)) cl_in[(pos++) * 32 + c] = (uint16_t)(e0 | (f << 11));
+      }
+    }
+    g = NQ >= 3 ? 2 : 1;    // generated groups are {0,1} {2} {3} {4,5} {6,7}
+  } else {
+    // table-driven: one window of one frame per lane, ordered fp64 sums
+    const int j0 = c_casc.group_first[0], j1 = c_casc.group_first[1];
+    for (int it = warp; it < 4 * TH * 4; it += CASCADE_WARPS) {
+      const int f = it & 3, v = (it >> 2) >> 1, u = (((it >> 2) & 1) << 5) | lane;
+      const int lx = u >> 1, ly = v >> 1;
+      bool alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh) && f < f_valid;
+      const int e = (f << 11) | (v << 6) | u;
+      const uint8_t *tA, *tB;
+      bases(e, tA, tB);
+      double sum = 0.0;
+      for (int j = j0; j < j1; ++j) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        sum = stage_sum_ordered(tA, tB, j);
+        alive = alive && !(sum < c_casc.stage[j].threshold);
+      }
+      if (alive) {
+        if (c_casc.n_groups == 1 && !has_late) emit(e, sum);
+        else { const int c = bank_class(u, v); cl_in[atomicAdd(&cnt[c], 1) * 32 + c] = (uint16_t)e; }
+      }
+    }
+    if (c_casc.n_groups == 1 && !has_late) return;
+    g = 1;
   }
+  __syncthreads();
+
+  // ---- survivor lists: lane L walks the entries of class L; survivors are appended to the other buffer ----
   for (; g < c_casc.n_groups; ++g) {
+    const int jb = c_casc.group_first[g], je = c_casc.group_first[g + 1];
     const bool emit_here = (g == c_casc.n_groups - 1) && !has_late;
-    auto ev = table_stages(c_casc.group_first[g], c_casc.group_first[g + 1]);
-    const int n_slots = (g == 0) ? run_dense(emit_here, ev) : run_lists(emit_here, ev);
+    const int mylen = cnt[phase * 32 + lane];
+    int ml = mylen;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, o));
+    if (ml == 0) return;   // uniform over the CTA
+    for (int e_i = warp; e_i < ml; e_i += CASCADE_WARPS) {
+      bool alive = e_i < mylen;
+      const int e = alive ? cl_in[e_i * 32 + lane] : 0;
+      const uint8_t *tA, *tB;
+      bases(e, tA, tB);
+      double sum = 0.0;
+      for (int j = jb; j < je; ++j) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (FAST && j < HT_GEN_STAGES) {
+          int r = gen_stage(j, tA, tB);
+          if (force_ties & 1) r = -1;
+          if (r < 0) r = stage_pass_ordered(tA, tB, j) ? 1 : 0;
+          alive = alive && (r != 0);
+        } else {
+          sum = stage_sum_ordered(tA, tB, j);
+          alive = alive && !(sum < c_casc.stage[j].threshold);
+        }
+      }
+      if (alive) {
+        if (emit_here) {
+          if (FAST && je - 1 < HT_GEN_STAGES) sum = stage_sum_ordered(tA, tB, je - 1);
+          emit(e, sum);
+        } else {
+          cl_out[atomicAdd(&cnt[(phase + 1) * 32 + lane], 1) * 32 + lane] = (uint16_t)e;
+        }
+      }
+    }
     if (emit_here) return;
-    compact(n_slots);
-    if (total_s == 0) return;
+    __syncthreads();
+    ++phase;
+    uint16_t *t = cl_in; cl_in = cl_out; cl_out = t;
   }
   if (!has_late) return;
 
-  // ---- late stages: one warp per surviving window, one feature per lane, exact integer sums ----
+  // ---- late stages: one warp per surviving window, one feature per lane, exact integer sums.  The features of
+  //      a stage are pre-arranged in chunks of 32 (build_late_schedule, ht_api.cu) so that the 32 addresses of
+  //      each load slot fall into 32 different banks: the order of an exact integer sum is free ----
   {
-    // flatten the class lists (raw[] is free again after the last compaction)
-    {
-      const int mylen = len_s[lane], base = pre_s[lane];
-      for (int e = warp; e < mylen; e += 8) raw[base + e] = cl[e * 32 + lane];
+    const int mylen = cnt[phase * 32 + lane];
+    int incl = mylen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    __syncthreads();
-    const int n_in = total_s;
-    for (int w = warp; w < n_in; w += CASCADE_THREADS / 32) {
-      const int wid = raw[w];
-      int lx, ly, q;
-      const uint8_t *win = decode(wid, lx, ly, q);
+    const int total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - mylen;
+    for (int wdx = warp; wdx < total; wdx += CASCADE_WARPS) {
+      const unsigned owner = __ballot_sync(0xffffffffu, wdx >= excl && wdx < incl);
+      const int c = __ffs(owner) - 1;
+      const int e = cl_in[(wdx - __shfl_sync(0xffffffffu, excl, c)) * 32 + c];
+      const uint8_t *tA, *tB;
+      bases(e, tA, tB);
+      const unsigned sA = (unsigned)__cvta_generic_to_shared(tA), sB = (unsigned)__cvta_generic_to_shared(tB);
       bool pass = true;
       for (int j = late_first; j < c_casc.n_stages && pass; ++j) {
-        const int first = c_casc.stage[j].first, count = c_casc.stage[j].count;
         long long acc = 0;
-        for (int base = 0; base < count; base += 32) {
-          const int kk = base + lane;
-          if (kk < count) {
-            const uint4 *f = reinterpret_cast<const uint4 *>(late + first + kk);
-            const uint4 a = __ldg(f), b = __ldg(f + 1);
-            const unsigned np = b.z & 0xffu, nn = (b.z >> 8) & 0xffu;
-            // branch-free: predicated shared loads (inactive slots keep the neutral element and cost no bank traffic)
-            const unsigned wbase = (unsigned)__cvta_generic_to_shared(win);
-            unsigned pm = lds_u8_if(wbase + (a.x & 0xffffu), true, 255u);
-            unsigned nm = lds_u8_if(wbase + (a.z >> 16), true, 0u);
-            pm = __vimin3_u32(pm, lds_u8_if(wbase + (a.x >> 16), np > 1, 255u), lds_u8_if(wbase + (a.y & 0xffffu), np > 2, 255u));
-            pm = __vimin3_u32(pm, lds_u8_if(wbase + (a.y >> 16), np > 3, 255u), lds_u8_if(wbase + (a.z & 0xffffu), np > 4, 255u));
-            nm = __vimax3_u32(nm, lds_u8_if(wbase + (a.w & 0xffffu), nn > 1, 0u), lds_u8_if(wbase + (a.w >> 16), nn > 2, 0u));
-            nm = __vimax3_u32(nm, lds_u8_if(wbase + (b.x & 0xffffu), nn > 3, 0u), lds_u8_if(wbase + (b.x >> 16), nn > 4, 0u));
-            const int ai = (int)b.y;
-            acc += (pm > nm) ? (long long)ai : -(long long)ai;
+        const int c0 = late_chunk0[j], c1 = late_chunk0[j + 1];
+        for (int ch = c0; ch < c1; ++ch) {
+          const uint4 *fp = reinterpret_cast<const uint4 *>(late + (size_t)ch * 32 + lane);
+          const uint4 a = __ldg(fp), b = __ldg(fp + 1);
+          // off[0..9] = a.x lo, a.x hi, a.y lo, a.y hi, a.z lo (p) | a.z hi, a.w lo, a.w hi, b.x lo, b.x hi (n); b.y = alpha_int
+          const unsigned o[10] = {a.x & 0xffffu, a.x >> 16, a.y & 0xffffu, a.y >> 16, a.z & 0xffffu,
+                                  a.z >> 16, a.w & 0xffffu, a.w >> 16, b.x & 0xffffu, b.x >> 16};
+          unsigned vv[10];
+#pragma unroll
+          for (int s = 0; s < 10; ++s) {
+            const unsigned addr = ((o[s] & 0x8000u) ? sB : sA) + 4u * (o[s] & 0x7fffu);
+            vv[s] = lds_u8_if(addr, o[s] != 0xffffu, s < 5 ? 255u : 0u);   // unused slots: neutral element, no bank traffic
           }
+          const unsigned pm = __vimin3_u32(__vimin3_u32(vv[0], vv[1], vv[2]), vv[3], vv[4]);
+          const unsigned nm = __vimax3_u32(__vimax3_u32(vv[5], vv[6], vv[7]), vv[8], vv[9]);
+          const int ai = (int)b.y;
+          acc += (pm > nm) ? (long long)ai : -(long long)ai;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         const long long thr = c_casc.thr_int[j];
-        if (acc == thr) {  // exact tie of the decimal sums: decide with the reference's ordered fp64 adds
-          double s;
-          pass = stage_pass(win, j, true, s);
-        } else {
-          pass = acc > thr;
-        }
+        if (acc == thr || (force_ties & 2)) pass = stage_pass_ordered(tA, tB, j);   // exact tie: the reference's ordered adds
+        else pass = acc > thr;
       }
       if (pass) {  // confidence = ordered fp64 sum of the last stage
-        double s;
-        stage_pass(win, c_casc.n_stages - 1, true, s);
-        if (lane == 0) emit(lx, ly, q, s);
+        const double s = stage_sum_ordered(tA, tB, c_casc.n_stages - 1);
+        if (lane == 0) emit(e, s);
       }
     }
   }

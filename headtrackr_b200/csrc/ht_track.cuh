@@ -12,9 +12,7 @@
 
 namespace ht {
 
-__device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:63-66, 345-348
-  return ((px & 0xf0u) << 4) | ((px >> 8) & 0xf0u) | ((px >> 20) & 0xfu);
-}
+// rgb_bin() (src/camshift.js:63-66, 345-348) is defined in ht_detect.cuh: the fused gray pass uses it too.
 
 // ------------------------------------------------------------------------------------------------
 // K1'  4096-bin RGB histogram of whole frames — src/camshift.js:49-72 via :268 — plus the per-pixel
@@ -31,9 +29,18 @@ __global__ void __launch_bounds__(256) k_hist(const uint8_t *__restrict__ rgba, 
   const int n_pair = (n_px + 1) / 2;
   const int per = (n_pair + chunks - 1) / chunks;
   const int beg = blockIdx.x * per, end = min(n_pair, beg + per);
+  // the 8 B load / 4 B store of the paired path need this FRAME's pointers aligned: with an odd w*h every odd frame
+  // index starts at 4 mod 8 (and its bin plane at 2 mod 4), and the caller's pointer is only 4-byte aligned
+  const bool paired = ((reinterpret_cast<uintptr_t>(px) & 7u) == 0) && (!bout || (reinterpret_cast<uintptr_t>(bout) & 3u) == 0);
   for (int i = beg + threadIdx.x; i < end; i += 256) {
     const int p0 = 2 * i;
-    if (p0 + 1 < n_px) {
+    if (!paired) {
+      for (int p = p0; p < min(p0 + 2, n_px); ++p) {
+        const uint32_t b0 = rgb_bin(__ldg(px + p));
+        atomicAdd(&sh[b0], 1u);
+        if (bout) bout[p] = (uint16_t)(b0 << 3);
+      }
+    } else if (p0 + 1 < n_px) {
       const uint2 v = __ldg(reinterpret_cast<const uint2 *>(px + p0));
       const uint32_t b0 = rgb_bin(v.x), b1 = rgb_bin(v.y);
       atomicAdd(&sh[b0], 1u);
@@ -251,7 +258,9 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         // memo != 0: moments are a pure function of (frame, weights, window) and all three are fixed for the calls of
         // one launch, so the leader keeps the moments of the last windows it has seen and re-uses them when
         // mean-shift returns to one of them (a converged stream, or one oscillating between two windows)
-        int memo) {
+        int memo,
+        // force_serial != 0 (ht_debug_set_exactness bit 2): every pass takes the strict-order fallback
+        int force_serial) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double wsm[4096 + 1];   // [4096] = +0.0: the weight of pixels outside the window
@@ -463,7 +472,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
       for (;;) {
         double inv = 1.0 / m.m00;                                    // :109-111
         double vxf = m.m10 * inv - s.sw / 2.0, vyf = m.m01 * inv - s.sh / 2.0;
-        if (!exact && (trunc_ambiguous(vxf) || trunc_ambiguous(vyf))) {
+        if (!exact && (force_serial || trunc_ambiguous(vxf) || trunc_ambiguous(vyf))) {
           m = moments_serial(px, W, cw0, cw1, cw2, cw3, wsm);
           exact = true;
           ++st_serial;

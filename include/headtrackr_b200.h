@@ -152,6 +152,15 @@ int ht_debug_model_hist(ht_ctx *ctx, int slot, uint32_t *out4096);
 /* mean-shift counters since the last reset: {moment passes summed on the device, passes redone in strict reference
  * order, window pixels visited, track() calls, passes answered from the per-launch window memo} */
 int ht_debug_track_stats(ht_ctx *ctx, uint64_t *out5, int reset);
+/* Exactness fallbacks (tests only).  The kernels decide the integer outputs of the reference exactly with cheap
+ * arithmetic plus a fallback that reproduces the reference's own operation order when the cheap path is not
+ * conclusive.  flags force the fallbacks so that they are exercised (results must not change):
+ *   bit 0: every generated cascade-stage decision of the survivor lists is treated as an exact tie and re-decided
+ *          with ordered fp64 adds (src/ccv.js:186-222)
+ *   bit 1: the same for the late (warp-per-window, exact-integer) stages
+ *   bit 2: every mean-shift pass of ht_track re-derives its moments in the reference's strict summation order
+ *          (src/camshift.js:90-107) as if a truncation had been ambiguous */
+int ht_debug_set_exactness(ht_ctx *ctx, int flags);
 /* Window memo of ht_track / ht_detect_track (default on).  The moments of a search window depend only on the frame,
  * the histogram weights and the window, and all three are fixed for the n_calls track() calls of one launch; the
  * kernel therefore keeps the moments of the last 8 windows of a stream and re-uses them when mean-shift comes back
