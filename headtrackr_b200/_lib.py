@@ -37,6 +37,11 @@ class Window(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
 
 
+class StreamEvent(C.Structure):
+    _fields_ = [("detection", C.c_int32), ("status", C.c_int32), ("x", C.c_double), ("y", C.c_double),
+                ("width", C.c_double), ("height", C.c_double), ("angle", C.c_double), ("confidence", C.c_double)]
+
+
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
                 ("max_frames", C.c_int32), ("max_raw_per_frame", C.c_int32), ("max_rects_per_frame", C.c_int32),
@@ -64,7 +69,7 @@ def build(force=False):
 _lib = None
 
 EXPORTS = ["ht_version", "ht_create", "ht_destroy", "ht_last_error", "ht_sync", "ht_max_rects", "ht_detect",
-           "ht_track_init", "ht_track_init_from_detect", "ht_track", "ht_detect_track", "ht_backprojection", "ht_whitebalance",
+           "ht_track_init", "ht_track_init_from_detect", "ht_track", "ht_detect_track", "ht_stream_reset", "ht_stream_step", "ht_backprojection", "ht_whitebalance",
            "ht_plan_info", "ht_debug_plane", "ht_debug_raw", "ht_debug_model_hist", "ht_debug_track_stats", "ht_set_track_memo", "ht_debug_set_exactness", "ht_debug_track_trace", "ht_launch_count",
            "ht_profile", "ht_profile_read"]
 
@@ -96,6 +101,8 @@ def lib():
     L.ht_track.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.ht_detect_track.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   vp, vp, vp, vp, vp]
+    L.ht_stream_reset.argtypes = [vp, C.c_int, C.c_int]
+    L.ht_stream_step.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.ht_backprojection.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp]
     L.ht_whitebalance.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.ht_plan_info.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]

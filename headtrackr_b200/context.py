@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import HtError, Rect, TrackObj, Window
+from ._lib import HtError, Rect, StreamEvent, TrackObj, Window
 from .synth import load_cascade_blob
 
 
@@ -173,6 +173,26 @@ class Context:
         return (dets, list(found),
                 [dict(x=o.x, y=o.y, width=o.width, height=o.height, angle=o.angle) for o in objs],
                 [(w.x, w.y, w.width, w.height) for w in wins])
+
+    # ---- facetrackr state machine for n streams, on the device ----
+    def stream_reset(self, first=0, n=None):
+        """Streams [first, first+n) start over in "VJ" (a new facetrackr.Tracker with whitebalancing off)."""
+        self._check(self._L.ht_stream_reset(self._h, first, self.max_frames - first if n is None else n))
+
+    def stream_step(self, frames, interval=5, min_neighbors=1, calc_angles=False, out_events=None):
+        """One frame per stream through ht_stream_step.  -> per stream, the TrackObj facetrackr.getTrackingObject()
+        would return after track(): dict(detection="VJ"|"CS", x, y, width, height, angle, confidence, found, lost).
+        out_events (a torch CUDA uint8 tensor of n*56 bytes): asynchronous, nothing returned."""
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        if out_events is not None:
+            self._check(self._L.ht_stream_step(self._h, ptr, n, W, H, interval, min_neighbors, int(bool(calc_angles)),
+                                               out_events.data_ptr()))
+            return None
+        ev = (StreamEvent * n)()
+        self._check(self._L.ht_stream_step(self._h, ptr, n, W, H, interval, min_neighbors, int(bool(calc_angles)),
+                                           C.addressof(ev)))
+        return [dict(detection=("", "VJ", "CS")[e.detection], x=e.x, y=e.y, width=e.width, height=e.height, angle=e.angle,
+                     confidence=e.confidence, found=bool(e.status & 1), lost=bool(e.status & 2)) for e in ev]
 
     def backprojection(self, frame, slot=0):
         ptr, n, H, W, keep = _frames_ptr(frame)

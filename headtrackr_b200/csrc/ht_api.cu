@@ -500,7 +500,10 @@ struct ht_ctx {
   DevBuf d_trace;
   int track_nt = 256;                       // threads per k_track CTA (HT_TRACK_NT=128|256)
   bool track_lpt = true;                    // longest-chain-first launch order (HT_TRACK_LPT=0 disables)
-  int track_heavy_div = 0;                  // >0: the n/div streams with the largest windows run on a cluster of
+  DevBuf d_stream_mode, d_stream_mask, d_stream_cs, d_stream_init, d_stream_events;   // ht_stream_step
+  bool track_history = true;                // order by the cost of each stream's previous launch (HT_TRACK_HISTORY=0: by window area)
+  DevBuf d_track_cost;                      // [max_frames][2] {passes, window pixels / 256} per slot
+  int track_heavy_div = 64;                 // >0: the n/div costliest streams run on a cluster of
   int track_heavy_cluster = 8;              //     track_heavy_cluster CTAs on sched_stream (HT_TRACK_HEAVY=div[,cluster])
   cudaStream_t sched_stream = nullptr;
   cudaEvent_t sched_ready = nullptr, sched_done = nullptr;
@@ -589,18 +592,21 @@ int ensure_tracker_buffers(ht_ctx *ctx) {
     CK(ctx->d_objs.reserve(mf * 6 * sizeof(int32_t)));
     CK(ctx->d_windows.reserve(mf * 4 * sizeof(int32_t)));
     CK(ctx->d_sched.reserve((2 * mf + 64) * sizeof(int32_t)));
+    CK(ctx->d_track_cost.reserve(2 * mf * sizeof(int32_t)));
+    CK(cudaMemsetAsync(ctx->d_track_cost.p, 0, 2 * mf * sizeof(int32_t), ctx->stream));
     if (ctx->track_trace) CK(ctx->d_trace.reserve(4 * mf * sizeof(unsigned long long)));
   }
   return HT_OK;
 }
 
-int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_t *hist, uint16_t *bins) {
+int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_t *hist, uint16_t *bins,
+                const uint8_t *enable = nullptr) {
   const int n_px = w * h;
   int chunks = 1;
   if (n < 592) chunks = std::min(64, std::max(1, 1184 / n));  // keep ~8 CTAs per SM busy for small batches
-  if (chunks > 1) CK(cudaMemsetAsync(hist, 0, (size_t)n * 4096 * sizeof(uint32_t), ctx->stream));
+  if (chunks > 1) CK(cudaMemsetAsync(hist, 0, (size_t)n * 4096 * sizeof(uint32_t), ctx->stream));   // (also for disabled frames: harmless)
   ctx->prof_begin(HT_PROF_HIST);
-  k_hist<<<dim3(chunks, n), 256, 0, ctx->stream>>>(d_rgba, (size_t)n_px * 4, n_px, hist, bins, chunks);
+  k_hist<<<dim3(chunks, n), 256, 0, ctx->stream>>>(d_rgba, (size_t)n_px * 4, n_px, hist, bins, chunks, enable);
   ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
@@ -616,6 +622,8 @@ struct TrackOpts {
   unsigned long long *trace;   // HT_TRACK_TRACE=1: per-stream timeline buffer (else NULL)
   int memo;                    // ht_ctx::track_memo
   int force_serial;            // ht_ctx::force_ties & 4
+  int32_t *cost;               // per slot {passes, window pixels / 256} of the last launch (scheduling history)
+  const uint8_t *enable;       // ht_stream_step: per stream, 0 = not tracking this frame (else NULL)
 };
 
 template <int C, int NT = 256>
@@ -633,7 +641,7 @@ cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, 
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_track<C, NT>, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
-                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, opt.trace, opt.memo, opt.force_serial);
+                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, opt.trace, opt.memo, opt.force_serial, opt.cost, opt.enable);
 }
 
 // cluster size x CTA size chosen at run time
@@ -659,11 +667,12 @@ cudaError_t launch_track_any(int c, int nt, cudaStream_t st, int n, const uint16
 }
 
 int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h, const int32_t *d_slots, const uint32_t *mh,
-                 const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs, int32_t *d_win, int32_t *flag) {
+                 const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs, int32_t *d_win, int32_t *flag,
+                 const uint8_t *enable = nullptr) {
   unsigned long long *stats = ctx->d_flags.as<unsigned long long>() + 8;
   cudaStream_t st = ctx->stream;
   const TrackOpts opt{ctx->track_trace ? ctx->d_trace.as<unsigned long long>() + 4 * (size_t)f0 : nullptr,
-                      ctx->track_memo ? 1 : 0, (ctx->force_ties & 4) ? 1 : 0};
+                      ctx->track_memo ? 1 : 0, (ctx->force_ties & 4) ? 1 : 0, ctx->d_track_cost.as<int32_t>(), enable};
   // per-chunk scheduling scratch: [calls_done | area n][bail_list | order n][bail_count 1]
   int32_t *calls_done = ctx->d_sched.as<int32_t>() + (size_t)f0;
   int32_t *bail_list = ctx->d_sched.as<int32_t>() + (size_t)ctx->cfg.max_frames + f0;
@@ -693,9 +702,10 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
     } else {
       // longest chain first: order the streams by search-window area (k_track_area / k_track_rank); optionally the
       // n / track_heavy_div largest get a cluster of 8 on a second stream, concurrently with the others
-      k_track_area<<<(n + 255) / 256, 256, 0, st>>>(state, d_slots, n, calls_done);
+      k_track_area<<<(n + 255) / 256, 256, 0, st>>>(state, d_slots, n, ctx->track_history ? ctx->d_track_cost.as<int32_t>() : nullptr, calls_done);
       k_track_rank<<<(n + 255) / 256, 256, 0, st>>>(calls_done, n, bail_list);
       ctx->launches += 2;
+      // the costliest n / track_heavy_div streams (default 1/64: 16 of 1024) get 8-CTA clusters and start first
       const int n_heavy = (ctx->track_heavy_div > 0) ? n / ctx->track_heavy_div : 0;
       if (n_heavy > 0) {
         if (!ctx->sched_stream) {
@@ -731,7 +741,7 @@ int track_init_common(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *d
   int32_t *d_found = out_found ? (found_dev ? out_found : ctx->d_found.as<int32_t>()) : nullptr;
   ctx->prof_begin(HT_PROF_TRACK_INIT);
   k_track_init<<<n, 256, 0, ctx->stream>>>(d_rgba, (size_t)w * h * 4, w, h, d_slots, d_rects, calc_angles ? 1 : 0,
-                                           ctx->model_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), d_found);
+                                           ctx->model_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), d_found, nullptr);
   ctx->prof_end();
   ++ctx->launches;
   CK(cudaGetLastError());
@@ -771,7 +781,7 @@ struct HistOut {
 // ctx->detect_pipe the gray + pyramid kernels of wave w+1 run on a second stream (and a second arena) under the
 // cascade of wave w.
 int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n, int min_neighbors, Rect *d_rects_batch,
-               int32_t *d_counts_batch, HistOut ho = HistOut{nullptr, nullptr}) {
+               int32_t *d_counts_batch, HistOut ho = HistOut{nullptr, nullptr}, const uint8_t *quad_mask = nullptr) {
   cudaStream_t st = ctx->stream;
   const int w = P->w, h = P->h;
   const size_t frame_bytes = (size_t)w * h * 4;
@@ -804,6 +814,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
     const int nw = std::min(wave, n - w0), fa = f0 + w0, quads = (nw + 3) / 4;
     uint32_t *arena = ctx->arena.as<uint32_t>() + (piped ? (size_t)(wi & 1) * wave_words : 0);
     const uint8_t *d_rgba = d_rgba_batch + (size_t)fa * frame_bytes;
+    const uint8_t *qm = quad_mask ? quad_mask + w0 / 4 : nullptr;   // (ht_stream_step) quads of this wave that have work
     cudaStream_t ps = piped ? ctx->pipe_stream : st;
     if (piped && wi >= 2) CK(cudaStreamWaitEvent(ps, ctx->pipe_events[2 + (wi & 1)], 0));   // cascade of wave wi-2 is done with this arena
     ctx->stream = ps;
@@ -817,11 +828,11 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       ctx->prof_begin(HT_PROF_GRAY);
       const dim3 grid((unsigned)chunks, (unsigned)quads);
       if (hist) {
-        if (vec) k_gray<true, true><<<grid, 256, GRAY_HIST_SMEM, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, hp, bp, chunks);
-        else k_gray<false, true><<<grid, 256, GRAY_HIST_SMEM, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, hp, bp, chunks);
+        if (vec) k_gray<true, true><<<grid, 256, GRAY_HIST_SMEM, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, hp, bp, chunks, qm);
+        else k_gray<false, true><<<grid, 256, GRAY_HIST_SMEM, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, hp, bp, chunks, qm);
       } else {
-        if (vec) k_gray<true, false><<<grid, 256, 0, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, nullptr, nullptr, chunks);
-        else k_gray<false, false><<<grid, 256, 0, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, nullptr, nullptr, chunks);
+        if (vec) k_gray<true, false><<<grid, 256, 0, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, nullptr, nullptr, chunks, qm);
+        else k_gray<false, false><<<grid, 256, 0, ps>>>(d_rgba, frame_bytes, nw, arena, P->arena_stride, w, h, P->planes[0].pitch, nullptr, nullptr, chunks, qm);
       }
       ctx->prof_end();
       ++ctx->launches;
@@ -831,7 +842,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       const int t0 = P->gen_tile_begin[g], t1 = P->gen_tile_begin[g + 1];
       if (t1 > t0) {
         ctx->prof_begin(HT_PROF_PYRAMID);
-        k_resample<<<dim3(t1 - t0, quads), 256, 0, ps>>>(P->dplan, t0, arena, P->arena_stride);
+        k_resample<<<dim3(t1 - t0, quads), 256, 0, ps>>>(P->dplan, t0, arena, P->arena_stride, nw, qm);
         ctx->prof_end();
         ++ctx->launches;
       }
@@ -848,7 +859,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       kern<<<dim3((unsigned)P->casc_tiles.size(), quads), CASCADE_THREADS, CASC_SMEM, st>>>(
           P->dplan, ctx->d_casc.as<LateFeat>(), ctx->d_late_chunk0.as<int32_t>(), arena, P->arena_stride, nw,
           ctx->raw_keys.as<uint32_t>() + (size_t)fa * ctx->raw_cap, ctx->raw_conf.as<double>() + (size_t)fa * ctx->raw_cap,
-          ctx->raw_count.as<uint32_t>() + fa, ctx->raw_cap, ctx->force_ties);
+          ctx->raw_count.as<uint32_t>() + fa, ctx->raw_cap, ctx->force_ties, qm);
       ctx->prof_end();
       ++ctx->launches;
     }
@@ -884,7 +895,7 @@ int run_track_from_detect(ht_ctx *ctx, const uint8_t *d_rgba_batch, int w, int h
   k_pick_face<<<(n + 127) / 128, 128, 0, st>>>(d_det + (size_t)f0 * ctx->K, d_cnt + f0, ctx->K, n, d_rects4);
   k_track_init<<<n, 256, 0, st>>>(d_rgba, (size_t)w * h * 4, w, h, nullptr, d_rects4, calc_angles ? 1 : 0,
                                   ctx->model_hist.as<uint32_t>() + (size_t)f0 * 4096,
-                                  ctx->track_state.as<TrackState>() + f0, d_found ? d_found + f0 : nullptr);
+                                  ctx->track_state.as<TrackState>() + f0, d_found ? d_found + f0 : nullptr, nullptr);
   ctx->prof_end();
   ctx->launches += 2;
   if (n_calls > 0) {
@@ -979,6 +990,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
   if (const char *tt = getenv("HT_TRACK_TRACE")) c->track_trace = atoi(tt) != 0;
   if (const char *tn = getenv("HT_TRACK_NT")) c->track_nt = (atoi(tn) == 128) ? 128 : 256;
   if (const char *tl = getenv("HT_TRACK_LPT")) c->track_lpt = atoi(tl) != 0;
+  if (const char *thi = getenv("HT_TRACK_HISTORY")) c->track_history = atoi(thi) != 0;
   if (const char *th = getenv("HT_TRACK_HEAVY")) {
     c->track_heavy_div = std::max(0, atoi(th));
     if (const char *comma = strchr(th, ',')) {
@@ -1023,7 +1035,7 @@ void ht_destroy(ht_ctx *ctx) {
   for (auto &kv : ctx->plans) kv.second->dev.release();
   DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
                     &ctx->labels, &ctx->seq2, &ctx->d_out_rects, &ctx->d_out_counts, &ctx->d_flags, &ctx->model_hist,
-                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_late_chunk0, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
+                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_late_chunk0, &ctx->d_track_cost, &ctx->d_stream_mode, &ctx->d_stream_mask, &ctx->d_stream_cs, &ctx->d_stream_init, &ctx->d_stream_events, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
                     &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
   for (DevBuf *b : bufs) b->release();
   for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -1291,6 +1303,92 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   if (!objs_dev) { CK(cudaMemcpyAsync(out_objs, d_objs, sizeof(ht_trackobj) * n, cudaMemcpyDeviceToHost, st)); any_host = true; }
   if (out_windows && !win_dev) { CK(cudaMemcpyAsync(out_windows, d_win, sizeof(ht_window) * n, cudaMemcpyDeviceToHost, st)); any_host = true; }
   if (any_host) return ht_sync(ctx);
+  return HT_OK;
+}
+
+static_assert(sizeof(ht_stream_event) == sizeof(StreamEvent) && sizeof(ht_stream_event) == 56, "ht_stream_event layout");
+
+static int ensure_stream_buffers(ht_ctx *ctx) {
+  const size_t mf = (size_t)ctx->cfg.max_frames;
+  if (!ctx->d_stream_mode.p) {
+    CK(ctx->d_stream_mode.reserve(mf * sizeof(int32_t)));
+    CK(cudaMemsetAsync(ctx->d_stream_mode.p, 0, mf * sizeof(int32_t), ctx->stream));   // every stream starts in "VJ"
+    CK(ctx->d_stream_mask.reserve((mf + 3) / 4 + 16));
+    CK(ctx->d_stream_cs.reserve(mf));
+    CK(ctx->d_stream_init.reserve(mf));
+    CK(ctx->d_stream_events.reserve(mf * sizeof(StreamEvent)));
+  }
+  return HT_OK;
+}
+
+int ht_stream_reset(ht_ctx *ctx, int first, int n) {
+  if (!ctx) return HT_ERR_ARG;
+  if (first < 0 || n <= 0 || first + n > ctx->cfg.max_frames) return ctx->fail(HT_ERR_ARG, "stream range outside [0,%d)", ctx->cfg.max_frames);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_stream_buffers(ctx);
+  if (rc != HT_OK) return rc;
+  CK(cudaMemsetAsync(ctx->d_stream_mode.as<int32_t>() + first, 0, (size_t)n * sizeof(int32_t), ctx->stream));
+  return HT_OK;
+}
+
+// One frame of n independent streams through facetrackr's state machine, entirely on the device:
+//   streams in "VJ": gray + pyramid + cascade + grouping on their frame (masked frame quads), max-confidence pick,
+//                    confidence gate, initTracker on the same frame, switch to "CS"        src/facetrackr.js:67-126,137-175
+//   streams in "CS": histogram + one camshift track() on their frame; a 0-sized result switches the stream back to
+//                    "VJ" for the next frame                                                src/facetrackr.js:178-209, src/main.js:230-244
+// No host round trip between the kernels; the host only drains the event records.
+int ht_stream_step(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors, int calc_angles,
+                   ht_stream_event *out_events) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!out_events) return ctx->fail(HT_ERR_ARG, "out_events is NULL");
+  int rc = check_batch(ctx, n);
+  if (rc != HT_OK) return rc;
+  CK(cudaSetDevice(ctx->cfg.device));
+  Plan *P = nullptr;
+  rc = get_plan(ctx, w, h, interval, &P);
+  if (rc != HT_OK) return rc;
+  rc = ensure_tracker_buffers(ctx);
+  if (rc != HT_OK) return rc;
+  rc = ensure_stream_buffers(ctx);
+  if (rc != HT_OK) return rc;
+  const uint8_t *d_rgba = nullptr;
+  rc = device_frames(ctx, rgba, n, w, h, &d_rgba);
+  if (rc != HT_OK) return rc;
+  CK(ctx->bins.reserve((size_t)n * w * h * sizeof(uint16_t)));
+  cudaStream_t st = ctx->stream;
+  int32_t *mode = ctx->d_stream_mode.as<int32_t>();
+  uint8_t *vj_mask = ctx->d_stream_mask.as<uint8_t>(), *cs_en = ctx->d_stream_cs.as<uint8_t>(), *init_en = ctx->d_stream_init.as<uint8_t>();
+  k_stream_plan<<<(n + 127) / 128, 128, 0, st>>>(mode, n, vj_mask, cs_en, init_en);
+  ++ctx->launches;
+  // detection for the streams in "VJ" (frame quads without such a stream exit at once)
+  rc = run_detect(ctx, P, d_rgba, 0, n, min_neighbors, ctx->d_out_rects.as<Rect>(), ctx->d_out_counts.as<int32_t>(),
+                  HistOut{nullptr, nullptr}, vj_mask);
+  if (rc != HT_OK) return rc;
+  // one track() for the streams in "CS" (src/camshift.js:213-312; the whole-frame histogram is :268)
+  rc = launch_hist(ctx, d_rgba, n, w, h, ctx->cur_hist.as<uint32_t>(), ctx->bins.as<uint16_t>(), cs_en);
+  if (rc != HT_OK) return rc;
+  ctx->prof_begin(HT_PROF_TRACK);
+  rc = launch_track(ctx, n, 0, ctx->bins.as<uint16_t>(), w, h, nullptr, ctx->model_hist.as<uint32_t>(),
+                    ctx->cur_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), 1, ctx->d_objs.as<int32_t>(), nullptr,
+                    ctx->d_flags.as<int32_t>() + 2, cs_en);
+  if (rc != HT_OK) return rc;
+  ctx->prof_end();
+  // events + transitions, then initTracker for the streams that just found their face
+  StreamEvent *d_ev = is_device_ptr(out_events) ? reinterpret_cast<StreamEvent *>(out_events) : ctx->d_stream_events.as<StreamEvent>();
+  k_stream_update<<<(n + 127) / 128, 128, 0, st>>>(mode, n, ctx->d_out_rects.as<Rect>(), ctx->d_out_counts.as<int32_t>(), ctx->K,
+                                                   ctx->d_objs.as<int32_t>(), ctx->d_rects.as<int32_t>(), init_en, d_ev);
+  ctx->prof_begin(HT_PROF_TRACK_INIT);
+  k_track_init<<<n, 256, 0, st>>>(d_rgba, (size_t)w * h * 4, w, h, nullptr, ctx->d_rects.as<int32_t>(), calc_angles ? 1 : 0,
+                                  ctx->model_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), nullptr, init_en);
+  ctx->prof_end();
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  ctx->last_plan = P;
+  ctx->last_n = n;
+  if (!is_device_ptr(out_events)) {
+    CK(cudaMemcpyAsync(out_events, d_ev, sizeof(StreamEvent) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    return ht_sync(ctx);
+  }
   return HT_OK;
 }
 

@@ -10,6 +10,14 @@
 
 namespace ht {
 
+// Which of the 4 frames of a quad take part in a launch: the first n_frames - 4*quad of them (batch calls), or the
+// per-quad mask the stream scheduler built (ht_stream_step: only the streams that are in detection mode).
+__device__ __forceinline__ unsigned quad_frames(int quad, int n_frames, const uint8_t *__restrict__ quad_mask) {
+  const int left = n_frames - 4 * quad;
+  const unsigned prefix = left >= 4 ? 15u : (left > 0 ? (1u << left) - 1u : 0u);
+  return quad_mask ? (prefix & quad_mask[quad]) : prefix;
+}
+
 __device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:63-66, 345-348
   return ((px & 0xf0u) << 4) | ((px >> 8) & 0xf0u) | ((px >> 20) & 0xfu);
 }
@@ -43,9 +51,11 @@ template <bool VEC, bool HIST>
 __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_frames,
                                               uint32_t *__restrict__ arena, size_t quad_stride, int w, int h,
                                               int pitch0, uint32_t *__restrict__ hist, uint16_t *__restrict__ bins,
-                                              int chunks) {
+                                              int chunks, const uint8_t *__restrict__ quad_mask) {
   extern __shared__ uint32_t sh_hist[];   // HIST: [4][4096]
   const int quad = blockIdx.y;
+  const unsigned fmask = quad_frames(quad, n_frames, quad_mask);
+  if (fmask == 0u) return;
   if (HIST) {
     for (int i = threadIdx.x; i < 4 * 4096; i += 256) sh_hist[i] = 0;
     __syncthreads();
@@ -56,14 +66,13 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
   const int beg = blockIdx.x * per, end = min(n_groups, beg + per);
   const int n_px = w * h;
   uint32_t *dst_plane = arena + (size_t)quad * quad_stride;
-  const int f_valid = min(4, n_frames - 4 * quad);    // frames of this quad that exist
   for (int it = beg + threadIdx.x; it < end; it += 256) {
     const int row = it / gpr, col = (it - row * gpr) * 4;
     uint32_t px[4][4];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
       px[f][0] = px[f][1] = px[f][2] = px[f][3] = 0;
-      if (f < f_valid && col < w) {
+      if (((fmask >> f) & 1u) && col < w) {
         const uint8_t *src = rgba + (size_t)(4 * quad + f) * frame_bytes + ((size_t)row * w + col) * 4;
         if (VEC) {  // w % 4 == 0 and 16 B aligned frames
           const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
@@ -82,14 +91,14 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
       if (col + i < w) {            // pad columns and missing frames are written as 0
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          if (f < f_valid) out[i] |= gray_of(px[f][i]) << (8 * f);
+          if ((fmask >> f) & 1u) out[i] |= gray_of(px[f][i]) << (8 * f);
       }
     }
     *reinterpret_cast<uint4 *>(dst_plane + (size_t)row * pitch0 + col) = make_uint4(out[0], out[1], out[2], out[3]);
     if (HIST) {
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
-        if (f >= f_valid || col >= w) continue;
+        if (!((fmask >> f) & 1u) || col >= w) continue;
         uint32_t b[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -111,7 +120,8 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
   }
   if (HIST) {
     __syncthreads();
-    for (int f = 0; f < f_valid; ++f) {
+    for (int f = 0; f < 4; ++f) {
+      if (!((fmask >> f) & 1u)) continue;
       uint32_t *out = hist + (size_t)(4 * quad + f) * 4096;
       if (chunks == 1) {
         for (int i = threadIdx.x; i < 4096; i += 256) out[i] = sh_hist[f * 4096 + i];
@@ -130,7 +140,8 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
 // Every load and store is a whole word (4 frames): the tap positions, weights and addresses - most of round 1's
 // 43 instructions per output pixel - are computed once for four frames.
 __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint32_t *__restrict__ arena,
-                                                  size_t quad_stride) {
+                                                  size_t quad_stride, int n_frames, const uint8_t *__restrict__ quad_mask) {
+  if (quad_frames(blockIdx.y, n_frames, quad_mask) == 0u) return;
   // per-block metadata: one 8 B tile record and one 64 B job record, fetched with vector loads
   const uint2 tl = __ldg(reinterpret_cast<const uint2 *>(plan.pyr_tiles + tile0 + blockIdx.x));
   const int job_id = (int)(tl.x & 0xffffu), tx = (int)(tl.x >> 16), ty = (int)(tl.y & 0xffffu);
@@ -292,7 +303,8 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
                                                                 int n_frames, uint32_t *__restrict__ raw_keys,
                                                                 double *__restrict__ raw_conf,
                                                                 uint32_t *__restrict__ raw_count, int raw_cap,
-                                                                int force_ties) {
+                                                                int force_ties, const uint8_t *__restrict__ quad_mask) {
+  if (quad_frames(blockIdx.y, n_frames, quad_mask) == 0u) return;   // uniform over the CTA
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t *tile = smem;                                                   // TILE_WORDS
   uint16_t *cl0 = reinterpret_cast<uint16_t *>(smem + TILE_WORDS);         // [CLASS_CAP][32] survivor lists (ping)
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
   const DevScale sc = plan.scales[tl.scale];
   const uint32_t *qa = arena + (size_t)quad * quad_stride;
   const int x0 = tl.tx * TW, y0 = tl.ty * TH;  // quarter-res origin of the tile
-  const int f_valid = min(4, n_frames - 4 * quad);
+  const unsigned fmask = quad_frames(quad, n_frames, quad_mask);
 
   for (int i = tid; i < (MAX_GROUPS + 2) * 32; i += CASCADE_THREADS) cnt[i] = 0;
 
@@ -384,8 +396,8 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
       const uint32_t *tA = tile + v * (2 * P0) + u, *tB = tile + v * P1 + u;
       uint32_t a_lo = 0, a_hi = 0;   // alive bits: frame 0 -> lo bit 15, 2 -> lo bit 31, 1 -> hi bit 15, 3 -> hi bit 31
       if (x0 + lx < sc.qw && y0 + ly < sc.qh) {
-        a_lo = (f_valid > 0 ? 0x8000u : 0u) | (f_valid > 2 ? 0x80000000u : 0u);
-        a_hi = (f_valid > 1 ? 0x8000u : 0u) | (f_valid > 3 ? 0x80000000u : 0u);
+        a_lo = ((fmask & 1u) ? 0x8000u : 0u) | ((fmask & 4u) ? 0x80000000u : 0u);
+        a_hi = ((fmask & 2u) ? 0x8000u : 0u) | ((fmask & 8u) ? 0x80000000u : 0u);
       }
 #define HT_QSTAGE(J)                                                                                        \
   if (NQ > J && __any_sync(0xffffffffu, (a_lo | a_hi) != 0u)) {                                              \
@@ -427,7 +439,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
     for (int it = warp; it < 4 * TH * 4; it += CASCADE_WARPS) {
       const int f = it & 3, v = (it >> 2) >> 1, u = (((it >> 2) & 1) << 5) | lane;
       const int lx = u >> 1, ly = v >> 1;
-      bool alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh) && f < f_valid;
+      bool alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh) && ((fmask >> f) & 1u);
       const int e = (f << 11) | (v << 6) | u;
       const uint8_t *tA, *tB;
       bases(e, tA, tB);

@@ -20,8 +20,10 @@ namespace ht {
 // holds 8 * bin: the byte offset of the pixel's weight in k_track's fp64 table (8 * 4095 < 2^16).
 // grid = (chunks, n_frames).  Shared-memory histogram per CTA, flushed to hist[frame][4096].
 __global__ void __launch_bounds__(256) k_hist(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_px,
-                                              uint32_t *__restrict__ hist, uint16_t *__restrict__ bins, int chunks) {
+                                              uint32_t *__restrict__ hist, uint16_t *__restrict__ bins, int chunks,
+                                              const uint8_t *__restrict__ enable) {
   __shared__ uint32_t sh[4096];
+  if (enable && !enable[blockIdx.y]) return;   // ht_stream_step: only the streams that are tracking
   for (int i = threadIdx.x; i < 4096; i += 256) sh[i] = 0;
   __syncthreads();
   const uint32_t *px = reinterpret_cast<const uint32_t *>(rgba + (size_t)blockIdx.y * frame_bytes);
@@ -70,9 +72,10 @@ __global__ void __launch_bounds__(256) k_track_init(const uint8_t *__restrict__ 
                                                     const int32_t *__restrict__ slots,
                                                     const int32_t *__restrict__ rects, int calc_angles,
                                                     uint32_t *__restrict__ model_hist, TrackState *__restrict__ state,
-                                                    int32_t *__restrict__ found) {
+                                                    int32_t *__restrict__ found, const uint8_t *__restrict__ enable) {
   __shared__ uint32_t sh[4096];
   const int k = blockIdx.x;
+  if (enable && !enable[k]) return;            // ht_stream_step: only the streams that just found a face
   const int slot = slots ? slots[k] : k;
   const int rx = rects[4 * k + 0], ry = rects[4 * k + 1], rw = rects[4 * k + 2], rh = rects[4 * k + 3];
   if (rw <= 0 || rh <= 0) {  // no candidate (device pick): the slot becomes uninitialised
@@ -187,11 +190,22 @@ constexpr int TRACK_CLUSTER_MAX = 8;   // the cluster size is a launch-time choi
 // duration of the whole launch.  area[i] = search-window area of stream i; order = indices by descending area
 // (ties by index, so the order is deterministic).
 __global__ void k_track_area(const TrackState *__restrict__ state, const int32_t *__restrict__ slots, int n,
-                             int32_t *__restrict__ area) {
+                             const int32_t *__restrict__ cost, int32_t *__restrict__ area) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const TrackState *s = state + (slots ? slots[i] : i);
-  long long a = s->initialised ? (long long)max(s->sw, 0) * (long long)max(s->sh, 0) : 0;
+  const int slot = slots ? slots[i] : i;
+  const TrackState *s = state + slot;
+  long long a = 0;
+  if (s->initialised) {
+    // History first: what this stream cost in its previous launch (k_track's leader records {passes, window pixels
+    // / 256}) predicts the chain it is about to run far better than its current window does - the windows that end
+    // up covering the frame start small.  Units: one pass = 120, one pixel per thread of a 256-thread CTA = 1
+    // (3 us vs 0.025 us, tools/track_chain_probe.py).  Streams without history: the window area of a typical
+    // 70-pass chain.
+    const int passes = cost ? cost[2 * slot] : 0;
+    if (passes > 0) a = 120ll * passes + cost[2 * slot + 1];
+    else a = 120ll * 70 + 70ll * (((long long)max(s->sw, 0) * (long long)max(s->sh, 0)) >> 8);
+  }
   area[i] = (int32_t)min(a, (long long)0x7fffffff);
 }
 __global__ void k_track_rank(const int32_t *__restrict__ area, int n, int32_t *__restrict__ order) {
@@ -260,18 +274,27 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         // mean-shift returns to one of them (a converged stream, or one oscillating between two windows)
         int memo,
         // force_serial != 0 (ht_debug_set_exactness bit 2): every pass takes the strict-order fallback
-        int force_serial) {
+        int force_serial,
+        // per slot {passes, window pixels / 256} of this launch: the scheduling key of the next one (k_track_area)
+        int32_t *__restrict__ cost,
+        // enable != NULL (ht_stream_step): streams with enable[k] == 0 are not in tracking mode and are skipped
+        const uint8_t *__restrict__ enable) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double wsm[4096 + 1];   // [4096] = +0.0: the weight of pixels outside the window
   constexpr int NW = NT / 32;   // warps per CTA
   __shared__ double red[NW][6];
-  __shared__ double cpart[TRACK_CLUSTER_MAX][6];  // used in rank 0: partial moments of every CTA of the cluster
-  __shared__ int win[4];                          // wadx, wady, wadw, wadh (written by rank 0 into every CTA)
+  // Every CTA of the cluster keeps its OWN copy of the reference's loop state and runs the scalar mean-shift step
+  // redundantly (same inputs, same operations -> bit-identical windows), so a pass needs ONE cluster barrier - the
+  // exchange of the partial moments - instead of two (round 1: partials to rank 0, barrier, rank 0 publishes the
+  // next window, barrier).  cpart is double-buffered by pass parity: a CTA that is already exchanging pass p+1
+  // cannot overwrite what a slower CTA still reads for pass p.
+  __shared__ double cpart[2][TRACK_CLUSTER_MAX][6];  // partial moments of every CTA of the cluster (written remotely)
+  __shared__ int win[4];                          // wadx, wady, wadw, wadh of the next pass
   __shared__ int ctrl;                            // 0 = run another pass over win[], 1 = this stream is finished
   constexpr int MEMO_N = 8;
   struct MemoEnt { int w[4]; int exact; int valid; Mom m; };
-  __shared__ MemoEnt memo_tab[MEMO_N];            // leader only
+  __shared__ MemoEnt memo_tab[MEMO_N];            // thread 0 of every CTA
   __shared__ int memo_next;
   __shared__ unsigned long long st_memo_sh;
   const int crank = (int)cluster.block_rank();
@@ -284,9 +307,11 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
     k = bail_list[k];
     call0 = calls_done[k];
   }
+  if (enable && !enable[k]) return;               // uniform over the cluster, before any cluster barrier
   const int slot = slots ? slots[k] : k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool leader = (crank == 0 && tid == 0);
+  const bool leader = (crank == 0 && tid == 0);   // the one thread that writes results, state and statistics
+  const bool stepper = (tid == 0);                 // thread 0 of EVERY CTA runs the mean-shift step
   // The reference's loop state lives in shared memory: only the leader thread touches it after this point, and
   // keeping it out of registers leaves them to the pipelined pass loop.
   struct Lead { TrackState s; unsigned long long st_pass, st_serial, st_px; int call, it, prevx, prevy; bool bailed; };
@@ -329,20 +354,17 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   }
   const uint16_t *px = bins + (size_t)k * W * H;   // 12-bit colour bin of every pixel of this slot's frame (k_hist)
   const bool vec4 = (W & 3) == 0;
-  double *cpart0 = cluster.map_shared_rank(&cpart[0][0], 0);
+  int parity = 0;
 
   // leader-only bookkeeping of the reference's loops (src/camshift.js:213-312)
   unsigned long long &st_pass = lead_sh.st_pass, &st_serial = lead_sh.st_serial, &st_px = lead_sh.st_px;
   int &call = lead_sh.call, &it = lead_sh.it, &prevx = lead_sh.prevx, &prevy = lead_sh.prevy;
   bool &bailed = lead_sh.bailed;
-  auto publish = [&](int done) {   // leader: next window (or the finish flag) into every CTA of the cluster
+  auto publish = [&](int done) {   // stepper: next window (or the finish flag) for this CTA
     const int w0 = max(s.sx, 0), w1 = max(s.sy, 0);                // :286-289
     const int w2 = min(w0 + s.sw, W), w3 = min(w1 + s.sh, H);
-    for (int r = 0; r < TRACK_CLUSTER; ++r) {
-      int *rw = cluster.map_shared_rank(win, r);
-      rw[0] = w0; rw[1] = w1; rw[2] = w2; rw[3] = w3;
-      *cluster.map_shared_rank(&ctrl, r) = done;
-    }
+    win[0] = w0; win[1] = w1; win[2] = w2; win[3] = w3;
+    ctrl = done;
   };
   auto start_call = [&]() {        // leader: returns true when the stream stops here (all calls done, or bail-out)
     if (call >= n_calls) return true;
@@ -351,8 +373,8 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
     return false;
   };
   if (TRACK_CLUSTER > 1) cluster.sync();  // every CTA is resident before the first remote shared-memory access
-  if (leader) publish(start_call() ? 1 : 0);
-  if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
+  if (stepper) publish(start_call() ? 1 : 0);
+  __syncthreads();
 
   constexpr int ROW_STRIDE = NW * TRACK_CLUSTER;
   while (!ctrl) {
@@ -452,17 +474,18 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
       red[warp][3] = a11; red[warp][4] = a20; red[warp][5] = a02;
     }
     __syncthreads();
-    if (tid < 6) {   // fixed-order sums: run-to-run deterministic
+    if (tid < 6 * TRACK_CLUSTER) {   // fixed-order sums (run-to-run deterministic), one copy into every CTA
+      const int q = tid % 6, r = tid / 6;
       double t = 0;
-      for (int w8 = 0; w8 < NW; ++w8) t += red[w8][tid];
-      cpart0[crank * 6 + tid] = t;
+      for (int w8 = 0; w8 < NW; ++w8) t += red[w8][q];
+      cluster.map_shared_rank(&cpart[0][0][0], r)[(parity * TRACK_CLUSTER_MAX + crank) * 6 + q] = t;
     }
     if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
-    if (leader) {
+    if (stepper) {
       Mom m = {0, 0, 0, 0, 0, 0};
       for (int r = 0; r < TRACK_CLUSTER; ++r) {
-        m.m00 += cpart[r][0]; m.m10 += cpart[r][1]; m.m01 += cpart[r][2];
-        m.m11 += cpart[r][3]; m.m20 += cpart[r][4]; m.m02 += cpart[r][5];
+        m.m00 += cpart[parity][r][0]; m.m10 += cpart[parity][r][1]; m.m01 += cpart[parity][r][2];
+        m.m11 += cpart[parity][r][3]; m.m20 += cpart[parity][r][4]; m.m02 += cpart[parity][r][5];
       }
       bool exact = false;          // m is in the reference's strict summation order (moments_serial)
       bool fresh = true;           // m was computed by this pass (false: taken from the memo)
@@ -557,9 +580,14 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         break;
       }
     }
-    if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
+    parity ^= 1;
+    __syncthreads();
   }
   if (leader) {
+    if (cost) {
+      cost[2 * slot] = (int32_t)min(st_pass, 0x7fffffffull);
+      cost[2 * slot + 1] = (int32_t)min(st_px >> 8, 0x7fffffffull);
+    }
     if (stats) {
       atomicAdd(&stats[0], st_pass); atomicAdd(&stats[1], st_serial);
       atomicAdd(&stats[2], st_px); atomicAdd(&stats[3], (unsigned long long)(call - call0));
@@ -585,6 +613,74 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
     }
   }
   if (TRACK_CLUSTER > 1) cluster.sync();  // no CTA may exit while another one can still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------
+// facetrackr's per-frame state machine on the device (src/facetrackr.js:67-126 with whitebalancing off, plus the
+// lost-face rule of src/main.js:230-244) for n independent streams: ht_stream_step.
+//   mode[k] : 0 = "VJ" (detect on this frame), 1 = "CS" (camshift on this frame)
+// k_stream_plan runs before the frame's kernels and turns the modes into the masks they take; k_stream_update runs
+// after them, writes the frame's event record and applies the transitions.
+struct StreamEvent {       // == ht_stream_event (include/headtrackr_b200.h)
+  int32_t detection;       // 1 = "VJ", 2 = "CS"  (facetrackr TrackObj.detection, src/facetrackr.js:233-241)
+  int32_t status;          // bit 0: VJ found a face, the stream switches to CS (src/facetrackr.js:97-108)
+                           // bit 1: CS lost the face (width or height 0), the stream re-detects (src/main.js:230-244)
+  double x, y, width, height, angle, confidence;
+};
+
+__global__ void k_stream_plan(const int32_t *__restrict__ mode, int n, uint8_t *__restrict__ vj_quad_mask,
+                              uint8_t *__restrict__ cs_enable, uint8_t *__restrict__ init_enable) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  cs_enable[k] = mode[k] == 1 ? 1 : 0;
+  init_enable[k] = 0;
+  if ((k & 3) == 0) {
+    unsigned m = 0;
+    for (int f = 0; f < 4 && k + f < n; ++f) m |= (mode[k + f] == 0 ? 1u : 0u) << f;
+    vj_quad_mask[k >> 2] = (uint8_t)m;
+  }
+}
+
+__global__ void k_stream_update(int32_t *__restrict__ mode, int n, const Rect *__restrict__ det,
+                                const int32_t *__restrict__ counts, int K, const int32_t *__restrict__ objs,
+                                int32_t *__restrict__ rects, uint8_t *__restrict__ init_enable,
+                                StreamEvent *__restrict__ events) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  StreamEvent e;
+  e.status = 0;
+  e.x = e.y = e.width = e.height = e.angle = 0.0;     // new TrackObj(), src/facetrackr.js:233-241
+  e.confidence = -10000.0;
+  if (mode[k] == 0) {                                  // doVJDetection, src/facetrackr.js:137-175
+    e.detection = 1;
+    const int c = counts[k];
+    if (c > 0) {
+      const Rect *d = det + (size_t)k * K;
+      int best = 0;
+      for (int i = 1; i < c; ++i)
+        if (d[i].confidence > d[best].confidence) best = i;   // first maximum, :161-165
+      e.x = d[best].x; e.y = d[best].y; e.width = d[best].width; e.height = d[best].height;
+      e.confidence = d[best].confidence;
+    }
+    if (e.confidence > -10.0) {                        // :97: switch to camshift, initTracker on THIS frame
+      rects[4 * k + 0] = (int32_t)floor(e.x); rects[4 * k + 1] = (int32_t)floor(e.y);
+      rects[4 * k + 2] = (int32_t)floor(e.width); rects[4 * k + 3] = (int32_t)floor(e.height);
+      init_enable[k] = 1;
+      mode[k] = 1;
+      e.status |= 1;
+    }
+  } else {                                             // doCSDetection, src/facetrackr.js:178-209
+    e.detection = 2;
+    const int32_t *o = objs + 6 * (size_t)k;
+    e.x = o[0]; e.y = o[1]; e.width = o[2]; e.height = o[3];
+    e.angle = *reinterpret_cast<const double *>(o + 4);
+    e.confidence = 1.0;
+    if (o[2] == 0 || o[3] == 0) {                      // src/main.js:230: lost -> a fresh facetrackr without whitebalancing
+      mode[k] = 0;
+      e.status |= 2;
+    }
+  }
+  events[k] = e;
 }
 
 // getBackProjectionImg — src/camshift.js:177-196 (debug path)

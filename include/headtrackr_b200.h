@@ -131,6 +131,28 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
                     int calc_angles, int n_calls, ht_rect *out_rects, int32_t *out_counts, int32_t *out_found,
                     ht_trackobj *out_objs, ht_window *out_windows);
 
+/* facetrackr's per-frame state machine for n independent video streams, on the device.
+ * Stream k (tracker slot k) is in one of the reference's detection modes (src/facetrackr.js:57,75-81; whitebalancing
+ * off, as after src/main.js:236):
+ *   "VJ": ccv.detect_objects on the frame, first-max-confidence pick (src/facetrackr.js:157-165); if its confidence
+ *         exceeds -10 the tracker is seeded with the floored rectangle on this same frame and the stream switches
+ *         to "CS" (src/facetrackr.js:97-108)
+ *   "CS": one camshift track() on the frame (src/facetrackr.js:178-209); a result with width or height 0 means the
+ *         face is lost and the stream starts over in "VJ" on the next frame (src/main.js:230-244, retryDetection)
+ * ht_stream_step consumes ONE frame per stream (rgba = n frames, stream-major) and returns the TrackObj facetrackr
+ * would hold after track() for each stream; the host emits `facetrackingEvent` for records with detection == 2
+ * (src/facetrackr.js:112-125).  Mode switches, the pick and the tracker seeding happen in kernels: the only host
+ * traffic per frame is the frame upload (if `rgba` is host memory) and the n event records. */
+typedef struct {
+  int32_t detection;   /* 1 = "VJ", 2 = "CS" */
+  int32_t status;      /* bit 0: face found on this frame (VJ -> CS); bit 1: face lost on this frame (CS -> VJ) */
+  double x, y, width, height, angle, confidence;   /* VJ: top-left, fp64 as ccv returns; CS: centre, integers */
+} ht_stream_event;
+/* put streams [first, first+n) back into "VJ" (new facetrackr.Tracker) */
+int ht_stream_reset(ht_ctx *ctx, int first, int n);
+int ht_stream_step(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors,
+                   int calc_angles, ht_stream_event *out_events);
+
 /* getBackProjectionImg() of the last track() state for one slot: RGBA w*h*4, floor(255*weight) gray
  * (src/camshift.js:177-196).  Debug path of the reference (src/facetrackr.js:194-196). */
 int ht_backprojection(ht_ctx *ctx, int slot, const uint8_t *rgba, int w, int h, uint8_t *out_rgba);

@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > $O/r02c2_gpu.t
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > $O/r02c2_sanitizer.log 2>&1
 echo "sanitizer rc=$?"; tail -5 $O/r02c2_sanitizer.log
 # 2. parity tests
-timeout 1500 python -m pytest tests -m gpu -x -q > $O/r02c2_pytest.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > $O/r02c2_pytest.log 2>&1
 echo "pytest rc=$?"; tail -15 $O/r02c2_pytest.log
 # 3. timing variants (detect workload isolates the new kernels)
 run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline $BARGS > $O/r02c2_$tag.json 2> $O/r02c2_$tag.err; }
