@@ -661,6 +661,8 @@ cudaError_t launch_track_any(int c, int nt, cudaStream_t st, int n, const uint16
                              const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
                              int32_t *d_win, int32_t *flag, unsigned long long *stats, int32_t *calls_done, int32_t *list,
                              int32_t *count, int use_list, int list_off, TrackOpts opt) {
+  if (nt == 512)
+    return launch_track_nt<512>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off, opt);
   if (nt == 128)
     return launch_track_nt<128>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off, opt);
   return launch_track_nt<256>(c, st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, calls_done, list, count, use_list, list_off, opt);
@@ -988,7 +990,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
   if (const char *dp = getenv("HT_DETECT_PIPE")) c->detect_pipe = std::max(0, atoi(dp));
   if (const char *tm2 = getenv("HT_TRACK_MEMO")) c->track_memo = atoi(tm2) != 0;
   if (const char *tt = getenv("HT_TRACK_TRACE")) c->track_trace = atoi(tt) != 0;
-  if (const char *tn = getenv("HT_TRACK_NT")) c->track_nt = (atoi(tn) == 128) ? 128 : 256;
+  if (const char *tn = getenv("HT_TRACK_NT")) c->track_nt = (atoi(tn) == 128) ? 128 : (atoi(tn) == 512 ? 512 : 256);
   if (const char *tl = getenv("HT_TRACK_LPT")) c->track_lpt = atoi(tl) != 0;
   if (const char *thi = getenv("HT_TRACK_HISTORY")) c->track_history = atoi(thi) != 0;
   if (const char *th = getenv("HT_TRACK_HEAVY")) {

@@ -21,7 +21,19 @@ run det_q3 HT_LIB=variants/libht_q3.so
 BARGS=""
 run full_w32
 run full_w32_pipe HT_DETECT_PIPE=1
-for f in $O/r02c2_det_*.json $O/r02c2_full_*.json; do python - "$f" <<'PY'
+run full_nt512c1 HT_TRACK_NT=512 HT_TRACK_CLUSTER=1
+run full_noheavy HT_TRACK_HEAVY=0
+run full_nohist HT_TRACK_HISTORY=0
+run full_heavy32 HT_TRACK_HEAVY=32
+BARGS="--workload streams --streams 1 --stream-frames 120"
+run streams1
+BARGS="--workload streams --streams 16 --stream-frames 120"
+run streams16
+BARGS="--workload detect720 --interval 3"
+run d720_i3
+BARGS="--width 320 --height 240"
+run full_320
+for f in $O/r02c2_det_*.json $O/r02c2_full_*.json $O/r02c2_streams*.json $O/r02c2_d720*.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[1].split("r02c2_")[1], round(d["value"]), round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"]), d["kernel_ms_per_step"])
