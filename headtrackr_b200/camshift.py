@@ -6,8 +6,6 @@
     TrackObj                                                     src/camshift.js:362-377
 Each Tracker owns one tracker slot of a Context; all arithmetic runs in the CUDA library.
 """
-import itertools
-
 from .canvas import as_pixels
 from .runtime import default_context
 
@@ -34,7 +32,19 @@ class TrackObj:
         return c
 
 
-_slot_counter = itertools.count()
+def _take_slot(ctx):
+    """Tracker slots are a per-context resource: a free list on the Context, no silent sharing when it runs dry."""
+    free = ctx.__dict__.setdefault("_free_slots", list(range(ctx.max_frames - 1, -1, -1)))
+    if not free:
+        raise RuntimeError(f"all {ctx.max_frames} tracker slots of this context are in use "
+                           "(create the Context with a larger max_frames, or drop Trackers you no longer need)")
+    ctx.__dict__["_live_trackers"] = ctx.__dict__.get("_live_trackers", 0) + 1
+    return free.pop()
+
+
+def _give_slot(ctx, slot):
+    ctx.__dict__.setdefault("_free_slots", []).append(slot)
+    ctx.__dict__["_live_trackers"] = max(0, ctx.__dict__.get("_live_trackers", 1) - 1)
 
 
 class Tracker:
@@ -51,8 +61,16 @@ class Tracker:
         if self._ctx is None:
             self._ctx = default_context(px.shape[1], px.shape[0])
         if self._slot is None:
-            self._slot = next(_slot_counter) % self._ctx.max_frames
+            self._slot = _take_slot(self._ctx)
+            self._own_slot = True
         return self._ctx
+
+    def __del__(self):
+        try:
+            if getattr(self, "_own_slot", False) and self._ctx is not None:
+                _give_slot(self._ctx, self._slot)
+        except Exception:
+            pass
 
     def initTracker(self, canvas, trackedArea):
         px = as_pixels(canvas)

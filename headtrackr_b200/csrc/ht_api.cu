@@ -71,7 +71,7 @@ struct Plan {
   DevPlan dplan{};
 };
 
-int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std::string &err) {
+int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std::string &err, bool upload = true) {
   P.w = W; P.h = H; P.interval = interval;
   const double scale = std::pow(2.0, 1.0 / (interval + 1.0));                      // ccv.js:110
   P.next = interval + 1;                                                            // ccv.js:111
@@ -212,6 +212,7 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
     scale_x *= scale;                                                               // :244
   }
   P.windows_per_frame = win_base;
+  if (!upload) return HT_OK;   // host-only self-test
   // ---- upload ----
   size_t o_planes = 0, o_jobs = align_up(o_planes + P.planes.size() * sizeof(DevPlane), (size_t)256);
   size_t o_taps = align_up(o_jobs + P.jobs.size() * sizeof(DevJob), (size_t)256);
@@ -1581,6 +1582,163 @@ int ht_debug_model_hist(ht_ctx *ctx, int slot, uint32_t *out4096) {
 //   nvcc -DHT_HOST_SELFTEST -o ht_selftest ht_api.cu && ./ht_selftest ../data/cascade_face.bin
 // Prints one JSON line; tests/test_late_schedule.py checks it.
 #ifdef HT_HOST_SELFTEST
+// ---- CPU emulation of k_cascade's tile evaluation (tests/test_cascade_host.py) ----
+// Same generated stage code (cascade_face_gen.inc, compiled for the host), same tile layout (point_word), same
+// staging index arithmetic, same bank-class bookkeeping, same late-stage schedule and integer thresholds as the
+// kernel; only the parallel execution is replaced by loops.  The arena is one frame quad in the device layout.
+extern "C" int ht_selftest_planes(int w, int h, int interval, int32_t *out, int cap) {
+  Plan P;
+  std::string err;
+  if (build_plan(P, w, h, interval, 24, 24, err, false) != HT_OK) return -1;
+  if ((int)P.planes.size() * 6 + 2 > cap) return -2;
+  out[0] = (int32_t)P.planes.size();
+  out[1] = (int32_t)P.arena_stride;
+  for (size_t i = 0; i < P.planes.size(); ++i) {
+    int slot = -1, q = -1;
+    for (size_t k = 0; k < P.plane_id.size(); ++k) if (P.plane_id[k] == (int)i) { slot = (int)(k / 4); q = (int)(k % 4); }
+    int32_t *o = out + 2 + 6 * i;
+    o[0] = (int32_t)P.planes[i].off; o[1] = P.planes[i].pitch; o[2] = P.planes[i].w; o[3] = P.planes[i].h; o[4] = slot; o[5] = q;
+  }
+  return 0;
+}
+
+extern "C" int ht_selftest_cascade(const void *blob, size_t blob_len, int w, int h, int interval, const uint32_t *arena,
+                                   int n_frames, int force_ties, int quad_stages, double *out /* [4][cap][4] x,y,width,conf */,
+                                   int32_t *counts, int cap) {
+  static HostCascade hc;   // (ConstCascade is 63 KB: keep it off the stack)
+  std::string err;
+  if (parse_cascade(blob, blob_len, hc, err) != HT_OK) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
+  if (!hc.fast) return -3;
+  Plan P;
+  if (build_plan(P, w, h, interval, hc.width, hc.height, err, false) != HT_OK) { fprintf(stderr, "%s\n", err.c_str()); return -2; }
+  g_host_casc = &hc.cc;
+  const ConstCascade &cc = hc.cc;
+  const int late_first = cc.group_first[cc.n_groups];
+  struct Hit { uint32_t key; double x, y, width, conf; };
+  std::vector<Hit> hits[4];
+  std::vector<uint32_t> tile((size_t)TILE_WORDS);
+  const unsigned fmask = n_frames >= 4 ? 15u : (1u << n_frames) - 1u;
+  for (const DevCascTile &tl : P.casc_tiles) {
+    const DevScale &sc = P.scales[tl.scale];
+    const int x0 = tl.tx * TW, y0 = tl.ty * TH;
+    // staging: the kernel's loops, word for word
+    {
+      const DevPlane pl = P.planes[sc.p0];
+      const uint32_t *src = arena + pl.off;
+      const int X0 = 4 * x0, Y0 = 4 * y0;
+      for (int i = 0; i < L0_ROWS * P0; ++i) {
+        const int r = i / P0, c = i - r * P0;
+        const int X = (c < H0) ? 2 * c : 2 * (c - H0) + 1;
+        const bool ok = (Y0 + r < pl.h) && (X0 + X < pl.pitch);
+        tile[(size_t)i] = ok ? src[(size_t)(Y0 + r) * pl.pitch + X0 + X] : 0u;
+      }
+    }
+    {
+      const DevPlane pl = P.planes[sc.p1];
+      const uint32_t *src = arena + pl.off;
+      const int X0 = 2 * x0, Y0 = 2 * y0;
+      for (int i = 0; i < L1_ROWS * P1; ++i) {
+        const int r = i / P1, c = i - r * P1;
+        const bool ok = (Y0 + r < pl.h) && (X0 + c < pl.pitch);
+        tile[(size_t)(W1 + i)] = ok ? src[(size_t)(Y0 + r) * pl.pitch + X0 + c] : 0u;
+      }
+    }
+    for (int i = 0; i < 2 * L2_ROWS * P2; ++i) {
+      const int rr = i / P2, c2 = i - rr * P2;
+      const int q = (c2 & 1) | ((rr & 1) << 1), r = rr >> 1, c = c2 >> 1;
+      const DevPlane pl = P.planes[sc.p2[q]];
+      const uint32_t *src = arena + pl.off;
+      const bool ok = (y0 + r < pl.h) && (x0 + c < pl.pitch);
+      tile[(size_t)(W2 + i)] = ok ? src[(size_t)(y0 + r) * pl.pitch + x0 + c] : 0u;
+    }
+    const uint8_t *tile_b = reinterpret_cast<const uint8_t *>(tile.data());
+    auto bases = [&](int e, const uint8_t *&tA, const uint8_t *&tB) {
+      const int u = e & 63, v = (e >> 6) & 31, f = e >> 11;
+      tA = tile_b + 4 * (v * (2 * P0) + u) + f;
+      tB = tile_b + 4 * (v * P1 + u) + f;
+    };
+    // dense group (quad form)
+    std::vector<int> list[32];
+    for (int v = 0; v < 2 * TH; ++v)
+      for (int u = 0; u < 2 * TW; ++u) {
+        const int lx = u >> 1, ly = v >> 1;
+        const uint32_t *tA = tile.data() + v * (2 * P0) + u, *tB = tile.data() + v * P1 + u;
+        uint32_t a_lo = 0, a_hi = 0;
+        if (x0 + lx < sc.qw && y0 + ly < sc.qh) {
+          a_lo = ((fmask & 1u) ? 0x8000u : 0u) | ((fmask & 4u) ? 0x80000000u : 0u);
+          a_hi = ((fmask & 2u) ? 0x8000u : 0u) | ((fmask & 8u) ? 0x80000000u : 0u);
+        }
+        for (int J = 0; J < quad_stages; ++J) {
+          uint32_t p_lo = 0, p_hi = 0, t_lo = 0, t_hi = 0;
+          if (J == 0) gen_q_stage0(tA, tB, p_lo, p_hi, t_lo, t_hi);
+          else if (J == 1) gen_q_stage1(tA, tB, p_lo, p_hi, t_lo, t_hi);
+          else gen_q_stage2(tA, tB, p_lo, p_hi, t_lo, t_hi);
+          t_lo &= a_lo; t_hi &= a_hi;
+          for (int f = 0; f < 4; ++f) {
+            const uint32_t bit = (f & 2) ? 0x80000000u : 0x8000u;
+            uint32_t &tt = (f & 1) ? t_hi : t_lo, &pp = (f & 1) ? p_hi : p_lo;
+            if (tt & bit) {
+              const uint8_t *bA = reinterpret_cast<const uint8_t *>(tA) + f, *bB = reinterpret_cast<const uint8_t *>(tB) + f;
+              if (!stage_pass_ordered(bA, bB, J)) pp &= ~bit;
+            }
+          }
+          a_lo &= p_lo; a_hi &= p_hi;
+        }
+        const uint32_t m = ((a_lo >> 15) & 1u) | ((a_hi >> 14) & 2u) | ((a_lo >> 29) & 4u) | ((a_hi >> 28) & 8u);
+        for (int f = 0; f < 4; ++f)
+          if (m & (1u << f)) list[bank_class(u, v)].push_back((v << 6) | u | (f << 11));
+      }
+    // survivor lists, then late stages
+    for (int c = 0; c < 32; ++c)
+      for (int e : list[c]) {
+        const uint8_t *tA, *tB;
+        bases(e, tA, tB);
+        bool alive = true;
+        for (int j = quad_stages; j < late_first && alive; ++j) {
+          int r = gen_stage(j, tA, tB);
+          if (force_ties & 1) r = -1;
+          if (r < 0) r = stage_pass_ordered(tA, tB, j) ? 1 : 0;
+          alive = r != 0;
+        }
+        for (int j = late_first; j < cc.n_stages && alive; ++j) {
+          long long acc = 0;
+          for (int ch = hc.late_chunk0[j]; ch < hc.late_chunk0[j + 1]; ++ch)
+            for (int lane = 0; lane < 32; ++lane) {
+              const LateFeat &lf = hc.late[(size_t)ch * 32 + lane];
+              unsigned pm = 255u, nm = 0u;
+              for (int s = 0; s < 10; ++s) {
+                if (lf.off[s] == 0xFFFF) continue;
+                const unsigned v8 = px_at(tA, tB, lf.off[s]);
+                if (s < 5) pm = std::min(pm, v8); else nm = std::max(nm, v8);
+              }
+              acc += (pm > nm) ? (long long)lf.a_int : -(long long)lf.a_int;
+            }
+          if (acc == cc.thr_int[j] || (force_ties & 2)) alive = stage_pass_ordered(tA, tB, j);
+          else alive = acc > cc.thr_int[j];
+        }
+        if (!alive) continue;
+        const int u = e & 63, v = (e >> 6) & 31, f = e >> 11;
+        const int lx = u >> 1, ly = v >> 1, q = (u & 1) | ((v & 1) << 1);
+        Hit hit;
+        hit.key = sc.win_base + (uint32_t)((q * sc.qh + (y0 + ly)) * sc.qw + (x0 + lx));
+        hit.x = (double)((x0 + lx) * 4 + (q & 1) * 2) * sc.scale_x;          // k_group's decoding, src/ccv.js:228-233
+        hit.y = (double)((y0 + ly) * 4 + (q >> 1) * 2) * sc.scale_x;
+        hit.width = 24.0 * sc.scale_x;
+        hit.conf = stage_sum_ordered(tA, tB, cc.n_stages - 1);
+        hits[f].push_back(hit);
+      }
+  }
+  for (int f = 0; f < 4; ++f) {
+    std::sort(hits[f].begin(), hits[f].end(), [](const Hit &a, const Hit &b) { return a.key < b.key; });
+    counts[f] = (int32_t)hits[f].size();
+    for (size_t i = 0; i < hits[f].size() && (int)i < cap; ++i) {
+      double *o = out + ((size_t)f * cap + i) * 4;
+      o[0] = hits[f][i].x; o[1] = hits[f][i].y; o[2] = hits[f][i].width; o[3] = hits[f][i].conf;
+    }
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 2) { fprintf(stderr, "usage: %s cascade.bin\n", argv[0]); return 2; }
   FILE *f = fopen(argv[1], "rb");

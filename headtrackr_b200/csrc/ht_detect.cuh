@@ -219,24 +219,83 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint3
 // taken on exact integers or truth tables (tools/gen_cascade_code.py, LateFeat in ht_common.cuh).
 
 __constant__ ConstCascade c_casc;
+// The stage evaluators below also compile for the HOST (tests/test_cascade_host.py emulates k_cascade's tile
+// evaluation on the CPU with the very same generated code, tile layout, tables and late-stage schedule): device
+// code reads the __constant__ image, host code a pointer the self-test sets.
+static const ConstCascade *g_host_casc = nullptr;
+#ifdef __CUDA_ARCH__
+#define HT_CASC c_casc
+#else
+#define HT_CASC (*g_host_casc)
+#endif
 
 // ---- stages specialised at build time (tools/gen_cascade_code.py) ----
-#define HT_MIN2(a, b) __vimin3_u32(a, b, b)      /* VIMNMX3.U32 (plain min() is turned into U16x2 + masks) */
-#define HT_MIN3(a, b, c) __vimin3_u32(a, b, c)
-#define HT_MAX2(a, b) __vimax3_u32(a, b, b)
-#define HT_MAX3(a, b, c) __vimax3_u32(a, b, c)
-#define HT_LO(w) __byte_perm(w, 0u, 0x4240)      /* frames 0 and 2 as u16x2 */
-#define HT_HI(w) __byte_perm(w, 0u, 0x4341)      /* frames 1 and 3 as u16x2 */
-#define HT_QMIN2(a, b) __vimin3_u16x2(a, b, b)   /* VIMNMX3.U16x2 */
-#define HT_QMIN3(a, b, c) __vimin3_u16x2(a, b, c)
-#define HT_QMAX2(a, b) __vimax3_u16x2(a, b, b)
-#define HT_QMAX3(a, b, c) __vimax3_u16x2(a, b, c)
+__host__ __device__ __forceinline__ unsigned min3_u32(unsigned a, unsigned b, unsigned c) {
+#ifdef __CUDA_ARCH__
+  return __vimin3_u32(a, b, c);      // VIMNMX3.U32 (plain min() is turned into U16x2 + masks)
+#else
+  return a < b ? (a < c ? a : c) : (b < c ? b : c);
+#endif
+}
+__host__ __device__ __forceinline__ unsigned max3_u32(unsigned a, unsigned b, unsigned c) {
+#ifdef __CUDA_ARCH__
+  return __vimax3_u32(a, b, c);
+#else
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+  return __vimin3_u16x2(a, b, c);    // VIMNMX3.U16x2
+#else
+  return (min3_u32(a >> 16, b >> 16, c >> 16) << 16) | min3_u32(a & 0xffffu, b & 0xffffu, c & 0xffffu);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t max3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+  return __vimax3_u16x2(a, b, c);
+#else
+  return (max3_u32(a >> 16, b >> 16, c >> 16) << 16) | max3_u32(a & 0xffffu, b & 0xffffu, c & 0xffffu);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t frames02(uint32_t w) {   // frames 0 and 2 of a quad word as u16x2
+#ifdef __CUDA_ARCH__
+  return __byte_perm(w, 0u, 0x4240);
+#else
+  return w & 0x00ff00ffu;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t frames13(uint32_t w) {   // frames 1 and 3
+#ifdef __CUDA_ARCH__
+  return __byte_perm(w, 0u, 0x4341);
+#else
+  return (w >> 8) & 0x00ff00ffu;
+#endif
+}
+#define HT_GEN_FN __host__ __device__ __forceinline__
+#define HT_MIN2(a, b) min3_u32(a, b, b)
+#define HT_MIN3(a, b, c) min3_u32(a, b, c)
+#define HT_MAX2(a, b) max3_u32(a, b, b)
+#define HT_MAX3(a, b, c) max3_u32(a, b, c)
+#define HT_LO(w) frames02(w)
+#define HT_HI(w) frames13(w)
+#define HT_QMIN2(a, b) min3_u16x2(a, b, b)
+#define HT_QMIN3(a, b, c) min3_u16x2(a, b, c)
+#define HT_QMAX2(a, b) max3_u16x2(a, b, b)
+#define HT_QMAX3(a, b, c) max3_u16x2(a, b, c)
 #define HT_QCMP(nm, pm) ((nm) - (pm) + 0x80008000u)   /* bit 15 / 31 clear <=> min(p) > max(n) in that frame */
 template <int LUT>
-__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+__host__ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
   uint32_t d;
   asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
   return d;
+#else
+  uint32_t d = 0;   // bit i of LUT is the output for (a,b,c) = bits (2,1,0) of i
+  for (int i = 0; i < 8; ++i)
+    if ((LUT >> i) & 1) d |= ((i & 4) ? a : ~a) & ((i & 2) ? b : ~b) & ((i & 1) ? c : ~c);
+  return d;
+#endif
 }
 // stage decision as a truth table of the four "feature did not fire" bits: x3 ? B(x0,x1,x2) : A(x0,x1,x2)
 #define HT_LUT4(x0, x1, x2, x3, A, B) lop3<0xCA>(x3, lop3<B>(x0, x1, x2), lop3<A>(x0, x1, x2))
@@ -244,6 +303,7 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 #ifndef HT_QUAD_STAGES
 #define HT_QUAD_STAGES 2   // stages the dense group evaluates in quad form (2: {0,1}; 3: {0,1,2})
 #endif
+#undef HT_GEN_FN
 #undef HT_MIN2
 #undef HT_MIN3
 #undef HT_MAX2
@@ -258,28 +318,28 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 #undef HT_LUT4
 
 // byte address of a table offset (ConstCascade::off / LateFeat::off): bit 15 selects baseB
-__device__ __forceinline__ unsigned px_at(const uint8_t *__restrict__ tA, const uint8_t *__restrict__ tB, unsigned o) {
+__host__ __device__ __forceinline__ unsigned px_at(const uint8_t *__restrict__ tA, const uint8_t *__restrict__ tB, unsigned o) {
   return (o & 0x8000u) ? tB[4u * (o & 0x7fffu)] : tA[4u * o];
 }
 
 // The reference's stage sum for one window: ordered fp64 adds, src/ccv.js:186-221.  All table reads are uniform.
-__device__ __noinline__ double stage_sum_ordered(const uint8_t *__restrict__ tA, const uint8_t *__restrict__ tB, int j) {
-  const int first = c_casc.stage[j].first, last = first + c_casc.stage[j].count;
+__host__ __device__ __noinline__ double stage_sum_ordered(const uint8_t *__restrict__ tA, const uint8_t *__restrict__ tB, int j) {
+  const int first = HT_CASC.stage[j].first, last = first + HT_CASC.stage[j].count;
   double sum = 0.0;
   for (int k = first; k < last; ++k) {
-    const unsigned kind = c_casc.np_nn[k];
+    const unsigned kind = HT_CASC.np_nn[k];
     const unsigned np = kind & 15u, nn = kind >> 4;
-    unsigned pmin = px_at(tA, tB, c_casc.off[k][0]);
-    unsigned nmax = px_at(tA, tB, c_casc.off[k][5]);
-    for (unsigned i = 1; i < np; ++i) pmin = min(pmin, px_at(tA, tB, c_casc.off[k][i]));
-    for (unsigned i = 1; i < nn; ++i) nmax = max(nmax, px_at(tA, tB, c_casc.off[k][5 + i]));
-    const double a = c_casc.alpha[k];
+    unsigned pmin = px_at(tA, tB, HT_CASC.off[k][0]);
+    unsigned nmax = px_at(tA, tB, HT_CASC.off[k][5]);
+    for (unsigned i = 1; i < np; ++i) pmin = min3_u32(pmin, pmin, px_at(tA, tB, HT_CASC.off[k][i]));
+    for (unsigned i = 1; i < nn; ++i) nmax = max3_u32(nmax, nmax, px_at(tA, tB, HT_CASC.off[k][5 + i]));
+    const double a = HT_CASC.alpha[k];
     sum += (pmin > nmax) ? a : -a;   // src/ccv.js:194,219 (alpha[2k] == -alpha[2k+1], checked on the host)
   }
   return sum;
 }
-__device__ __forceinline__ bool stage_pass_ordered(const uint8_t *tA, const uint8_t *tB, int j) {
-  return !(stage_sum_ordered(tA, tB, j) < c_casc.stage[j].threshold);   // src/ccv.js:222
+__host__ __device__ __forceinline__ bool stage_pass_ordered(const uint8_t *tA, const uint8_t *tB, int j) {
+  return !(stage_sum_ordered(tA, tB, j) < HT_CASC.stage[j].threshold);   // src/ccv.js:222
 }
 
 // predicated ld.shared.u8: lanes with p == false issue no shared-memory access and return dflt

@@ -8,7 +8,9 @@ def default_context(width, height, cascade=None, max_frames=16, device=0):
     key = (device, None if cascade is None else hash(cascade))
     c = _ctx.get(key)
     if c is None or c.max_w < width or c.max_h < height:
-        if c is not None:
+        # a context that still has live camshift.Trackers is NOT closed (they hold its slots and state): the larger
+        # one simply replaces it as the default, the old one lives as long as its trackers do
+        if c is not None and not c.__dict__.get("_live_trackers", 0):
             c.close()
         c = Context(max_width=max(width, 640), max_height=max(height, 480), max_frames=max_frames, device=device,
                     cascade=cascade)

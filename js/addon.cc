@@ -12,6 +12,9 @@
 //   track(handle, slot, rgba, w, h, nCalls) -> {x,y,width,height,angle, window:{x,y,width,height}}
 //   whitebalance(handle, rgba, w, h) -> Number
 //   backprojection(handle, slot, rgba, w, h) -> Uint8ClampedArray
+//   streamStep(handle, rgba /* n frames, one per stream */, n, w, h, interval, minNeighbors, calcAngles)
+//        -> Array<{detection:"VJ"|"CS", x,y,width,height,angle,confidence, found, lost}>   (ht_stream_step)
+//   streamReset(handle, first, n)
 //   destroy(handle)
 #include <node_api.h>
 
@@ -166,6 +169,50 @@ static napi_value Track(napi_env env, napi_callback_info info) {
   return out;
 }
 
+// facetrackr's state machine for n streams in one call (src/facetrackr.js:67-126 + src/main.js:230-244 on the device)
+static napi_value StreamStep(napi_env env, napi_callback_info info) {
+  size_t argc = 8;
+  napi_value argv[8];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  ht_ctx *ctx = Ctx(env, argv[0]);
+  uint8_t *rgba; size_t len;
+  int32_t n, w, h, interval, min_neighbors, calc;
+  if (!GetBytes(env, argv[1], &rgba, &len)) return Throw(env, ctx, HT_ERR_ARG);
+  napi_get_value_int32(env, argv[2], &n); napi_get_value_int32(env, argv[3], &w); napi_get_value_int32(env, argv[4], &h);
+  napi_get_value_int32(env, argv[5], &interval); napi_get_value_int32(env, argv[6], &min_neighbors);
+  napi_get_value_int32(env, argv[7], &calc);
+  if (n <= 0 || len < (size_t)n * w * h * 4) return Throw(env, ctx, HT_ERR_ARG);
+  std::vector<ht_stream_event> ev((size_t)n);
+  int rc = ht_stream_step(ctx, rgba, n, w, h, interval, min_neighbors, calc, ev.data());
+  if (rc < 0) return Throw(env, ctx, rc);
+  napi_value out;
+  napi_create_array_with_length(env, (size_t)n, &out);
+  for (int k = 0; k < n; ++k) {
+    napi_value o, s, b;
+    napi_create_object(env, &o);
+    napi_create_string_utf8(env, ev[k].detection == 2 ? "CS" : "VJ", 2, &s);
+    napi_set_named_property(env, o, "detection", s);
+    SetNum(env, o, "x", ev[k].x); SetNum(env, o, "y", ev[k].y); SetNum(env, o, "width", ev[k].width);
+    SetNum(env, o, "height", ev[k].height); SetNum(env, o, "angle", ev[k].angle); SetNum(env, o, "confidence", ev[k].confidence);
+    napi_get_boolean(env, (ev[k].status & 1) != 0, &b); napi_set_named_property(env, o, "found", b);
+    napi_get_boolean(env, (ev[k].status & 2) != 0, &b); napi_set_named_property(env, o, "lost", b);
+    napi_set_element(env, out, (uint32_t)k, o);
+  }
+  return out;
+}
+
+static napi_value StreamReset(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value argv[3];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  ht_ctx *ctx = Ctx(env, argv[0]);
+  int32_t first, n;
+  napi_get_value_int32(env, argv[1], &first); napi_get_value_int32(env, argv[2], &n);
+  int rc = ht_stream_reset(ctx, first, n);
+  if (rc < 0) return Throw(env, ctx, rc);
+  return nullptr;
+}
+
 static napi_value Whitebalance(napi_env env, napi_callback_info info) {
   size_t argc = 4;
   napi_value argv[4];
@@ -205,6 +252,8 @@ static napi_value Init(napi_env env, napi_value exports) {
       {"detect", nullptr, Detect, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"trackInit", nullptr, TrackInit, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"track", nullptr, Track, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"streamStep", nullptr, StreamStep, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"streamReset", nullptr, StreamReset, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"whitebalance", nullptr, Whitebalance, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"backprojection", nullptr, Backprojection, nullptr, nullptr, nullptr, napi_default, nullptr},
   };

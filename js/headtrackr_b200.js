@@ -58,6 +58,27 @@ exports.install = function (headtrackr, cascadeBlob, opts) {
     };
   };
 
+  // Many streams at once: facetrackr's per-frame state machine for n canvases in one call (ht_stream_step).
+  // Dispatches the same `facetrackingEvent` the reference sends (src/facetrackr.js:112-125), with `stream` added.
+  headtrackr.b200StreamSet = function (n, params) {
+    params = params || {};
+    addon.streamReset(h, 0, n);
+    this.track = function (canvases) {
+      var w = canvases[0].width, hgt = canvases[0].height, all = new Uint8Array(n * w * hgt * 4);
+      for (var k = 0; k < n; k++) all.set(pixels(canvases[k]), k * w * hgt * 4);
+      var ev = addon.streamStep(h, all, n, w, hgt, 5, 1, params.calcAngles ? 1 : 0);
+      for (k = 0; k < n; k++) {
+        if (ev[k].detection !== 'CS') continue;
+        var evt = document.createEvent('Event');
+        evt.initEvent('facetrackingEvent', true, true);
+        evt.stream = k; evt.height = ev[k].height; evt.width = ev[k].width; evt.angle = ev[k].angle;
+        evt.x = ev[k].x; evt.y = ev[k].y; evt.confidence = ev[k].confidence; evt.detection = 'CS'; evt.time = 0;
+        document.dispatchEvent(evt);
+      }
+      return ev;
+    };
+  };
+
   // src/whitebalance.js:5
   headtrackr.getWhitebalance = function (canvas) {
     return addon.whitebalance(h, pixels(canvas), canvas.width, canvas.height);

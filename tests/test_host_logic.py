@@ -98,3 +98,29 @@ def test_synthetic_frames_are_deterministic():
     a, b = synth.frame(5, 160, 120), synth.frame(5, 160, 120)
     assert np.array_equal(a, b) and a.dtype == np.uint8 and a.shape == (120, 160, 4) and (a[..., 3] == 255).all()
     assert not np.array_equal(a, synth.frame(6, 160, 120))
+
+
+def test_tracker_slots_are_a_per_context_free_list():
+    """the 17th Tracker of a 16-slot context used to share slot 0 silently."""
+    import pytest
+
+    class FakeCtx:
+        max_frames = 3
+    c = FakeCtx()
+    got = [camshift._take_slot(c) for _ in range(3)]
+    assert sorted(got) == [0, 1, 2] and c._live_trackers == 3
+    with pytest.raises(RuntimeError):
+        camshift._take_slot(c)
+    camshift._give_slot(c, got[1])
+    assert camshift._take_slot(c) == got[1]
+    other = FakeCtx()
+    assert camshift._take_slot(other) == 0                        # the pool is per context, not global
+
+
+def test_detect_objects_only_accepts_a_grayscaled_canvas():
+    """the reference's detect_objects does no graying (src/ccv.js:171-192); ht_detect always does, so the
+    mirror refuses the one call shape it could not serve identically."""
+    import pytest
+    from headtrackr_b200 import ccv
+    with pytest.raises(TypeError):
+        ccv.detect_objects(Canvas(synth.frame(0, 160, 120)), None, 5, 1, context=object())
