@@ -485,6 +485,12 @@ struct ht_ctx {
   int force_ties = 0;                       // ht_debug_set_exactness: force the exactness fallbacks (tests)
   cudaStream_t pipe_stream = nullptr;
   cudaEvent_t pipe_start = nullptr, pipe_events[4] = {};
+  bool use_tma = false;                     // HT_TMA=1: stage level-1 cascade tiles with cp.async.bulk.tensor
+  DevBuf d_tmaps;                           // [arenas][scales] 128 B CUtensorMaps over the level-1 planes
+  const void *tmap_arena = nullptr;
+  const void *tmap_plan = nullptr;
+  size_t tmap_wave_words = 0;
+  int tmap_arenas = 0;
   int last_wave_f0 = 0, last_wave_n = 0;    // frames whose pyramid is still in the arena (ht_debug_plane)
   const uint32_t *last_wave_arena = nullptr;
   DevBuf d_late_chunk0;
@@ -573,8 +579,13 @@ int upload_slots(ht_ctx *ctx, const int32_t *slots, int n, const int32_t **d_slo
   *d_slots = nullptr;
   if (!slots) return HT_OK;
   if (is_device_ptr(slots)) { *d_slots = slots; return HT_OK; }
-  for (int i = 0; i < n; ++i)
+  // two entries with the same slot would make two clusters of k_track (or two CTAs of k_track_init) race on
+  // state[slot] / model_hist[slot].  (Device-resident slot arrays are the caller's responsibility: see the header.)
+  std::vector<uint8_t> seen((size_t)ctx->cfg.max_frames, 0);
+  for (int i = 0; i < n; ++i) {
     if (slots[i] < 0 || slots[i] >= ctx->cfg.max_frames) return ctx->fail(HT_ERR_ARG, "slot %d out of range", slots[i]);
+    if (seen[(size_t)slots[i]]++) return ctx->fail(HT_ERR_ARG, "slot %d appears twice in one batch", slots[i]);
+  }
   CK(ctx->d_slots.reserve(sizeof(int32_t) * ctx->cfg.max_frames));
   CK(cudaMemcpyAsync(ctx->d_slots.p, slots, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
   *d_slots = ctx->d_slots.as<int32_t>();
@@ -769,6 +780,52 @@ int set_kernel_attributes(ht_ctx *ctx) {
   return HT_OK;
 }
 
+// Tensor maps for the TMA staging of level-1 cascade tiles: one 3-D map (column, row, frame quad) per scale and
+// arena over the pyramid arena (32-bit elements: one word = the pixel in 4 frames).  Re-encoded whenever the arena
+// allocation, its partition into waves or the plan changes.
+int ensure_tensor_maps(ht_ctx *ctx, Plan *P, int n_arenas, size_t wave_words, int quads_per_arena) {
+  if (ctx->tmap_arena == ctx->arena.p && ctx->tmap_plan == P && ctx->tmap_wave_words == wave_words && ctx->tmap_arenas == n_arenas)
+    return HT_OK;
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return ctx->fail(HT_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  const size_t ns = P->scales.size();
+  std::vector<CUtensorMap> maps(ns * (size_t)n_arenas);
+  memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+  for (int a = 0; a < n_arenas; ++a)
+    for (size_t i = 0; i < ns; ++i) {
+      const DevScale &sc = P->scales[i];
+      if (sc.qw <= 0 || sc.qh <= 0) continue;
+      const DevPlane &pl = P->planes[sc.p1];
+      cuuint64_t dims[3] = {(cuuint64_t)pl.pitch, (cuuint64_t)pl.h, (cuuint64_t)quads_per_arena};
+      cuuint64_t strides[2] = {(cuuint64_t)pl.pitch * 4, (cuuint64_t)P->arena_stride * 4};
+      cuuint32_t box[3] = {(cuuint32_t)P1, (cuuint32_t)L1_ROWS, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      void *base = ctx->arena.as<uint32_t>() + (size_t)a * wave_words + pl.off;
+      CUresult r = encode(&maps[(size_t)a * ns + i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return ctx->fail(HT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for scale %d", (int)r, (int)i);
+    }
+  CK(ctx->d_tmaps.reserve(maps.size() * sizeof(CUtensorMap)));
+  CK(cudaMemcpyAsync(ctx->d_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // `maps` is a local; re-encoding only happens when buffers change
+  ctx->tmap_arena = ctx->arena.p;
+  ctx->tmap_plan = P;
+  ctx->tmap_wave_words = wave_words;
+  ctx->tmap_arenas = n_arenas;
+  return HT_OK;
+}
+
 // what camshift needs from the frame, produced by the gray pass of the same read (src/camshift.js:268)
 struct HistOut {
   uint32_t *hist;   // [n][4096] current-frame histograms (frame f0 first), or NULL
@@ -792,6 +849,10 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
   const size_t wave_words = P->arena_stride * (size_t)(wave / 4);
   const bool piped = ctx->detect_pipe > 0 && n > wave;
   CK(ctx->arena.reserve(wave_words * 4 * (piped ? 2 : 1)));
+  if (ctx->use_tma) {
+    const int trc = ensure_tensor_maps(ctx, P, piped ? 2 : 1, wave_words, wave / 4);
+    if (trc != HT_OK) return trc;
+  }
   CK(cudaMemsetAsync(ctx->raw_count.as<uint32_t>() + f0, 0, sizeof(uint32_t) * n, st));
   if (ho.hist) CK(cudaMemsetAsync(ho.hist, 0, (size_t)n * 4096 * sizeof(uint32_t), st));
   // make this context's cascade the active __constant__ table (contexts with the same blob share it;
@@ -860,7 +921,9 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       ctx->prof_begin(HT_PROF_CASCADE);
       auto kern = ctx->hc.fast ? k_cascade<true> : k_cascade<false>;
       kern<<<dim3((unsigned)P->casc_tiles.size(), quads), CASCADE_THREADS, CASC_SMEM, st>>>(
-          P->dplan, ctx->d_casc.as<LateFeat>(), ctx->d_late_chunk0.as<int32_t>(), arena, P->arena_stride, nw,
+          P->dplan, ctx->d_casc.as<LateFeat>(), ctx->d_late_chunk0.as<int32_t>(),
+          ctx->use_tma ? ctx->d_tmaps.as<uint8_t>() + (piped ? (size_t)(wi & 1) : 0) * P->scales.size() * 128 : nullptr, 0,
+          arena, P->arena_stride, nw,
           ctx->raw_keys.as<uint32_t>() + (size_t)fa * ctx->raw_cap, ctx->raw_conf.as<double>() + (size_t)fa * ctx->raw_cap,
           ctx->raw_count.as<uint32_t>() + fa, ctx->raw_cap, ctx->force_ties, qm);
       ctx->prof_end();
@@ -1002,6 +1065,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
     }
   }
   if (const char *wv = getenv("HT_WAVE")) c->wave_frames = std::max(4, atoi(wv));
+  if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
   if (const char *ov = getenv("HT_OVERLAP")) { c->overlap_track = atoi(ov) != 0 ? 1 : 0; c->overlap_parts = atoi(ov); }
   if (const char *hc2 = getenv("HT_H2D_CHUNK")) c->h2d_chunk = std::max(1, atoi(hc2));
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
@@ -1038,7 +1102,7 @@ void ht_destroy(ht_ctx *ctx) {
   for (auto &kv : ctx->plans) kv.second->dev.release();
   DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
                     &ctx->labels, &ctx->seq2, &ctx->d_out_rects, &ctx->d_out_counts, &ctx->d_flags, &ctx->model_hist,
-                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_late_chunk0, &ctx->d_track_cost, &ctx->d_stream_mode, &ctx->d_stream_mask, &ctx->d_stream_cs, &ctx->d_stream_init, &ctx->d_stream_events, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
+                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_tmaps, &ctx->d_late_chunk0, &ctx->d_track_cost, &ctx->d_stream_mode, &ctx->d_stream_mask, &ctx->d_stream_cs, &ctx->d_stream_init, &ctx->d_stream_events, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
                     &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
   for (DevBuf *b : bufs) b->release();
   for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }

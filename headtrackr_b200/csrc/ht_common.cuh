@@ -45,9 +45,9 @@ constexpr int P1 = 76;
 constexpr int L2_ROWS = TH + 5;               // 21 per copy
 constexpr int L2_COLS = TW + 5;               // 37 per copy
 constexpr int P2 = 76;
-constexpr int W1 = L0_ROWS * P0;              // 12900
-constexpr int W2 = W1 + L1_ROWS * P1;         // 16168
-constexpr int TILE_WORDS = W2 + 2 * L2_ROWS * P2;   // 19360 words = 77,440 B
+constexpr int W1 = (L0_ROWS * P0 + 31) / 32 * 32;   // 12928: 128-byte aligned, the level-1 box can be written by TMA
+constexpr int W2 = W1 + L1_ROWS * P1;         // 16196
+constexpr int TILE_WORDS = W2 + 2 * L2_ROWS * P2;   // 19388 words = 77,552 B
 static_assert((2 * P0 - P1) % 32 == 0 && P1 == P2, "bank classes of the two bases must coincide");
 static_assert(2 * L2_COLS <= P2 && L1_COLS <= P1, "tile pitches");
 constexpr int NQUADWIN = TW * TH * 4;         // window positions per tile (each x 4 frames)

@@ -359,6 +359,7 @@ __device__ __forceinline__ void cp_async4(unsigned saddr, const void *g, bool va
 template <bool FAST>
 __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
                                                                 const int32_t *__restrict__ late_chunk0,
+                                                                const void *__restrict__ tmaps, int tma_quad0,
                                                                 const uint32_t *__restrict__ arena, size_t quad_stride,
                                                                 int n_frames, uint32_t *__restrict__ raw_keys,
                                                                 double *__restrict__ raw_conf,
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
   uint16_t *cl0 = reinterpret_cast<uint16_t *>(smem + TILE_WORDS);         // [CLASS_CAP][32] survivor lists (ping)
   uint16_t *cl1 = cl0 + NWIN;                                              // (pong)
   int *cnt = reinterpret_cast<int *>(cl1 + NWIN);                          // [MAX_GROUPS + 2][32] list lengths per phase
+  __shared__ __align__(8) unsigned long long tma_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int quad = blockIdx.y;
@@ -383,6 +385,27 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
 
   // ---- stage the three levels in shared memory (layout in ht_common.cuh): 4-byte cp.async with the layout
   //      permutation in the destination address; words outside a plane are zero-filled ----
+  // Level 1 is a plain 2-D box of its plane (L1_ROWS x P1 words = 13 KB): when tensor maps are given it is staged
+  // by the TMA engine - one elected thread issues cp.async.bulk.tensor (3-D map: column, row, frame quad; elements
+  // outside the plane are zero-filled) completing on an mbarrier - while all threads scatter levels 0 and 2.
+  const bool use_tma = tmaps != nullptr;
+  if (use_tma) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // nobody may poll the barrier before it is initialised
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(L1_ROWS * P1 * 4)) : "memory");
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + W1);
+      const unsigned long long map = (unsigned long long)(reinterpret_cast<const uint8_t *>(tmaps) + 128 * (size_t)tl.scale);
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(dst), "l"(map), "r"(2 * x0), "r"(2 * y0), "r"(tma_quad0 + quad), "r"(bar)
+          : "memory");
+    }
+  }
   {
     const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
     {  // level 0: parity-split columns
@@ -396,7 +419,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
         cp_async4(tile_s + 4u * (unsigned)i, ok ? src + (size_t)(Y0 + r) * pl.pitch + X0 + X : src, ok);
       }
     }
-    {  // level 1
+    if (!use_tma) {  // level 1
       const DevPlane pl = plan.planes[sc.p1];
       const uint32_t *src = qa + pl.off;
       const int X0 = 2 * x0, Y0 = 2 * y0;
@@ -417,6 +440,15 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  }
+  if (use_tma) {   // every thread observes the completion of the bulk copy (phase 0 of the barrier)
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+    unsigned done = 0;
+    for (int spin = 0; !done && spin < (1 << 24); ++spin) {   // bounded: a bad descriptor must not hang the device
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar) : "memory");
+    }
+    if (!done) __trap();
   }
   __syncthreads();
 

@@ -517,6 +517,10 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
               const double b = (m.m11 - m.m01 * xc) * inv, d = a + c;
               const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
               amb = trunc_ambiguous(sqrt((d - e) * 0.5)) || trunc_ambiguous(sqrt((d + e) * 0.5));
+              // `if (ang < 0) ang += PI` (src/camshift.js:244) follows the SIGN of b = mu11 / m00: for a symmetric blob
+              // b is rounding residue and the parallel summation order may flip it (angle off by PI, far outside
+              // the 1e-4 tolerance) - take the strict order whenever b is not clearly away from 0
+              amb = amb || fabs(b) <= 1e-9 * (fabs(a) + fabs(c) + 1.0);
             } else {
               amb = trunc_ambiguous(sqrt(a)) || trunc_ambiguous(sqrt(c));
             }

@@ -104,7 +104,9 @@ int ht_detect(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interva
               ht_rect *out_rects, int32_t *out_counts);
 
 /* camshift.Tracker.initTracker(frame, Rectangle(x,y,w,h)) for n tracker slots (src/camshift.js:198-211).
- *   slots : [n] slot ids in [0,max_frames) (NULL -> 0..n-1); rgba: n frames; rects: [n][4] = x,y,w,h
+ *   slots : [n] DISTINCT slot ids in [0,max_frames) (NULL -> 0..n-1); rgba: n frames; rects: [n][4] = x,y,w,h
+ *           (host arrays are checked: out-of-range or repeated ids -> HT_ERR_ARG; a device-resident slot array is
+ *           used as is - ids out of range or repeated are undefined behaviour, like any bad device pointer)
  * Pixels of the rectangle outside the frame count as (0,0,0) like canvas getImageData. */
 int ht_track_init(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *rgba, int w, int h,
                   const int32_t *rects, int calc_angles);

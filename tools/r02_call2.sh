@@ -8,6 +8,8 @@ echo "sanitizer rc=$?"; tail -5 $O/r02c2_sanitizer.log
 # 2. parity tests
 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > $O/r02c2_pytest.log 2>&1
 echo "pytest rc=$?"; tail -15 $O/r02c2_pytest.log
+HT_TMA=1 timeout 900 python -m pytest tests/test_gpu_detect.py tests/test_gpu_quads.py -q --timeout 600 > $O/r02c2_pytest_tma.log 2>&1
+echo "pytest (HT_TMA=1) rc=$?"; tail -4 $O/r02c2_pytest_tma.log
 # 3. timing variants (detect workload isolates the new kernels)
 run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline $BARGS > $O/r02c2_$tag.json 2> $O/r02c2_$tag.err; }
 BARGS="--workload detect"
@@ -18,6 +20,7 @@ run det_w1024 HT_WAVE=1024
 run det_w32_pipe HT_DETECT_PIPE=1
 run det_w16_pipe HT_WAVE=16 HT_DETECT_PIPE=1
 run det_q3 HT_LIB=variants/libht_q3.so
+run det_tma HT_TMA=1
 BARGS=""
 run full_w32
 run full_w32_pipe HT_DETECT_PIPE=1
