@@ -1666,6 +1666,30 @@ extern "C" int ht_selftest_planes(int w, int h, int interval, int32_t *out, int 
   return 0;
 }
 
+// gray + pyramid of one frame quad with the kernels' own per-thread code (gray_item, resample_thread), thread by thread
+extern "C" int ht_selftest_pyramid(int w, int h, int interval, const uint8_t *rgba, int n_frames, uint32_t *arena, size_t arena_words) {
+  Plan P;
+  std::string err;
+  if (build_plan(P, w, h, interval, 24, 24, err, false) != HT_OK) return -1;
+  if (arena_words < P.arena_stride || n_frames < 1 || n_frames > 4) return -2;
+  DevPlan dp{};
+  dp.planes = P.planes.data(); dp.jobs = P.jobs.data(); dp.taps = P.taps.data(); dp.pyr_tiles = P.pyr_tiles.data();
+  dp.scales = P.scales.data(); dp.casc_tiles = P.casc_tiles.data();
+  dp.n_planes = (int)P.planes.size(); dp.n_jobs = (int)P.jobs.size();
+  dp.n_scales = (int)P.scales.size(); dp.n_casc_tiles = (int)P.casc_tiles.size();
+  const unsigned fmask = (1u << n_frames) - 1u;
+  const int pitch0 = P.planes[0].pitch, gpr = pitch0 >> 2;
+  const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(rgba) & 15u) == 0);
+  for (int it = 0; it < gpr * h; ++it) {
+    if (vec) gray_item<true, false>(rgba, (size_t)w * h * 4, 0, fmask, arena, w, pitch0, gpr, it, nullptr, nullptr, w * h);
+    else gray_item<false, false>(rgba, (size_t)w * h * 4, 0, fmask, arena, w, pitch0, gpr, it, nullptr, nullptr, w * h);
+  }
+  for (size_t g = 1; g + 1 < P.gen_tile_begin.size(); ++g)
+    for (int t = P.gen_tile_begin[g]; t < P.gen_tile_begin[g + 1]; ++t)
+      for (int tid = 0; tid < 256; ++tid) resample_thread(dp, P.gen_tile_begin[g], arena, P.arena_stride, t - P.gen_tile_begin[g], 0, tid);
+  return 0;
+}
+
 extern "C" int ht_selftest_cascade(const void *blob, size_t blob_len, int w, int h, int interval, const uint32_t *arena,
                                    int n_frames, int force_ties, int quad_stages, double *out /* [4][cap][4] x,y,width,conf */,
                                    int32_t *counts, int cap) {

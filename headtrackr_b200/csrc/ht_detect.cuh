@@ -12,13 +12,13 @@ namespace ht {
 
 // Which of the 4 frames of a quad take part in a launch: the first n_frames - 4*quad of them (batch calls), or the
 // per-quad mask the stream scheduler built (ht_stream_step: only the streams that are in detection mode).
-__device__ __forceinline__ unsigned quad_frames(int quad, int n_frames, const uint8_t *__restrict__ quad_mask) {
+__host__ __device__ __forceinline__ unsigned quad_frames(int quad, int n_frames, const uint8_t *__restrict__ quad_mask) {
   const int left = n_frames - 4 * quad;
   const unsigned prefix = left >= 4 ? 15u : (left > 0 ? (1u << left) - 1u : 0u);
   return quad_mask ? (prefix & quad_mask[quad]) : prefix;
 }
 
-__device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:63-66, 345-348
+__host__ __device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:63-66, 345-348
   return ((px & 0xf0u) << 4) | ((px >> 8) & 0xf0u) | ((px >> 20) & 0xfu);
 }
 
@@ -32,7 +32,8 @@ __device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/camshift.js:6
 // a byte becomes a double by planting it in the mantissa of 2^52 and subtracting 2^52 (exact), and the round-half-
 // even store is `v + 2^52` read back from the low mantissa bits (exact for 0 <= v < 2^31; proven equal to
 // rint() for every triple in the same test).  9 fp64 pipe operations per pixel, no conversions.
-__device__ __forceinline__ uint32_t gray_of(uint32_t px) {
+__host__ __device__ __forceinline__ uint32_t gray_of(uint32_t px) {
+#ifdef __CUDA_ARCH__
   const double M = 4503599627370496.0;   // 2^52
   const double r = __dsub_rn(__hiloint2double(0x43300000, (int)(px & 0xffu)), M);
   const double g = __dsub_rn(__hiloint2double(0x43300000, (int)((px >> 8) & 0xffu)), M);
@@ -40,6 +41,30 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t px) {
   const double v = __dadd_rn(__dadd_rn(__dmul_rn(r, 0.3), __dmul_rn(g, 0.59)), __dmul_rn(b, 0.11));
   const uint32_t iv = (uint32_t)__double2loint(__dadd_rn(v, M));   // round half to even == Uint8ClampedArray store
   return min(iv, 255u);
+#else   // host emulation: the same operations through a union (no FMA contraction: the file is built with -fmad=false
+        // and the host compiler is not given an FMA target)
+  union { double d; unsigned long long u; } c;
+  const double M = 4503599627370496.0;
+  volatile double r, g, b, t0, t1, t2, v;
+  c.u = 0x4330000000000000ull | (px & 0xffu); r = c.d - M;
+  c.u = 0x4330000000000000ull | ((px >> 8) & 0xffu); g = c.d - M;
+  c.u = 0x4330000000000000ull | ((px >> 16) & 0xffu); b = c.d - M;
+  t0 = r * 0.3; t1 = g * 0.59; t2 = b * 0.11;
+  v = t0 + t1; v = v + t2;
+  c.d = v + M;
+  const uint32_t iv = (uint32_t)(c.u & 0xffffffffull);
+  return iv < 255u ? iv : 255u;
+#endif
+}
+
+// ld.global.nc on the device, a plain load in the host emulation (tests/test_pyramid_host.py)
+template <class T>
+__host__ __device__ __forceinline__ T ld_ro(const T *p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
 }
 
 // One thread = 4 horizontally adjacent pixels of the 4 frames of a quad: four 16 B loads (one per frame), sixteen
@@ -47,6 +72,65 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t px) {
 // from the same read of the frame (src/camshift.js:49-72 via :268): the 4096-bin RGB histogram of each frame
 // (shared-memory atomics, flushed per CTA) and the u16 plane of weight-table offsets (8 * bin) that k_track reads.
 // grid = (chunks, quads).  HBM-bound: 4 B read + 1 B (+ 2 B) written per pixel.
+// gray_item is one loop iteration of a thread (also run on the host by the emulation test, HIST = false).
+template <bool VEC, bool HIST>
+__host__ __device__ __forceinline__ void gray_item(const uint8_t *__restrict__ rgba, size_t frame_bytes, int quad, unsigned fmask,
+                                                   uint32_t *__restrict__ dst_plane, int w, int pitch0, int gpr, int it,
+                                                   uint32_t *sh_hist, uint16_t *__restrict__ bins, int n_px) {
+  const int row = it / gpr, col = (it - row * gpr) * 4;
+  uint32_t px[4][4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    px[f][0] = px[f][1] = px[f][2] = px[f][3] = 0;
+    if (((fmask >> f) & 1u) && col < w) {
+      const uint8_t *src = rgba + (size_t)(4 * quad + f) * frame_bytes + ((size_t)row * w + col) * 4;
+      if (VEC) {  // w % 4 == 0 and 16 B aligned frames
+        const uint4 v = ld_ro(reinterpret_cast<const uint4 *>(src));
+        px[f][0] = v.x; px[f][1] = v.y; px[f][2] = v.z; px[f][3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (col + i < w) px[f][i] = ld_ro(reinterpret_cast<const uint32_t *>(src) + i);
+      }
+    }
+  }
+  uint32_t out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out[i] = 0;
+    if (col + i < w) {            // pad columns and missing frames are written as 0
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        if ((fmask >> f) & 1u) out[i] |= gray_of(px[f][i]) << (8 * f);
+    }
+  }
+  *reinterpret_cast<uint4 *>(dst_plane + (size_t)row * pitch0 + col) = make_uint4(out[0], out[1], out[2], out[3]);
+#ifdef __CUDA_ARCH__
+  if (HIST) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if (!((fmask >> f) & 1u) || col >= w) continue;
+      uint32_t b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        b[i] = rgb_bin(px[f][i]);
+        if (col + i < w) atomicAdd(&sh_hist[f * 4096 + b[i]], 1u);
+      }
+      if (bins) {
+        uint16_t *bo = bins + (size_t)(4 * quad + f) * n_px + (size_t)row * w + col;
+        if (VEC) {
+          *reinterpret_cast<uint2 *>(bo) = make_uint2((b[0] << 3) | (b[1] << 19), (b[2] << 3) | (b[3] << 19));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (col + i < w) bo[i] = (uint16_t)(b[i] << 3);
+        }
+      }
+    }
+  }
+#endif
+}
+
 template <bool VEC, bool HIST>
 __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_frames,
                                               uint32_t *__restrict__ arena, size_t quad_stride, int w, int h,
@@ -64,60 +148,9 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
   const int n_groups = gpr * h;
   const int per = (n_groups + chunks - 1) / chunks;
   const int beg = blockIdx.x * per, end = min(n_groups, beg + per);
-  const int n_px = w * h;
   uint32_t *dst_plane = arena + (size_t)quad * quad_stride;
-  for (int it = beg + threadIdx.x; it < end; it += 256) {
-    const int row = it / gpr, col = (it - row * gpr) * 4;
-    uint32_t px[4][4];
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      px[f][0] = px[f][1] = px[f][2] = px[f][3] = 0;
-      if (((fmask >> f) & 1u) && col < w) {
-        const uint8_t *src = rgba + (size_t)(4 * quad + f) * frame_bytes + ((size_t)row * w + col) * 4;
-        if (VEC) {  // w % 4 == 0 and 16 B aligned frames
-          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
-          px[f][0] = v.x; px[f][1] = v.y; px[f][2] = v.z; px[f][3] = v.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (col + i < w) px[f][i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
-        }
-      }
-    }
-    uint32_t out[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      out[i] = 0;
-      if (col + i < w) {            // pad columns and missing frames are written as 0
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-          if ((fmask >> f) & 1u) out[i] |= gray_of(px[f][i]) << (8 * f);
-      }
-    }
-    *reinterpret_cast<uint4 *>(dst_plane + (size_t)row * pitch0 + col) = make_uint4(out[0], out[1], out[2], out[3]);
-    if (HIST) {
-#pragma unroll
-      for (int f = 0; f < 4; ++f) {
-        if (!((fmask >> f) & 1u) || col >= w) continue;
-        uint32_t b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          b[i] = rgb_bin(px[f][i]);
-          if (col + i < w) atomicAdd(&sh_hist[f * 4096 + b[i]], 1u);
-        }
-        if (bins) {
-          uint16_t *bo = bins + (size_t)(4 * quad + f) * n_px + (size_t)row * w + col;
-          if (VEC) {
-            *reinterpret_cast<uint2 *>(bo) = make_uint2((b[0] << 3) | (b[1] << 19), (b[2] << 3) | (b[3] << 19));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (col + i < w) bo[i] = (uint16_t)(b[i] << 3);
-          }
-        }
-      }
-    }
-  }
+  for (int it = beg + threadIdx.x; it < end; it += 256)
+    gray_item<VEC, HIST>(rgba, frame_bytes, quad, fmask, dst_plane, w, pitch0, gpr, it, sh_hist, bins, w * h);
   if (HIST) {
     __syncthreads();
     for (int f = 0; f < 4; ++f) {
@@ -139,14 +172,13 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
 // complete).  Block = 32 x 32 pixels of one destination plane of one frame quad; thread = one column x 4 rows.
 // Every load and store is a whole word (4 frames): the tap positions, weights and addresses - most of round 1's
 // 43 instructions per output pixel - are computed once for four frames.
-__global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint32_t *__restrict__ arena,
-                                                  size_t quad_stride, int n_frames, const uint8_t *__restrict__ quad_mask) {
-  if (quad_frames(blockIdx.y, n_frames, quad_mask) == 0u) return;
+__host__ __device__ __forceinline__ void resample_thread(const DevPlan &plan, int tile0, uint32_t *__restrict__ arena,
+                                                         size_t quad_stride, int bx, int by, int tid) {
   // per-block metadata: one 8 B tile record and one 64 B job record, fetched with vector loads
-  const uint2 tl = __ldg(reinterpret_cast<const uint2 *>(plan.pyr_tiles + tile0 + blockIdx.x));
+  const uint2 tl = ld_ro(reinterpret_cast<const uint2 *>(plan.pyr_tiles + tile0 + bx));
   const int job_id = (int)(tl.x & 0xffffu), tx = (int)(tl.x >> 16), ty = (int)(tl.y & 0xffffu);
   const uint4 *jp = reinterpret_cast<const uint4 *>(plan.jobs + job_id);
-  const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1), j2 = __ldg(jp + 2);
+  const uint4 j0 = ld_ro(jp), j1 = ld_ro(jp + 1), j2 = ld_ro(jp + 2);
   // DevJob: {src_off, dst_off, src_pitch, dst_pitch} {dst_h, dw, dh, col_off} {row_off, magic, shift, half} {..}
   const uint32_t src_off = j0.x, dst_off = j0.y;
   const int src_pitch = (int)j0.z, dst_pitch = (int)j0.w;
@@ -154,15 +186,15 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint3
   const uint32_t col_off = j1.w, row_off = j2.x, magic = j2.y, shift = j2.z, half = j2.w;
   // lane = column (adjacent lanes read adjacent-ish source words), each thread produces 4 consecutive rows and
   // reuses its column taps for all of them.
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = tid & 31, warp = tid >> 5;
   const int X = tx * 32 + lane;
   const int Y0 = ty * 32 + warp * 4;
   if (Y0 >= dst_h || X >= dst_pitch) return;
-  uint32_t *quad = arena + (size_t)blockIdx.y * quad_stride;
+  uint32_t *quad = arena + (size_t)by * quad_stride;
   uint32_t xa = 0, xb = 0, wx0 = 0, wx1 = 0;
   const bool col_ok = X < dw;
   if (col_ok) {
-    const uint2 cx = __ldg(reinterpret_cast<const uint2 *>(plan.taps + col_off + X));   // {a | b<<16, f}
+    const uint2 cx = ld_ro(reinterpret_cast<const uint2 *>(plan.taps + col_off + X));   // {a | b<<16, f}
     xa = cx.x & 0xffffu; xb = cx.x >> 16;
     wx1 = cx.y & 0xffffu; wx0 = 2u * (uint32_t)dw - wx1;
   }
@@ -175,7 +207,7 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint3
   for (int r = 0; r < 4; ++r) {
     const int Y = Y0 + r;
     uint2 ry = make_uint2(0u, 0u);
-    if (Y < dh) ry = __ldg(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // warp-uniform
+    if (Y < dh) ry = ld_ro(reinterpret_cast<const uint2 *>(plan.taps + row_off + Y));   // warp-uniform
     oa[r] = (ry.x & 0xffffu) * (uint32_t)src_pitch;
     ob[r] = (ry.x >> 16) * (uint32_t)src_pitch;
     wy1[r] = ry.y & 0xffffu;
@@ -206,6 +238,12 @@ __global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint3
     }
     dst[(uint32_t)r * (uint32_t)dst_pitch] = out;
   }
+}
+
+__global__ void __launch_bounds__(256) k_resample(DevPlan plan, int tile0, uint32_t *__restrict__ arena,
+                                                  size_t quad_stride, int n_frames, const uint8_t *__restrict__ quad_mask) {
+  if (quad_frames(blockIdx.y, n_frames, quad_mask) == 0u) return;
+  resample_thread(plan, tile0, arena, quad_stride, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
