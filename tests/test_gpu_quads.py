@@ -158,3 +158,37 @@ def test_track_on_a_4_byte_aligned_device_pointer(ctx, blob):
     w = ot.track_obj()
     assert (objs[0]["x"], objs[0]["y"], objs[0]["width"], objs[0]["height"]) == (w["x"], w["y"], w["width"], w["height"])
     assert [tup(d) for d in ctx.detect(t, 5, 1)[0]] == want
+
+
+@pytest.mark.parametrize("calc_angles", [False, True])
+def test_crafted_frame_takes_the_serial_fallback_by_itself(ctx, calc_angles):
+    """A frame on which mean-shift steps are EXACT integers in real arithmetic: a 40x60 block of one colour on a
+    background of another, tracker seeded inside the block (so only the block's bin has weight, v = 1000/2400, not
+    dyadic).  Once the window contains the block, (xc - w/2) is an integer k in exact arithmetic and k +- 1e-14 in
+    fp64 depending on the summation order - `>>0` (src/camshift.js:295-296) would truncate to k or k-1.  The kernel
+    must notice (trunc_ambiguous) and re-derive the moments in the reference's order: serial_passes > 0 WITHOUT the
+    debug knob, and every call equal to the oracle."""
+    W, H = 160, 120
+    f = np.zeros((H, W, 4), np.uint8)
+    f[..., 3] = 255
+    f[..., :3] = (200, 50, 50)
+    f[30:90, 60:100, :3] = (50, 200, 50)
+    rect = [70, 40, 25, 40]
+    ctx.set_track_memo(False)
+    try:
+        ctx.debug_set_exactness(0)
+        ctx.track_init(f, [rect], calc_angles=calc_angles)
+        ot = oracle.CamshiftTracker(calc_angles=calc_angles)
+        ot.init_tracker(f, *rect)
+        ctx.debug_track_stats(reset=True)
+        for call in range(8):
+            objs, wins = ctx.track(f, n_calls=1)
+            ot.track(f)
+            w = ot.track_obj()
+            assert (objs[0]["x"], objs[0]["y"], objs[0]["width"], objs[0]["height"]) == (w["x"], w["y"], w["width"], w["height"]), call
+            assert abs(objs[0]["angle"] - w["angle"]) <= 1e-4
+            assert wins[0] == ot.search_window(), call
+        st = ctx.debug_track_stats(reset=True)
+        assert st["serial_passes"] > 0, st
+    finally:
+        ctx.set_track_memo(True)
