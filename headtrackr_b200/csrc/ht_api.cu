@@ -249,6 +249,7 @@ struct HostCascade {
   uint64_t id = 0;      // FNV-1a of cc: identical cascades share the loaded constants
   bool fast = false;    // blob == the cascade the generated stages were specialised for
   std::vector<LateFeat> late;          // late-stage records in scheduled order, 32 per chunk
+  size_t n_sched = 0;                  // records of the schedule; late[n_sched + k] = feature k in original order
   std::vector<int32_t> late_chunk0;    // [n_stages + 1] first chunk of every stage
   int late_conflicts = 0;              // bank conflicts the schedule could not avoid (diagnostic)
 };
@@ -419,6 +420,16 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   }
   hc.late_chunk0[hc.n_stages] = (int32_t)(hc.late.size() / 32);
   if (hc.late.empty()) hc.late.resize(32);
+  // every feature once more in ORIGINAL order: the warp-parallel ordered fp64 sum (stage_sum_ordered_warp)
+  hc.n_sched = hc.late.size();
+  for (int k = 0; k < hc.n_features; ++k) {
+    LateFeat lf{};
+    for (int q = 0; q < 10; ++q) lf.off[q] = 0xFFFF;
+    for (int q = 0; q < (cc.np_nn[k] & 15); ++q) lf.off[q] = cc.off[k][q];
+    for (int q = 0; q < (cc.np_nn[k] >> 4); ++q) lf.off[5 + q] = cc.off[k][5 + q];
+    lf.a_int = (int32_t)a_int[k];
+    hc.late.push_back(lf);
+  }
   uint64_t hsh = 1469598103934665603ull;
   const uint8_t *cb = reinterpret_cast<const uint8_t *>(&cc);
   for (size_t i = 0; i < sizeof(cc); ++i) { hsh ^= cb[i]; hsh *= 1099511628211ull; }
@@ -481,7 +492,8 @@ struct ht_ctx {
   // 37.6k vs 33.0k frames/s with 4 parts (8 parts 36.8k, 16 parts 28.6k).  For device-resident frames it was
   // measured slower (24.4-26.7 vs 22.3 ms per step) and stays off.  HT_OVERLAP=0 disables, HT_OVERLAP=<parts> forces.
   int detect_pipe = 0;                      // HT_DETECT_PIPE=1: gray + pyramid of wave w+1 on a second stream under the cascade of wave w
-  int wave_frames = 32;                     // frames per L2-resident wave of run_detect (HT_WAVE)
+  int wave_frames = 0;                      // frames per wave of run_detect (HT_WAVE); 0: from wave_mb
+  int wave_mb = 64;                         // pyramid-arena budget of one wave in MB (HT_WAVE_MB): half of the 126 MB L2
   int force_ties = 0;                       // ht_debug_set_exactness: force the exactness fallbacks (tests)
   cudaStream_t pipe_stream = nullptr;
   cudaEvent_t pipe_start = nullptr, pipe_events[4] = {};
@@ -845,7 +857,9 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
   cudaStream_t st = ctx->stream;
   const int w = P->w, h = P->h;
   const size_t frame_bytes = (size_t)w * h * 4;
-  const int wave = std::max(4, ctx->wave_frames & ~3);
+  // frames per wave: HT_WAVE, or as many as fit the arena budget (one frame of a quad costs arena_stride bytes)
+  const int wave = ctx->wave_frames > 0 ? std::max(4, ctx->wave_frames & ~3)
+                                        : std::max(4, (int)std::min<size_t>(((size_t)ctx->wave_mb << 20) / P->arena_stride, 1u << 20) & ~3);
   const size_t wave_words = P->arena_stride * (size_t)(wave / 4);
   const bool piped = ctx->detect_pipe > 0 && n > wave;
   CK(ctx->arena.reserve(wave_words * 4 * (piped ? 2 : 1)));
@@ -921,7 +935,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       ctx->prof_begin(HT_PROF_CASCADE);
       auto kern = ctx->hc.fast ? k_cascade<true> : k_cascade<false>;
       kern<<<dim3((unsigned)P->casc_tiles.size(), quads), CASCADE_THREADS, CASC_SMEM, st>>>(
-          P->dplan, ctx->d_casc.as<LateFeat>(), ctx->d_late_chunk0.as<int32_t>(),
+          P->dplan, ctx->d_casc.as<LateFeat>(), ctx->d_casc.as<LateFeat>() + ctx->hc.n_sched, ctx->d_late_chunk0.as<int32_t>(),
           ctx->use_tma ? ctx->d_tmaps.as<uint8_t>() + (piped ? (size_t)(wi & 1) : 0) * P->scales.size() * 128 : nullptr, 0,
           arena, P->arena_stride, nw,
           ctx->raw_keys.as<uint32_t>() + (size_t)fa * ctx->raw_cap, ctx->raw_conf.as<double>() + (size_t)fa * ctx->raw_cap,
@@ -1065,6 +1079,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
     }
   }
   if (const char *wv = getenv("HT_WAVE")) c->wave_frames = std::max(4, atoi(wv));
+  if (const char *wm = getenv("HT_WAVE_MB")) c->wave_mb = std::max(1, atoi(wm));
   if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
   if (const char *ov = getenv("HT_OVERLAP")) { c->overlap_track = atoi(ov) != 0 ? 1 : 0; c->overlap_parts = atoi(ov); }
   if (const char *hc2 = getenv("HT_H2D_CHUNK")) c->h2d_chunk = std::max(1, atoi(hc2));
@@ -1572,7 +1587,7 @@ int ht_debug_plane(ht_ctx *ctx, int frame, int slot, int q, uint8_t *out, int ca
   if (!out || cap_bytes < pl.w * pl.h) return ctx->fail(HT_ERR_ARG, "output too small");
   if (frame < ctx->last_wave_f0 || frame >= ctx->last_wave_f0 + ctx->last_wave_n || !ctx->last_wave_arena)
     return ctx->fail(HT_ERR_STATE, "the pyramid of frame %d is no longer resident (only the last wave of %d frames is; see HT_WAVE)",
-                     frame, ctx->wave_frames);
+                     frame, ctx->last_wave_n);
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));
   // the arena is frame-quad-interleaved: one word per pixel, byte f = frame within its quad

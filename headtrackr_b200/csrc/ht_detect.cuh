@@ -387,6 +387,47 @@ __device__ __forceinline__ unsigned lds_u8_if(unsigned saddr, bool p, unsigned d
   return v;
 }
 
+// One feature record (LateFeat) for one window, evaluated by one lane: min(p points) > max(n points).
+__device__ __forceinline__ bool feat_fires(unsigned sA, unsigned sB, const uint4 a, const uint4 b) {
+  // off[0..9] = a.x lo, a.x hi, a.y lo, a.y hi, a.z lo (p) | a.z hi, a.w lo, a.w hi, b.x lo, b.x hi (n)
+  const unsigned o[10] = {a.x & 0xffffu, a.x >> 16, a.y & 0xffffu, a.y >> 16, a.z & 0xffffu,
+                          a.z >> 16, a.w & 0xffffu, a.w >> 16, b.x & 0xffffu, b.x >> 16};
+  unsigned vv[10];
+#pragma unroll
+  for (int s = 0; s < 10; ++s) {
+    const unsigned addr = ((o[s] & 0x8000u) ? sB : sA) + 4u * (o[s] & 0x7fffu);
+    vv[s] = lds_u8_if(addr, o[s] != 0xffffu, s < 5 ? 255u : 0u);   // unused slots: neutral element, no bank traffic
+  }
+  const unsigned pm = __vimin3_u32(__vimin3_u32(vv[0], vv[1], vv[2]), vv[3], vv[4]);
+  const unsigned nm = __vimax3_u32(__vimax3_u32(vv[5], vv[6], vv[7]), vv[8], vv[9]);
+  return pm > nm;
+}
+
+// The reference's ordered fp64 stage sum (src/ccv.js:186-221) for ONE window by a whole warp: the 32 lanes evaluate
+// 32 features at a time (feature records in ORIGINAL order), the fire bits are collected with a ballot, and every
+// lane then performs the same sequential chain of fp64 adds in feature order (uniform alpha reads).  Round 2's
+// first version ran stage_sum_ordered on every lane: 14 k instructions of dependent loads per detection, the
+// straggler that set the duration of every CTA with a face in it.
+__device__ __forceinline__ double stage_sum_ordered_warp(unsigned sA, unsigned sB, int j, const LateFeat *__restrict__ feat_orig,
+                                                         int lane) {
+  const int first = c_casc.stage[j].first, count = c_casc.stage[j].count;
+  double sum = 0.0;
+  for (int base = 0; base < count; base += 32) {
+    bool fired = false;
+    if (base + lane < count) {
+      const uint4 *fp = reinterpret_cast<const uint4 *>(feat_orig + first + base + lane);
+      fired = feat_fires(sA, sB, __ldg(fp), __ldg(fp + 1));
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, fired);
+    const int n = min(32, count - base);
+    for (int i = 0; i < n; ++i) {
+      const double a = c_casc.alpha[first + base + i];
+      sum += ((mask >> i) & 1u) ? a : -a;   // src/ccv.js:194,219 (alpha[2k] == -alpha[2k+1], checked on the host)
+    }
+  }
+  return sum;
+}
+
 __device__ __forceinline__ void cp_async4(unsigned saddr, const void *g, bool valid) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(valid ? 4u : 0u) : "memory");
 }
@@ -396,6 +437,7 @@ __device__ __forceinline__ void cp_async4(unsigned saddr, const void *g, bool va
 // stage_pass_ordered, so results must not change (tests/test_gpu_fallbacks.py).
 template <bool FAST>
 __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
+                                                                const LateFeat *__restrict__ feat_orig,
                                                                 const int32_t *__restrict__ late_chunk0,
                                                                 const void *__restrict__ tmaps, int tma_quad0,
                                                                 const uint32_t *__restrict__ arena, size_t quad_stride,
@@ -404,7 +446,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
                                                                 uint32_t *__restrict__ raw_count, int raw_cap,
                                                                 int force_ties, const uint8_t *__restrict__ quad_mask) {
   if (quad_frames(blockIdx.y, n_frames, quad_mask) == 0u) return;   // uniform over the CTA
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(128) uint32_t smem[];   // (the TMA destination inside it needs 128-byte alignment)
   uint32_t *tile = smem;                                                   // TILE_WORDS
   uint16_t *cl0 = reinterpret_cast<uint16_t *>(smem + TILE_WORDS);         // [CLASS_CAP][32] survivor lists (ping)
   uint16_t *cl1 = cl0 + NWIN;                                              // (pong)
@@ -445,36 +487,68 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
     }
   }
   {
-    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
-    {  // level 0: parity-split columns
+    // 16-byte global loads (4 consecutive pixels x 4 frames), the layout permutation in the shared-memory stores;
+    // words outside a plane are zero.  Plane pitches and all tile origins are multiples of 4 words.
+    {  // level 0, columns split by parity: X, X+2 -> even half (one 8 B store), X+1, X+3 -> odd half
       const DevPlane pl = plan.planes[sc.p0];
       const uint32_t *src = qa + pl.off;
       const int X0 = 4 * x0, Y0 = 4 * y0;
-      for (int i = tid; i < L0_ROWS * P0; i += CASCADE_THREADS) {
-        const int r = i / P0, c = i - r * P0;
-        const int X = (c < H0) ? 2 * c : 2 * (c - H0) + 1;
-        const bool ok = (Y0 + r < pl.h) && (X0 + X < pl.pitch);
-        cp_async4(tile_s + 4u * (unsigned)i, ok ? src + (size_t)(Y0 + r) * pl.pitch + X0 + X : src, ok);
+      constexpr int G0 = (L0_COLS + 3) / 4;             // 38 groups per row (the last one half used)
+      for (int i0 = tid; i0 < L0_ROWS * G0; i0 += 4 * CASCADE_THREADS) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * CASCADE_THREADS, r = i / G0, X = (i - r * G0) * 4;
+          v[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (i < L0_ROWS * G0 && Y0 + r < pl.h && X0 + X < pl.pitch)
+            v[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(Y0 + r) * pl.pitch + X0 + X));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * CASCADE_THREADS, r = i / G0, X = (i - r * G0) * 4;
+          if (i >= L0_ROWS * G0) break;
+          uint32_t *row = tile + r * P0 + (X >> 1);
+          if (X + 2 < L0_COLS) *reinterpret_cast<uint2 *>(row) = make_uint2(v[k].x, v[k].z);   // even columns X, X+2
+          else row[0] = v[k].x;                            // last group of a row: X+2 is outside the tile
+          if (X + 1 < L0_COLS) row[H0] = v[k].y;           // odd columns X+1, X+3
+          if (X + 3 < L0_COLS) row[H0 + 1] = v[k].w;
+        }
       }
     }
-    if (!use_tma) {  // level 1
+    if (!use_tma) {  // level 1: a plain box, 16-byte cp.async
       const DevPlane pl = plan.planes[sc.p1];
       const uint32_t *src = qa + pl.off;
       const int X0 = 2 * x0, Y0 = 2 * y0;
-      for (int i = tid; i < L1_ROWS * P1; i += CASCADE_THREADS) {
-        const int r = i / P1, c = i - r * P1;
+      constexpr int G1 = P1 / 4;                          // 19 groups per row
+      for (int i = tid; i < L1_ROWS * G1; i += CASCADE_THREADS) {
+        const int r = i / G1, c = (i - r * G1) * 4;
         const bool ok = (Y0 + r < pl.h) && (X0 + c < pl.pitch);
-        cp_async4(tile_s + 4u * (unsigned)(W1 + i), ok ? src + (size_t)(Y0 + r) * pl.pitch + X0 + c : src, ok);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + W1 + r * P1 + c);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src + (size_t)(Y0 + r) * pl.pitch + X0 + c : src),
+                     "r"(ok ? 16u : 0u) : "memory");
       }
     }
-    {  // level 2: the four phase copies interleaved (row 2Y+dy, column 2X+dx)
-      for (int i = tid; i < 2 * L2_ROWS * P2; i += CASCADE_THREADS) {
-        const int rr = i / P2, cc = i - rr * P2;
-        const int q = (cc & 1) | ((rr & 1) << 1), r = rr >> 1, c = cc >> 1;
-        const DevPlane pl = plan.planes[plan.scales[tl.scale].p2[q]];  // (indexing the register copy `sc` would spill it)
-        const uint32_t *src = qa + pl.off;
-        const bool ok = (y0 + r < pl.h) && (x0 + c < pl.pitch);
-        cp_async4(tile_s + 4u * (unsigned)(W2 + i), ok ? src + (size_t)(y0 + r) * pl.pitch + x0 + c : src, ok);
+    {  // level 2: the four phase copies interleaved (row 2Y+dy, column 2X+dx): the dx = 0 / 1 copies of one dy are
+       // loaded together and written as two 16-byte stores of 8 consecutive words
+      constexpr int G2 = (L2_COLS + 3) / 4;               // 10 groups per row
+      for (int i = tid; i < 2 * L2_ROWS * G2; i += CASCADE_THREADS) {
+        const int dy = i / (L2_ROWS * G2), rem = i - dy * (L2_ROWS * G2), r = rem / G2, c = (rem - r * G2) * 4;
+        uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+        {
+          const DevPlane pl = plan.planes[plan.scales[tl.scale].p2[2 * dy]];      // (indexing the register copy `sc` would spill it)
+          if (y0 + r < pl.h && x0 + c < pl.pitch) v0 = __ldg(reinterpret_cast<const uint4 *>(qa + pl.off + (size_t)(y0 + r) * pl.pitch + x0 + c));
+        }
+        {
+          const DevPlane pl = plan.planes[plan.scales[tl.scale].p2[2 * dy + 1]];
+          if (y0 + r < pl.h && x0 + c < pl.pitch) v1 = __ldg(reinterpret_cast<const uint4 *>(qa + pl.off + (size_t)(y0 + r) * pl.pitch + x0 + c));
+        }
+        uint32_t *row = tile + W2 + (2 * r + dy) * P2 + 2 * c;
+        if (2 * c + 8 <= P2) {
+          *reinterpret_cast<uint4 *>(row) = make_uint4(v0.x, v1.x, v0.y, v1.y);
+          *reinterpret_cast<uint4 *>(row + 4) = make_uint4(v0.z, v1.z, v0.w, v1.w);
+        } else {                                          // last group of a row: P2 = 76 = 9 * 8 + 4
+          *reinterpret_cast<uint4 *>(row) = make_uint4(v0.x, v1.x, v0.y, v1.y);
+        }
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -658,28 +732,18 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
         for (int ch = c0; ch < c1; ++ch) {
           const uint4 *fp = reinterpret_cast<const uint4 *>(late + (size_t)ch * 32 + lane);
           const uint4 a = __ldg(fp), b = __ldg(fp + 1);
-          // off[0..9] = a.x lo, a.x hi, a.y lo, a.y hi, a.z lo (p) | a.z hi, a.w lo, a.w hi, b.x lo, b.x hi (n); b.y = alpha_int
-          const unsigned o[10] = {a.x & 0xffffu, a.x >> 16, a.y & 0xffffu, a.y >> 16, a.z & 0xffffu,
-                                  a.z >> 16, a.w & 0xffffu, a.w >> 16, b.x & 0xffffu, b.x >> 16};
-          unsigned vv[10];
-#pragma unroll
-          for (int s = 0; s < 10; ++s) {
-            const unsigned addr = ((o[s] & 0x8000u) ? sB : sA) + 4u * (o[s] & 0x7fffu);
-            vv[s] = lds_u8_if(addr, o[s] != 0xffffu, s < 5 ? 255u : 0u);   // unused slots: neutral element, no bank traffic
-          }
-          const unsigned pm = __vimin3_u32(__vimin3_u32(vv[0], vv[1], vv[2]), vv[3], vv[4]);
-          const unsigned nm = __vimax3_u32(__vimax3_u32(vv[5], vv[6], vv[7]), vv[8], vv[9]);
-          const int ai = (int)b.y;
-          acc += (pm > nm) ? (long long)ai : -(long long)ai;
+          const int ai = (int)b.y;                       // alpha_int (0 for padding records)
+          acc += feat_fires(sA, sB, a, b) ? (long long)ai : -(long long)ai;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         const long long thr = c_casc.thr_int[j];
-        if (acc == thr || (force_ties & 2)) pass = stage_pass_ordered(tA, tB, j);   // exact tie: the reference's ordered adds
+        if (acc == thr || (force_ties & 2))             // exact tie: the reference's ordered adds decide
+          pass = !(stage_sum_ordered_warp(sA, sB, j, feat_orig, lane) < c_casc.stage[j].threshold);
         else pass = acc > thr;
       }
       if (pass) {  // confidence = ordered fp64 sum of the last stage
-        const double s = stage_sum_ordered(tA, tB, c_casc.n_stages - 1);
+        const double s = stage_sum_ordered_warp(sA, sB, c_casc.n_stages - 1, feat_orig, lane);
         if (lane == 0) emit(e, s);
       }
     }

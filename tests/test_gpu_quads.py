@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 def tup(d):
-    return (d["x"], d["y"], d["width"], d["height"], d["confidence"], d["neighbors"])
+    return (d["x"], d["y"], d["width"], d["height"], d["confidence"], d.get("neighbors", d.get("neighbor")))
 
 
 def test_partial_quads_and_planes(ctx, blob):
