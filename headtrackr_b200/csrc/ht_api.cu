@@ -493,7 +493,8 @@ struct ht_ctx {
   // measured slower (24.4-26.7 vs 22.3 ms per step) and stays off.  HT_OVERLAP=0 disables, HT_OVERLAP=<parts> forces.
   int detect_pipe = 0;                      // HT_DETECT_PIPE=1: gray + pyramid of wave w+1 on a second stream under the cascade of wave w
   int wave_frames = 0;                      // frames per wave of run_detect (HT_WAVE); 0: from wave_mb
-  int wave_mb = 64;                         // pyramid-arena budget of one wave in MB (HT_WAVE_MB): half of the 126 MB L2
+  int wave_mb = 2048;                       // pyramid-arena budget of one wave in MB (HT_WAVE_MB).  64 (half of the L2) keeps
+                                            // the pyramid out of HBM but costs 28 % throughput in launch tails: lab notes
   int force_ties = 0;                       // ht_debug_set_exactness: force the exactness fallbacks (tests)
   cudaStream_t pipe_stream = nullptr;
   cudaEvent_t pipe_start = nullptr, pipe_events[4] = {};
@@ -524,6 +525,9 @@ struct ht_ctx {
   DevBuf d_track_cost;                      // [max_frames][2] {passes, window pixels / 256} per slot
   int track_heavy_div = 64;                 // >0: the n/div costliest streams run on a cluster of
   int track_heavy_cluster = 8;              //     track_heavy_cluster CTAs on sched_stream (HT_TRACK_HEAVY=div[,cluster])
+  int track_mid_div = 0, track_mid_cluster = 4;   // HT_TRACK_MID=div[,cluster]
+  cudaStream_t sched_stream2 = nullptr;
+  cudaEvent_t sched_done2 = nullptr;
   cudaStream_t sched_stream = nullptr;
   cudaEvent_t sched_ready = nullptr, sched_done = nullptr;
   int track_bail_area = 0;                  // >0: two-phase k_track; phase A hands streams with a larger window (px) to phase B
@@ -746,12 +750,26 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
         CK(cudaEventRecord(ctx->sched_done, ctx->sched_stream));
         ++ctx->launches;
       }
-      if (e == cudaSuccess && n > n_heavy) {
-        e = launch_track_any(c, nt, st, n - n_heavy, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
-                             calls_done, bail_list, bail_count, 2, n_heavy, opt);
+      // optional middle tier (HT_TRACK_MID=div[,cluster]): the next n / div streams on clusters of 4 on a third stream
+      int n_mid = (ctx->track_mid_div > 0 && n_heavy > 0) ? std::min(n - n_heavy, n / ctx->track_mid_div) : 0;
+      if (e == cudaSuccess && n_mid > 0) {
+        if (!ctx->sched_stream2) {
+          CK(cudaStreamCreateWithFlags(&ctx->sched_stream2, cudaStreamNonBlocking));
+          CK(cudaEventCreateWithFlags(&ctx->sched_done2, cudaEventDisableTiming));
+        }
+        CK(cudaStreamWaitEvent(ctx->sched_stream2, ctx->sched_ready, 0));
+        e = launch_track_any(ctx->track_mid_cluster, 256, ctx->sched_stream2, n_mid, bins, w, h, d_slots, mh, ch, state,
+                             n_calls, d_objs, d_win, flag, stats, calls_done, bail_list, bail_count, 2, n_heavy, opt);
+        CK(cudaEventRecord(ctx->sched_done2, ctx->sched_stream2));
+        ++ctx->launches;
+      }
+      if (e == cudaSuccess && n > n_heavy + n_mid) {
+        e = launch_track_any(c, nt, st, n - n_heavy - n_mid, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
+                             calls_done, bail_list, bail_count, 2, n_heavy + n_mid, opt);
         ++ctx->launches;
       }
       if (n_heavy > 0) CK(cudaStreamWaitEvent(st, ctx->sched_done, 0));
+      if (n_mid > 0) CK(cudaStreamWaitEvent(st, ctx->sched_done2, 0));
     }
   }
   if (e != cudaSuccess) return ctx->fail(HT_ERR_CUDA, "k_track launch: %s", cudaGetErrorString(e));
@@ -778,8 +796,8 @@ int track_init_common(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *d
   return HT_OK;
 }
 
-// Shared memory of one k_cascade CTA: the staged tile, two survivor-list buffers, the list lengths of every phase.
-constexpr size_t CASC_SMEM = (size_t)TILE_WORDS * 4 + 2 * (size_t)NWIN * sizeof(uint16_t) + (size_t)(MAX_GROUPS + 2) * 32 * sizeof(int);
+// Shared memory of one k_cascade CTA: the staged tile and three sets of per-class survivor bit masks.
+constexpr size_t CASC_SMEM = (size_t)TILE_WORDS * 4 + 3 * (size_t)MASK_WORDS * 32 * sizeof(uint32_t);
 constexpr size_t GRAY_HIST_SMEM = 4 * 4096 * sizeof(uint32_t);
 
 int set_kernel_attributes(ht_ctx *ctx) {
@@ -1078,6 +1096,13 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
       if (hc == 1 || hc == 2 || hc == 4 || hc == 8) c->track_heavy_cluster = hc;
     }
   }
+  if (const char *tmid = getenv("HT_TRACK_MID")) {
+    c->track_mid_div = std::max(0, atoi(tmid));
+    if (const char *comma = strchr(tmid, ',')) {
+      const int mc = atoi(comma + 1);
+      if (mc == 2 || mc == 4 || mc == 8) c->track_mid_cluster = mc;
+    }
+  }
   if (const char *wv = getenv("HT_WAVE")) c->wave_frames = std::max(4, atoi(wv));
   if (const char *wm = getenv("HT_WAVE_MB")) c->wave_mb = std::max(1, atoi(wm));
   if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
@@ -1129,6 +1154,8 @@ void ht_destroy(ht_ctx *ctx) {
   if (ctx->pipe_start) cudaEventDestroy(ctx->pipe_start);
   for (cudaEvent_t e : ctx->pipe_events) if (e) cudaEventDestroy(e);
   if (ctx->sched_stream) cudaStreamDestroy(ctx->sched_stream);
+  if (ctx->sched_stream2) cudaStreamDestroy(ctx->sched_stream2);
+  if (ctx->sched_done2) cudaEventDestroy(ctx->sched_done2);
   if (ctx->sched_ready) cudaEventDestroy(ctx->sched_ready);
   if (ctx->sched_done) cudaEventDestroy(ctx->sched_done);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

@@ -34,33 +34,45 @@ namespace ht {
 // (src/ccv.js:179-180,235-241).  2*P0 == P1 == P2 (mod 32), so bank(baseA) == bank(baseB) == (u + 12 v) & 31: the
 // "bank class" of the window.  Lane L only ever evaluates class-L windows -> conflict-free loads in every stage.
 constexpr int TW = 32;
-constexpr int TH = 16;
+#ifndef HT_TILE_TH
+#define HT_TILE_TH 8
+#endif
+constexpr int TH = HT_TILE_TH;                // quarter-res rows of a tile (8: four CTAs per SM, 16: two)
+constexpr int NV = 2 * TH;                    // v values of a tile
 constexpr int L0_COLS = 4 * TW + 22;          // 150 level-0 columns
-constexpr int L0_ROWS = 4 * TH + 22;          // 86
+constexpr int L0_ROWS = 4 * TH + 22;
 constexpr int H0 = L0_COLS / 2;               // 75: word offset of the odd-column half of a level-0 row
 constexpr int P0 = L0_COLS;                   // 150 words per level-0 row
-constexpr int L1_ROWS = 2 * TH + 11;          // 43
+constexpr int L1_ROWS = 2 * TH + 11;
 constexpr int L1_COLS = 2 * TW + 11;          // 75
 constexpr int P1 = 76;
-constexpr int L2_ROWS = TH + 5;               // 21 per copy
+constexpr int L2_ROWS = TH + 5;               // per copy
 constexpr int L2_COLS = TW + 5;               // 37 per copy
 constexpr int P2 = 76;
-constexpr int W1 = (L0_ROWS * P0 + 31) / 32 * 32;   // 12928: 128-byte aligned, the level-1 box can be written by TMA
-constexpr int W2 = W1 + L1_ROWS * P1;         // 16196
-constexpr int TILE_WORDS = W2 + 2 * L2_ROWS * P2;   // 19388 words = 77,552 B
+constexpr int W1 = (L0_ROWS * P0 + 31) / 32 * 32;   // 128-byte aligned: the level-1 box can be written by TMA
+constexpr int W2 = W1 + L1_ROWS * P1;
+constexpr int TILE_WORDS = W2 + 2 * L2_ROWS * P2;
 static_assert((2 * P0 - P1) % 32 == 0 && P1 == P2, "bank classes of the two bases must coincide");
 static_assert(2 * L2_COLS <= P2 && L1_COLS <= P1, "tile pitches");
-constexpr int NQUADWIN = TW * TH * 4;         // window positions per tile (each x 4 frames)
-constexpr int NWIN = NQUADWIN * 4;            // windows per tile
-constexpr int CLASS_CAP = NWIN / 32;          // 256: windows of one bank class in a tile
-constexpr int CASCADE_THREADS = 512;
+constexpr int BANK_K = (2 * P0) % 32;         // bank(baseA) = bank(baseB) = (u + BANK_K * v) & 31
+static_assert(P1 % 32 == BANK_K, "bank_class");
+constexpr int NWIN = TW * TH * 4 * 4;         // windows per tile (4 phases x 4 frames)
+// Survivors are kept as BIT MASKS per bank class: class c owns, for every v, the two windows u = ((c - BANK_K v) & 31)
+// + 32 uh, each in 4 frames -> bit 8 v + 4 uh + f of the class's mask (NV / 4 words).  masks[word][class].
+constexpr int MASK_WORDS = NV / 4;
+static_assert(NV % 4 == 0, "TH must be even");
+#ifndef HT_CASC_THREADS
+#define HT_CASC_THREADS 256
+#endif
+constexpr int CASCADE_THREADS = HT_CASC_THREADS;
 constexpr int CASCADE_WARPS = CASCADE_THREADS / 32;
 // shared-memory WORD offset of point (z, x, y) of the 24x24 window relative to baseA (z == 0) or baseB (z > 0)
 __host__ __device__ constexpr int point_word(int z, int x, int y) {
   return z == 0 ? y * P0 + (x & 1) * H0 + (x >> 1) : z == 1 ? W1 + y * P1 + x : W2 + 2 * y * P2 + 2 * x;
 }
-__host__ __device__ constexpr int bank_class(int u, int v) { return (u + 12 * v) & 31; }
-static_assert((2 * P0) % 32 == 12 && P1 % 32 == 12, "bank_class assumes v * 12");
+__host__ __device__ constexpr int bank_class(int u, int v) { return (u + BANK_K * v) & 31; }
+// the window of class c at (v, uh)
+__host__ __device__ constexpr int class_u(int c, int v, int uh) { return ((c - BANK_K * v) & 31) + 32 * uh; }
 
 constexpr int MAX_STAGES = 64;
 constexpr int MAX_GROUPS = 16;

@@ -35,9 +35,10 @@ __host__ __device__ __forceinline__ uint32_t rgb_bin(uint32_t px) {  // src/cams
 __host__ __device__ __forceinline__ uint32_t gray_of(uint32_t px) {
 #ifdef __CUDA_ARCH__
   const double M = 4503599627370496.0;   // 2^52
-  const double r = __dsub_rn(__hiloint2double(0x43300000, (int)(px & 0xffu)), M);
-  const double g = __dsub_rn(__hiloint2double(0x43300000, (int)((px >> 8) & 0xffu)), M);
-  const double b = __dsub_rn(__hiloint2double(0x43300000, (int)((px >> 16) & 0xffu)), M);
+  // one PRMT per channel: the byte, zero-extended, is the low mantissa word of 2^52 + byte
+  const double r = __dsub_rn(__hiloint2double(0x43300000, (int)__byte_perm(px, 0u, 0x4440)), M);
+  const double g = __dsub_rn(__hiloint2double(0x43300000, (int)__byte_perm(px, 0u, 0x4441)), M);
+  const double b = __dsub_rn(__hiloint2double(0x43300000, (int)__byte_perm(px, 0u, 0x4442)), M);
   const double v = __dadd_rn(__dadd_rn(__dmul_rn(r, 0.3), __dmul_rn(g, 0.59)), __dmul_rn(b, 0.11));
   const uint32_t iv = (uint32_t)__double2loint(__dadd_rn(v, M));   // round half to even == Uint8ClampedArray store
   return min(iv, 255u);
@@ -94,11 +95,18 @@ __host__ __device__ __forceinline__ void gray_item(const uint8_t *__restrict__ r
       }
     }
   }
+  // VEC implies w % 4 == 0: a group is entirely inside the frame or entirely in the pad columns - no per-pixel tests
+  const bool grp_in = col < w;
   uint32_t out[4];
+  if (VEC && grp_in && fmask == 15u) {   // the common case, branch-free: a full quad, a group inside the frame
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      out[i] = gray_of(px[0][i]) | (gray_of(px[1][i]) << 8) | (gray_of(px[2][i]) << 16) | (gray_of(px[3][i]) << 24);
+  } else
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     out[i] = 0;
-    if (col + i < w) {            // pad columns and missing frames are written as 0
+    if (VEC ? grp_in : (col + i < w)) {            // pad columns and missing frames are written as 0
 #pragma unroll
       for (int f = 0; f < 4; ++f)
         if ((fmask >> f) & 1u) out[i] |= gray_of(px[f][i]) << (8 * f);
@@ -114,7 +122,7 @@ __host__ __device__ __forceinline__ void gray_item(const uint8_t *__restrict__ r
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         b[i] = rgb_bin(px[f][i]);
-        if (col + i < w) atomicAdd(&sh_hist[f * 4096 + b[i]], 1u);
+        if (VEC || col + i < w) atomicAdd(&sh_hist[f * 4096 + b[i]], 1u);   // (col < w was tested above)
       }
       if (bins) {
         uint16_t *bo = bins + (size_t)(4 * quad + f) * n_px + (size_t)row * w + col;
@@ -225,14 +233,15 @@ __host__ __device__ __forceinline__ void resample_thread(const DevPlan &plan, in
     if (Y >= dst_h) break;
     uint32_t out = 0;
     if (col_ok && Y < dh) {                                  // unpainted columns / rows and the pitch padding are 0
+      // the four corner weights are shared by the 4 frames of the word: 4 multiply-adds per frame instead of 6
       const uint32_t wy0 = Dy - wy1[r];
+      const uint32_t w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1[r], w11 = wx1 * wy1[r];   // sum = 4 dw dh
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
         const uint32_t a = (p[r][0] >> (8 * f)) & 0xffu, b = (p[r][1] >> (8 * f)) & 0xffu;
         const uint32_t c = (p[r][2] >> (8 * f)) & 0xffu, d = (p[r][3] >> (8 * f)) & 0xffu;
-        const uint32_t top = wx0 * a + wx1 * b;              // <= 255 * 2dw
-        const uint32_t bot = wx0 * c + wx1 * d;
-        const uint32_t num = top * wy0 + bot * wy1[r] + half;  // <= 255.5 * 4 dw dh  < 2^32 (checked by the planner)
+        // == (wx0 a + wx1 b) wy0 + (wx0 c + wx1 d) wy1 + half  <= 255.5 * 4 dw dh < 2^32 (checked by the planner)
+        const uint32_t num = w00 * a + w01 * b + w10 * c + w11 * d + half;
         out |= (uint32_t)(((uint64_t)num * magic) >> shift) << (8 * f);
       }
     }
@@ -311,6 +320,7 @@ __host__ __device__ __forceinline__ uint32_t frames13(uint32_t w) {   // frames 
 #endif
 }
 #define HT_GEN_FN __host__ __device__ __forceinline__
+#define HT_PW(z, x, y) point_word(z, x, y)
 #define HT_MIN2(a, b) min3_u32(a, b, b)
 #define HT_MIN3(a, b, c) min3_u32(a, b, c)
 #define HT_MAX2(a, b) max3_u32(a, b, b)
@@ -342,6 +352,7 @@ __host__ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32
 #define HT_QUAD_STAGES 2   // stages the dense group evaluates in quad form (2: {0,1}; 3: {0,1,2})
 #endif
 #undef HT_GEN_FN
+#undef HT_PW
 #undef HT_MIN2
 #undef HT_MIN3
 #undef HT_MAX2
@@ -433,10 +444,25 @@ __device__ __forceinline__ void cp_async4(unsigned saddr, const void *g, bool va
 }
 
 // Debug switches of the exactness fallbacks (ht_debug_set_exactness): bit 0 = treat every generated byte-stage
-// decision as a tie, bit 1 = treat every late-stage integer decision as a tie.  Ties are decided by
-// stage_pass_ordered, so results must not change (tests/test_gpu_fallbacks.py).
+// decision as a tie, bit 1 = treat every late-stage integer decision as a tie.  Ties are decided by the reference's
+// ordered fp64 adds, so results must not change (tests/test_gpu_quads.py).
+#ifndef HT_CASC_MINB
+#define HT_CASC_MINB (TH <= 8 ? 4 : (TH <= 12 ? 3 : 2))
+#endif
+// r-th (0-based) set bit of the MASK_WORDS-word mask of class c, or -1.  All reads are shared-memory loads.
+__device__ __forceinline__ int nth_set_bit(const uint32_t *__restrict__ masks, int c, int r) {
+#pragma unroll
+  for (int j = 0; j < MASK_WORDS; ++j) {
+    const uint32_t w = masks[j * 32 + c];
+    const int pc = __popc(w);
+    if (r < pc) return j * 32 + (int)__fns(w, 0u, r + 1);
+    r -= pc;
+  }
+  return -1;
+}
+
 template <bool FAST>
-__global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
+__global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPlan plan, const LateFeat *__restrict__ late,
                                                                 const LateFeat *__restrict__ feat_orig,
                                                                 const int32_t *__restrict__ late_chunk0,
                                                                 const void *__restrict__ tmaps, int tma_quad0,
@@ -447,10 +473,8 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
                                                                 int force_ties, const uint8_t *__restrict__ quad_mask) {
   if (quad_frames(blockIdx.y, n_frames, quad_mask) == 0u) return;   // uniform over the CTA
   extern __shared__ __align__(128) uint32_t smem[];   // (the TMA destination inside it needs 128-byte alignment)
-  uint32_t *tile = smem;                                                   // TILE_WORDS
-  uint16_t *cl0 = reinterpret_cast<uint16_t *>(smem + TILE_WORDS);         // [CLASS_CAP][32] survivor lists (ping)
-  uint16_t *cl1 = cl0 + NWIN;                                              // (pong)
-  int *cnt = reinterpret_cast<int *>(cl1 + NWIN);                          // [MAX_GROUPS + 2][32] list lengths per phase
+  uint32_t *tile = smem;                                // TILE_WORDS
+  uint32_t *masks = smem + TILE_WORDS;                  // [3][MASK_WORDS][32] survivor bit masks (in / out / being cleared)
   __shared__ __align__(8) unsigned long long tma_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -461,13 +485,12 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
   const int x0 = tl.tx * TW, y0 = tl.ty * TH;  // quarter-res origin of the tile
   const unsigned fmask = quad_frames(quad, n_frames, quad_mask);
 
-  for (int i = tid; i < (MAX_GROUPS + 2) * 32; i += CASCADE_THREADS) cnt[i] = 0;
+  for (int i = tid; i < 3 * MASK_WORDS * 32; i += CASCADE_THREADS) masks[i] = 0u;
 
-  // ---- stage the three levels in shared memory (layout in ht_common.cuh): 4-byte cp.async with the layout
-  //      permutation in the destination address; words outside a plane are zero-filled ----
-  // Level 1 is a plain 2-D box of its plane (L1_ROWS x P1 words = 13 KB): when tensor maps are given it is staged
-  // by the TMA engine - one elected thread issues cp.async.bulk.tensor (3-D map: column, row, frame quad; elements
-  // outside the plane are zero-filled) completing on an mbarrier - while all threads scatter levels 0 and 2.
+  // ---- stage the three levels in shared memory (layout in ht_common.cuh) ----
+  // Level 1 is a plain 2-D box of its plane (L1_ROWS x P1 words): when tensor maps are given it is staged by the
+  // TMA engine - one elected thread issues cp.async.bulk.tensor (3-D map: column, row, frame quad; elements outside
+  // the plane are zero-filled) completing on an mbarrier - while all threads scatter levels 0 and 2.
   const bool use_tma = tmaps != nullptr;
   if (use_tma) {
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
@@ -543,12 +566,8 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
           if (y0 + r < pl.h && x0 + c < pl.pitch) v1 = __ldg(reinterpret_cast<const uint4 *>(qa + pl.off + (size_t)(y0 + r) * pl.pitch + x0 + c));
         }
         uint32_t *row = tile + W2 + (2 * r + dy) * P2 + 2 * c;
-        if (2 * c + 8 <= P2) {
-          *reinterpret_cast<uint4 *>(row) = make_uint4(v0.x, v1.x, v0.y, v1.y);
-          *reinterpret_cast<uint4 *>(row + 4) = make_uint4(v0.z, v1.z, v0.w, v1.w);
-        } else {                                          // last group of a row: P2 = 76 = 9 * 8 + 4
-          *reinterpret_cast<uint4 *>(row) = make_uint4(v0.x, v1.x, v0.y, v1.y);
-        }
+        *reinterpret_cast<uint4 *>(row) = make_uint4(v0.x, v1.x, v0.y, v1.y);
+        if (2 * c + 8 <= P2) *reinterpret_cast<uint4 *>(row + 4) = make_uint4(v0.z, v1.z, v0.w, v1.w);   // (P2 = 76 = 9 * 8 + 4)
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -564,11 +583,12 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
   }
   __syncthreads();
 
-  // A window of the tile is (u, v, f): u = 2 lx + dx, v = 2 ly + dy, f = frame in the quad; list entries are
-  // f << 11 | v << 6 | u.  cl[e * 32 + c] is entry e of bank class c; lane L evaluates class L.
+  // A window of the tile is (class c, bit b): b = 8 v + 4 uh + f, u = class_u(c, v, uh), f = frame in the quad.
+  // Lane L evaluates class L in EVERY phase: base words of a warp's 32 windows are consecutive modulo 32 -> every
+  // load, quad or byte, is bank-conflict free.
   const uint8_t *tile_b = reinterpret_cast<const uint8_t *>(tile);
-  auto emit = [&](int e, double sum) {  // src/ccv.js:227-234: (window id in reference order, last stage sum)
-    const int u = e & 63, v = (e >> 6) & 31, f = e >> 11;
+  auto emit = [&](int c, int b, double sum) {  // src/ccv.js:227-234: (window id in reference order, last stage sum)
+    const int v = b >> 3, uh = (b >> 2) & 1, f = b & 3, u = class_u(c, v, uh);
     const int lx = u >> 1, ly = v >> 1, q = (u & 1) | ((v & 1) << 1);
     const uint32_t key = sc.win_base + (uint32_t)((q * sc.qh + (y0 + ly)) * sc.qw + (x0 + lx));
     const int frame = 4 * quad + f;
@@ -578,31 +598,36 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
       raw_conf[(size_t)frame * raw_cap + pos] = sum;
     }
   };
-  auto bases = [&](int e, const uint8_t *&tA, const uint8_t *&tB) {
-    const int u = e & 63, v = (e >> 6) & 31, f = e >> 11;
+  auto bases = [&](int c, int b, const uint8_t *&tA, const uint8_t *&tB) {
+    const int v = b >> 3, uh = (b >> 2) & 1, f = b & 3, u = class_u(c, v, uh);
     tA = tile_b + 4 * (v * (2 * P0) + u) + f;
     tB = tile_b + 4 * (v * P1 + u) + f;
   };
   const int late_first = c_casc.group_first[c_casc.n_groups];
   const bool has_late = late_first < c_casc.n_stages;
-  int phase = 0;   // cnt[phase] = lengths of the lists the next group reads
-  uint16_t *cl_in = cl0, *cl_out = cl1;
+  uint32_t *m_in = masks, *m_out = masks + MASK_WORDS * 32, *m_clr = masks + 2 * MASK_WORDS * 32;
   int g = 0;
 
-  // ---- dense group: every window of the tile ----
-  if (FAST) {
-    // quad form (cascade_face_gen.inc): warp iteration = one v and 32 consecutive u, lane = u & 31, 4 frames per lane
+  // ---- dense group: every window of the tile.  A warp takes chunks of 4 (v, uh) units = 16 mask bits per lane ----
+  {
     constexpr int NQ = HT_QUAD_STAGES < HT_GEN_QUAD_STAGES ? HT_QUAD_STAGES : HT_GEN_QUAD_STAGES;
     static_assert(NQ == 2 || NQ == 3, "the dense group is {0,1} or {0,1,2}");
-    for (int it = warp; it < 4 * TH; it += CASCADE_WARPS) {
-      const int v = it >> 1, u = ((it & 1) << 5) | lane;
-      const int lx = u >> 1, ly = v >> 1;
-      const uint32_t *tA = tile + v * (2 * P0) + u, *tB = tile + v * P1 + u;
-      uint32_t a_lo = 0, a_hi = 0;   // alive bits: frame 0 -> lo bit 15, 2 -> lo bit 31, 1 -> hi bit 15, 3 -> hi bit 31
-      if (x0 + lx < sc.qw && y0 + ly < sc.qh) {
-        a_lo = ((fmask & 1u) ? 0x8000u : 0u) | ((fmask & 4u) ? 0x80000000u : 0u);
-        a_hi = ((fmask & 2u) ? 0x8000u : 0u) | ((fmask & 8u) ? 0x80000000u : 0u);
-      }
+    uint16_t *m16 = reinterpret_cast<uint16_t *>(m_in);
+    for (int chunk = warp; chunk < NV / 2; chunk += CASCADE_WARPS) {
+      uint32_t bits = 0;
+#pragma unroll 1
+      for (int unit = 0; unit < 4; ++unit) {
+        const int v = 2 * chunk + (unit >> 1), uh = unit & 1, u = class_u(lane, v, uh);
+        const int lx = u >> 1, ly = v >> 1;
+        uint32_t m = 0;
+        if (FAST) {
+          // quad form (cascade_face_gen.inc): 4 frames per lane
+          const uint32_t *tA = tile + v * (2 * P0) + u, *tB = tile + v * P1 + u;
+          uint32_t a_lo = 0, a_hi = 0;   // alive bits: frame 0 -> lo bit 15, 2 -> lo bit 31, 1 -> hi bit 15, 3 -> hi bit 31
+          if (x0 + lx < sc.qw && y0 + ly < sc.qh) {
+            a_lo = ((fmask & 1u) ? 0x8000u : 0u) | ((fmask & 4u) ? 0x80000000u : 0u);
+            a_hi = ((fmask & 2u) ? 0x8000u : 0u) | ((fmask & 8u) ? 0x80000000u : 0u);
+          }
 #define HT_QSTAGE(J)                                                                                        \
   if (NQ > J && __any_sync(0xffffffffu, (a_lo | a_hi) != 0u)) {                                              \
     uint32_t p_lo, p_hi, t_lo, t_hi;                                                                         \
@@ -620,71 +645,74 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
     }                                                                                                        \
     a_lo &= p_lo; a_hi &= p_hi;                                                                              \
   }
-      HT_QSTAGE(0)
-      HT_QSTAGE(1)
+          HT_QSTAGE(0)
+          HT_QSTAGE(1)
 #if HT_GEN_QUAD_STAGES >= 3
-      HT_QSTAGE(2)
+          HT_QSTAGE(2)
 #endif
 #undef HT_QSTAGE
-      const uint32_t m = ((a_lo >> 15) & 1u) | ((a_hi >> 14) & 2u) | ((a_lo >> 29) & 4u) | ((a_hi >> 28) & 8u);
-      if (m) {
-        const int c = bank_class(u, v);
-        int pos = atomicAdd(&cnt[c], __popc(m));
-        const int e0 = (v << 6) | u;
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-          if (m & (1u << f)) cl_in[(pos++) * 32 + c] = (uint16_t)(e0 | (f << 11));
+          m = ((a_lo >> 15) & 1u) | ((a_hi >> 14) & 2u) | ((a_lo >> 29) & 4u) | ((a_hi >> 28) & 8u);
+        } else {
+          // table-driven: ordered fp64 sums, one frame at a time
+          for (int f = 0; f < 4; ++f) {
+            bool alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh) && ((fmask >> f) & 1u);
+            const uint8_t *tA = tile_b + 4 * (v * (2 * P0) + u) + f, *tB = tile_b + 4 * (v * P1 + u) + f;
+            for (int j = c_casc.group_first[0]; j < c_casc.group_first[1]; ++j) {
+              if (!__any_sync(0xffffffffu, alive)) break;
+              alive = alive && stage_pass_ordered(tA, tB, j);
+            }
+            m |= (alive ? 1u : 0u) << f;
+          }
+        }
+        bits |= m << (4 * unit);      // bit (8 v + 4 uh + f) & 15 of this half word
       }
+      m16[(((chunk >> 1) * 32 + lane) << 1) | (chunk & 1)] = (uint16_t)bits;
     }
-    g = NQ >= 3 ? 2 : 1;    // generated groups are {0,1} {2} {3} {4,5} {6,7}
-  } else {
-    // table-driven: one window of one frame per lane, ordered fp64 sums
-    const int j0 = c_casc.group_first[0], j1 = c_casc.group_first[1];
-    for (int it = warp; it < 4 * TH * 4; it += CASCADE_WARPS) {
-      const int f = it & 3, v = (it >> 2) >> 1, u = (((it >> 2) & 1) << 5) | lane;
-      const int lx = u >> 1, ly = v >> 1;
-      bool alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh) && ((fmask >> f) & 1u);
-      const int e = (f << 11) | (v << 6) | u;
-      const uint8_t *tA, *tB;
-      bases(e, tA, tB);
-      double sum = 0.0;
-      for (int j = j0; j < j1; ++j) {
-        if (!__any_sync(0xffffffffu, alive)) break;
-        sum = stage_sum_ordered(tA, tB, j);
-        alive = alive && !(sum < c_casc.stage[j].threshold);
-      }
-      if (alive) {
-        if (c_casc.n_groups == 1 && !has_late) emit(e, sum);
-        else { const int c = bank_class(u, v); cl_in[atomicAdd(&cnt[c], 1) * 32 + c] = (uint16_t)e; }
-      }
-    }
-    if (c_casc.n_groups == 1 && !has_late) return;
-    g = 1;
+    g = FAST ? (NQ >= 3 ? 2 : 1) : 1;    // generated groups are {0,1} {2} {3} {4,5} {6,7}
   }
   __syncthreads();
 
-  // ---- survivor lists: lane L walks the entries of class L; survivors are appended to the other buffer ----
+  // ---- survivor masks: lane L walks the set bits of class L; warp w takes the entries of rank w, w + NW, ... ----
   for (; g < c_casc.n_groups; ++g) {
     const int jb = c_casc.group_first[g], je = c_casc.group_first[g + 1];
     const bool emit_here = (g == c_casc.n_groups - 1) && !has_late;
-    const int mylen = cnt[phase * 32 + lane];
-    int ml = mylen;
+    int n = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, o));
-    if (ml == 0) return;   // uniform over the CTA
-    for (int e_i = warp; e_i < ml; e_i += CASCADE_WARPS) {
-      bool alive = e_i < mylen;
-      const int e = alive ? cl_in[e_i * 32 + lane] : 0;
+    for (int j = 0; j < MASK_WORDS; ++j) n += __popc(m_in[j * 32 + lane]);
+    int maxn = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
+    if (maxn == 0) return;   // uniform over the CTA
+    for (int i = tid; i < MASK_WORDS * 32; i += CASCADE_THREADS) m_clr[i] = 0u;   // the mask of the group after next
+    // warp w takes the entries of rank [w n / NW, (w+1) n / NW) of every class: one nth_set_bit per lane and group,
+    // then a walk over consecutive set bits (round-2 call 3: rank-strided entries spent 16 % of the kernel's
+    // instructions in __fns)
+    const int r_beg = (warp * n) / CASCADE_WARPS, r_end = ((warp + 1) * n) / CASCADE_WARPS;
+    const int my_iters = r_end - r_beg;
+    int iters = my_iters;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) iters = max(iters, __shfl_xor_sync(0xffffffffu, iters, o));
+    int bpos = my_iters > 0 ? nth_set_bit(m_in, lane, r_beg) : 0;       // bit index of the current entry
+    uint32_t cur = my_iters > 0 ? (m_in[(bpos >> 5) * 32 + lane] & (0xffffffffu << (bpos & 31))) : 0u;   // its word, lower bits cleared
+    for (int it = 0; it < iters; ++it) {
+      bool alive = it < my_iters;
+      int b = 0;
+      if (alive) {
+        while (cur == 0u) { bpos = (bpos | 31) + 1; cur = m_in[(bpos >> 5) * 32 + lane]; }   // next word of the class
+        b = (bpos & ~31) | (__ffs(cur) - 1);
+        cur &= cur - 1u;
+        bpos = b;
+      }
       const uint8_t *tA, *tB;
-      bases(e, tA, tB);
+      bases(lane, b, tA, tB);
       double sum = 0.0;
       for (int j = jb; j < je; ++j) {
         if (!__any_sync(0xffffffffu, alive)) break;
         if (FAST && j < HT_GEN_STAGES) {
-          int r = gen_stage(j, tA, tB);
-          if (force_ties & 1) r = -1;
-          if (r < 0) r = stage_pass_ordered(tA, tB, j) ? 1 : 0;
-          alive = alive && (r != 0);
+          int rr = gen_stage(j, tA, tB);
+          if (force_ties & 1) rr = -1;
+          if (rr < 0) rr = stage_pass_ordered(tA, tB, j) ? 1 : 0;
+          alive = alive && (rr != 0);
         } else {
           sum = stage_sum_ordered(tA, tB, j);
           alive = alive && !(sum < c_casc.stage[j].threshold);
@@ -693,24 +721,38 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
       if (alive) {
         if (emit_here) {
           if (FAST && je - 1 < HT_GEN_STAGES) sum = stage_sum_ordered(tA, tB, je - 1);
-          emit(e, sum);
+          emit(lane, b, sum);
         } else {
-          cl_out[atomicAdd(&cnt[(phase + 1) * 32 + lane], 1) * 32 + lane] = (uint16_t)e;
+          atomicOr(&m_out[(b >> 5) * 32 + lane], 1u << (b & 31));
         }
       }
     }
     if (emit_here) return;
     __syncthreads();
-    ++phase;
-    uint16_t *t = cl_in; cl_in = cl_out; cl_out = t;
+    uint32_t *t = m_in; m_in = m_out; m_out = m_clr; m_clr = t;
   }
-  if (!has_late) return;
+  if (!has_late) {
+    if (c_casc.n_groups == 1) {   // a cascade that ends with the dense group: emit its survivors
+      int n = 0;
+#pragma unroll
+      for (int j = 0; j < MASK_WORDS; ++j) n += __popc(m_in[j * 32 + lane]);
+      for (int r = warp; r < n; r += CASCADE_WARPS) {
+        const int b = nth_set_bit(m_in, lane, r);
+        const uint8_t *tA, *tB;
+        bases(lane, b, tA, tB);
+        emit(lane, b, stage_sum_ordered(tA, tB, c_casc.n_stages - 1));
+      }
+    }
+    return;
+  }
 
   // ---- late stages: one warp per surviving window, one feature per lane, exact integer sums.  The features of
   //      a stage are pre-arranged in chunks of 32 (build_late_schedule, ht_api.cu) so that the 32 addresses of
   //      each load slot fall into 32 different banks: the order of an exact integer sum is free ----
   {
-    const int mylen = cnt[phase * 32 + lane];
+    int mylen = 0;
+#pragma unroll
+    for (int j = 0; j < MASK_WORDS; ++j) mylen += __popc(m_in[j * 32 + lane]);
     int incl = mylen;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -721,9 +763,9 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
     for (int wdx = warp; wdx < total; wdx += CASCADE_WARPS) {
       const unsigned owner = __ballot_sync(0xffffffffu, wdx >= excl && wdx < incl);
       const int c = __ffs(owner) - 1;
-      const int e = cl_in[(wdx - __shfl_sync(0xffffffffu, excl, c)) * 32 + c];
+      const int b = nth_set_bit(m_in, c, wdx - __shfl_sync(0xffffffffu, excl, c));
       const uint8_t *tA, *tB;
-      bases(e, tA, tB);
+      bases(c, b, tA, tB);
       const unsigned sA = (unsigned)__cvta_generic_to_shared(tA), sB = (unsigned)__cvta_generic_to_shared(tB);
       bool pass = true;
       for (int j = late_first; j < c_casc.n_stages && pass; ++j) {
@@ -731,9 +773,9 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
         const int c0 = late_chunk0[j], c1 = late_chunk0[j + 1];
         for (int ch = c0; ch < c1; ++ch) {
           const uint4 *fp = reinterpret_cast<const uint4 *>(late + (size_t)ch * 32 + lane);
-          const uint4 a = __ldg(fp), b = __ldg(fp + 1);
-          const int ai = (int)b.y;                       // alpha_int (0 for padding records)
-          acc += feat_fires(sA, sB, a, b) ? (long long)ai : -(long long)ai;
+          const uint4 a = __ldg(fp), bb = __ldg(fp + 1);
+          const int ai = (int)bb.y;                      // alpha_int (0 for padding records)
+          acc += feat_fires(sA, sB, a, bb) ? (long long)ai : -(long long)ai;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -744,7 +786,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, 2) k_cascade(DevPlan plan, co
       }
       if (pass) {  // confidence = ordered fp64 sum of the last stage
         const double s = stage_sum_ordered_warp(sA, sB, c_casc.n_stages - 1, feat_orig, lane);
-        if (lane == 0) emit(e, s);
+        if (lane == 0) emit(c, b, s);
       }
     }
   }
