@@ -498,7 +498,7 @@ struct ht_ctx {
   int force_ties = 0;                       // ht_debug_set_exactness: force the exactness fallbacks (tests)
   cudaStream_t pipe_stream = nullptr;
   cudaEvent_t pipe_start = nullptr, pipe_events[4] = {};
-  bool use_tma = false;                     // HT_TMA=1: stage level-1 cascade tiles with cp.async.bulk.tensor
+  bool use_tma = true;                      // stage level-1 cascade tiles with cp.async.bulk.tensor (HT_TMA=0: 16-byte cp.async)
   DevBuf d_tmaps;                           // [arenas][scales] 128 B CUtensorMaps over the level-1 planes
   const void *tmap_arena = nullptr;
   const void *tmap_plan = nullptr;
@@ -525,7 +525,8 @@ struct ht_ctx {
   DevBuf d_track_cost;                      // [max_frames][2] {passes, window pixels / 256} per slot
   int track_heavy_div = 64;                 // >0: the n/div costliest streams run on a cluster of
   int track_heavy_cluster = 8;              //     track_heavy_cluster CTAs on sched_stream (HT_TRACK_HEAVY=div[,cluster])
-  int track_mid_div = 0, track_mid_cluster = 4;   // HT_TRACK_MID=div[,cluster]
+  int track_mid_div = 16, track_mid_cluster = 4;  // HT_TRACK_MID=div[,cluster]: the next n/16 costliest streams on clusters of 4
+                                                  // (measured 4.12 -> 3.40 ms per 1024 x 30 calls; div 8: 3.55)
   cudaStream_t sched_stream2 = nullptr;
   cudaEvent_t sched_done2 = nullptr;
   cudaStream_t sched_stream = nullptr;
@@ -823,8 +824,11 @@ int ensure_tensor_maps(ht_ctx *ctx, Plan *P, int n_arenas, size_t wave_words, in
   if (!encode) {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
-      return ctx->fail(HT_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      cudaGetLastError();
+      ctx->use_tma = false;   // old driver: level 1 is staged with 16-byte cp.async like the other levels
+      return HT_OK;
+    }
     encode = reinterpret_cast<encode_fn>(fn);
   }
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
@@ -954,7 +958,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
       auto kern = ctx->hc.fast ? k_cascade<true> : k_cascade<false>;
       kern<<<dim3((unsigned)P->casc_tiles.size(), quads), CASCADE_THREADS, CASC_SMEM, st>>>(
           P->dplan, ctx->d_casc.as<LateFeat>(), ctx->d_casc.as<LateFeat>() + ctx->hc.n_sched, ctx->d_late_chunk0.as<int32_t>(),
-          ctx->use_tma ? ctx->d_tmaps.as<uint8_t>() + (piped ? (size_t)(wi & 1) : 0) * P->scales.size() * 128 : nullptr, 0,
+          (ctx->use_tma && ctx->d_tmaps.p) ? ctx->d_tmaps.as<uint8_t>() + (piped ? (size_t)(wi & 1) : 0) * P->scales.size() * 128 : nullptr, 0,
           arena, P->arena_stride, nw,
           ctx->raw_keys.as<uint32_t>() + (size_t)fa * ctx->raw_cap, ctx->raw_conf.as<double>() + (size_t)fa * ctx->raw_cap,
           ctx->raw_count.as<uint32_t>() + fa, ctx->raw_cap, ctx->force_ties, qm);
