@@ -397,11 +397,17 @@ def run_ours(args, cfg):
     ctx.set_track_memo(False)
     if streams:
         ctx.stream_reset(0, B)
+    # nvidia-smi needs a few hundred ms before its first sample: start it before the warm-up so that it is sampling
+    # every 20 ms when the timed region begins (a short run used to end before the first sample)
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_w = time.perf_counter()
     for _ in range(args.warmup):
         step_guarded()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    while time.perf_counter() - t_w < 0.6:      # (the extra warm-up steps are not timed)
+        step_guarded()
+        barrier()
     l0 = ctx.launch_count
     ctx.profile(True)
     ctx.profile_read(reset=True)

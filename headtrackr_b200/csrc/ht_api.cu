@@ -527,8 +527,9 @@ struct ht_ctx {
   int track_heavy_cluster = 8;              //     track_heavy_cluster CTAs on sched_stream (HT_TRACK_HEAVY=div[,cluster])
   int track_mid_div = 16, track_mid_cluster = 4;  // HT_TRACK_MID=div[,cluster]: the next n/16 costliest streams on clusters of 4
                                                   // (measured 4.12 -> 3.40 ms per 1024 x 30 calls; div 8: 3.55)
-  cudaStream_t sched_stream2 = nullptr;
-  cudaEvent_t sched_done2 = nullptr;
+  int track_light_div = 0, track_light_nt = 256;  // HT_TRACK_LIGHT=div[,threads]: the cheapest n/div streams on single CTAs
+  cudaStream_t tier_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t tier_done[3] = {nullptr, nullptr, nullptr};
   cudaStream_t sched_stream = nullptr;
   cudaEvent_t sched_ready = nullptr, sched_done = nullptr;
   int track_bail_area = 0;                  // >0: two-phase k_track; phase A hands streams with a larger window (px) to phase B
@@ -736,41 +737,44 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
       k_track_area<<<(n + 255) / 256, 256, 0, st>>>(state, d_slots, n, ctx->track_history ? ctx->d_track_cost.as<int32_t>() : nullptr, calls_done);
       k_track_rank<<<(n + 255) / 256, 256, 0, st>>>(calls_done, n, bail_list);
       ctx->launches += 2;
-      // the costliest n / track_heavy_div streams (default 1/64: 16 of 1024) get 8-CTA clusters and start first
-      const int n_heavy = (ctx->track_heavy_div > 0) ? n / ctx->track_heavy_div : 0;
-      if (n_heavy > 0) {
-        if (!ctx->sched_stream) {
-          CK(cudaStreamCreateWithFlags(&ctx->sched_stream, cudaStreamNonBlocking));
-          CK(cudaEventCreateWithFlags(&ctx->sched_ready, cudaEventDisableTiming));
-          CK(cudaEventCreateWithFlags(&ctx->sched_done, cudaEventDisableTiming));
-        }
+      // Tiers by cost rank, each on its own stream so that they run concurrently, costliest first:
+      //   the costliest n / heavy_div streams on clusters of 8 (long chains over large windows: shorten every pass),
+      //   the next n / mid_div on clusters of 4, the cheapest n / light_div on single CTAs (small windows, few passes:
+      //   no cluster barrier at all, and half the CTA slots), the rest on clusters of `c` (2).
+      struct Tier { int count, cluster, threads, side; };   // side >= 0: ctx->tier_stream[side]; -1: the context's stream
+      Tier tiers[4];
+      int n_tiers = 0, left = n;
+      auto take = [&](int div, int cl, int threads, int side) {
+        const int k = (div > 0) ? std::min(left, n / div) : 0;
+        if (k > 0) { tiers[n_tiers++] = Tier{k, cl, threads, side}; left -= k; }
+        return k;
+      };
+      take(ctx->track_heavy_div, ctx->track_heavy_cluster, 256, 0);
+      take(ctx->track_mid_div, ctx->track_mid_cluster, 256, 1);
+      const int n_light = (ctx->track_light_div > 0) ? std::min(left, n / ctx->track_light_div) : 0;
+      if (left - n_light > 0) tiers[n_tiers++] = Tier{left - n_light, c, nt, -1};
+      if (n_light > 0) tiers[n_tiers++] = Tier{n_light, 1, ctx->track_light_nt, 2};
+      if (n_tiers > 1) {
+        for (int t = 0; t < 3; ++t)
+          if (!ctx->tier_stream[t]) {
+            CK(cudaStreamCreateWithFlags(&ctx->tier_stream[t], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->tier_done[t], cudaEventDisableTiming));
+          }
+        if (!ctx->sched_ready) CK(cudaEventCreateWithFlags(&ctx->sched_ready, cudaEventDisableTiming));
         CK(cudaEventRecord(ctx->sched_ready, st));
-        CK(cudaStreamWaitEvent(ctx->sched_stream, ctx->sched_ready, 0));
-        e = launch_track_any(ctx->track_heavy_cluster, 256, ctx->sched_stream, n_heavy, bins, w, h, d_slots, mh, ch, state,
-                             n_calls, d_objs, d_win, flag, stats, calls_done, bail_list, bail_count, 2, 0, opt);
-        CK(cudaEventRecord(ctx->sched_done, ctx->sched_stream));
-        ++ctx->launches;
       }
-      // optional middle tier (HT_TRACK_MID=div[,cluster]): the next n / div streams on clusters of 4 on a third stream
-      int n_mid = (ctx->track_mid_div > 0 && n_heavy > 0) ? std::min(n - n_heavy, n / ctx->track_mid_div) : 0;
-      if (e == cudaSuccess && n_mid > 0) {
-        if (!ctx->sched_stream2) {
-          CK(cudaStreamCreateWithFlags(&ctx->sched_stream2, cudaStreamNonBlocking));
-          CK(cudaEventCreateWithFlags(&ctx->sched_done2, cudaEventDisableTiming));
-        }
-        CK(cudaStreamWaitEvent(ctx->sched_stream2, ctx->sched_ready, 0));
-        e = launch_track_any(ctx->track_mid_cluster, 256, ctx->sched_stream2, n_mid, bins, w, h, d_slots, mh, ch, state,
-                             n_calls, d_objs, d_win, flag, stats, calls_done, bail_list, bail_count, 2, n_heavy, opt);
-        CK(cudaEventRecord(ctx->sched_done2, ctx->sched_stream2));
+      int off = 0;
+      for (int t = 0; t < n_tiers && e == cudaSuccess; ++t) {
+        cudaStream_t ts = tiers[t].side >= 0 ? ctx->tier_stream[tiers[t].side] : st;
+        if (tiers[t].side >= 0) CK(cudaStreamWaitEvent(ts, ctx->sched_ready, 0));
+        e = launch_track_any(tiers[t].cluster, tiers[t].threads, ts, tiers[t].count, bins, w, h, d_slots, mh, ch, state, n_calls,
+                             d_objs, d_win, flag, stats, calls_done, bail_list, bail_count, 2, off, opt);
         ++ctx->launches;
+        if (tiers[t].side >= 0) CK(cudaEventRecord(ctx->tier_done[tiers[t].side], ts));
+        off += tiers[t].count;
       }
-      if (e == cudaSuccess && n > n_heavy + n_mid) {
-        e = launch_track_any(c, nt, st, n - n_heavy - n_mid, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
-                             calls_done, bail_list, bail_count, 2, n_heavy + n_mid, opt);
-        ++ctx->launches;
-      }
-      if (n_heavy > 0) CK(cudaStreamWaitEvent(st, ctx->sched_done, 0));
-      if (n_mid > 0) CK(cudaStreamWaitEvent(st, ctx->sched_done2, 0));
+      for (int t = 0; t < n_tiers; ++t)
+        if (tiers[t].side >= 0) CK(cudaStreamWaitEvent(st, ctx->tier_done[tiers[t].side], 0));
     }
   }
   if (e != cudaSuccess) return ctx->fail(HT_ERR_CUDA, "k_track launch: %s", cudaGetErrorString(e));
@@ -799,7 +803,7 @@ int track_init_common(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *d
 
 // Shared memory of one k_cascade CTA: the staged tile and three sets of per-class survivor bit masks.
 constexpr size_t CASC_SMEM = (size_t)TILE_WORDS * 4 + 3 * (size_t)MASK_WORDS * 32 * sizeof(uint32_t);
-constexpr size_t GRAY_HIST_SMEM = 4 * 4096 * sizeof(uint32_t);
+constexpr size_t GRAY_HIST_SMEM = 2 * 4096 * sizeof(uint32_t);   // two frames per word, 16-bit counters
 
 int set_kernel_attributes(ht_ctx *ctx) {
   CK(cudaFuncSetAttribute(k_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CASC_SMEM));
@@ -921,8 +925,9 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
     // K1 grayscale (+ histogram + bin plane) -> plane 0
     {
       const bool hist = ho.hist != nullptr;
-      const int target = hist ? 444 : 1184;      // CTAs: 3 (64 KB of histograms each) or 8 per SM
-      const int chunks = std::max(1, std::min(h, (target + quads - 1) / quads));
+      const int target = hist ? 592 : 1184;      // CTAs: 4 (32 KB of histograms each, register-limited) or 8 per SM
+      int chunks = std::max(1, std::min(h, (target + quads - 1) / quads));
+      if (hist) chunks = std::max(chunks, (w * h + 59999) / 60000);   // 16-bit histogram counters per CTA
       uint32_t *hp = hist ? ho.hist + (size_t)w0 * 4096 : nullptr;
       uint16_t *bp = ho.bins ? ho.bins + (size_t)w0 * w * h : nullptr;
       ctx->prof_begin(HT_PROF_GRAY);
@@ -1100,6 +1105,13 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
       if (hc == 1 || hc == 2 || hc == 4 || hc == 8) c->track_heavy_cluster = hc;
     }
   }
+  if (const char *tli = getenv("HT_TRACK_LIGHT")) {
+    c->track_light_div = std::max(0, atoi(tli));
+    if (const char *comma = strchr(tli, ',')) {
+      const int ln = atoi(comma + 1);
+      if (ln == 128 || ln == 256 || ln == 512) c->track_light_nt = ln;
+    }
+  }
   if (const char *tmid = getenv("HT_TRACK_MID")) {
     c->track_mid_div = std::max(0, atoi(tmid));
     if (const char *comma = strchr(tmid, ',')) {
@@ -1158,8 +1170,10 @@ void ht_destroy(ht_ctx *ctx) {
   if (ctx->pipe_start) cudaEventDestroy(ctx->pipe_start);
   for (cudaEvent_t e : ctx->pipe_events) if (e) cudaEventDestroy(e);
   if (ctx->sched_stream) cudaStreamDestroy(ctx->sched_stream);
-  if (ctx->sched_stream2) cudaStreamDestroy(ctx->sched_stream2);
-  if (ctx->sched_done2) cudaEventDestroy(ctx->sched_done2);
+  for (int t = 0; t < 3; ++t) {
+    if (ctx->tier_stream[t]) cudaStreamDestroy(ctx->tier_stream[t]);
+    if (ctx->tier_done[t]) cudaEventDestroy(ctx->tier_done[t]);
+  }
   if (ctx->sched_ready) cudaEventDestroy(ctx->sched_ready);
   if (ctx->sched_done) cudaEventDestroy(ctx->sched_done);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

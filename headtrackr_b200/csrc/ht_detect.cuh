@@ -122,7 +122,8 @@ __host__ __device__ __forceinline__ void gray_item(const uint8_t *__restrict__ r
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         b[i] = rgb_bin(px[f][i]);
-        if (VEC || col + i < w) atomicAdd(&sh_hist[f * 4096 + b[i]], 1u);   // (col < w was tested above)
+        // two frames share a word (16-bit counters: a CTA sees < 65,536 pixels of a frame, enforced by the host)
+        if (VEC || col + i < w) atomicAdd(&sh_hist[(f >> 1) * 4096 + b[i]], (f & 1) ? 0x10000u : 1u);   // (col < w was tested above)
       }
       if (bins) {
         uint16_t *bo = bins + (size_t)(4 * quad + f) * n_px + (size_t)row * w + col;
@@ -140,16 +141,16 @@ __host__ __device__ __forceinline__ void gray_item(const uint8_t *__restrict__ r
 }
 
 template <bool VEC, bool HIST>
-__global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_frames,
+__global__ void __launch_bounds__(256, 4) k_gray(const uint8_t *__restrict__ rgba, size_t frame_bytes, int n_frames,
                                               uint32_t *__restrict__ arena, size_t quad_stride, int w, int h,
                                               int pitch0, uint32_t *__restrict__ hist, uint16_t *__restrict__ bins,
                                               int chunks, const uint8_t *__restrict__ quad_mask) {
-  extern __shared__ uint32_t sh_hist[];   // HIST: [4][4096]
+  extern __shared__ uint32_t sh_hist[];   // HIST: [2][4096] words of two 16-bit counters (frames 0|1 and 2|3)
   const int quad = blockIdx.y;
   const unsigned fmask = quad_frames(quad, n_frames, quad_mask);
   if (fmask == 0u) return;
   if (HIST) {
-    for (int i = threadIdx.x; i < 4 * 4096; i += 256) sh_hist[i] = 0;
+    for (int i = threadIdx.x; i < 2 * 4096; i += 256) sh_hist[i] = 0;
     __syncthreads();
   }
   const int gpr = pitch0 >> 2;                        // groups of 4 pixels per plane row (pad columns included)
@@ -164,11 +165,10 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ rgba, 
     for (int f = 0; f < 4; ++f) {
       if (!((fmask >> f) & 1u)) continue;
       uint32_t *out = hist + (size_t)(4 * quad + f) * 4096;
-      if (chunks == 1) {
-        for (int i = threadIdx.x; i < 4096; i += 256) out[i] = sh_hist[f * 4096 + i];
-      } else {
-        for (int i = threadIdx.x; i < 4096; i += 256)
-          if (sh_hist[f * 4096 + i]) atomicAdd(&out[i], sh_hist[f * 4096 + i]);
+      for (int i = threadIdx.x; i < 4096; i += 256) {
+        const uint32_t cnt = (sh_hist[(f >> 1) * 4096 + i] >> (16 * (f & 1))) & 0xffffu;
+        if (chunks == 1) out[i] = cnt;
+        else if (cnt) atomicAdd(&out[i], cnt);
       }
     }
   }
