@@ -42,6 +42,17 @@ class StreamEvent(C.Structure):
                 ("width", C.c_double), ("height", C.c_double), ("angle", C.c_double), ("confidence", C.c_double)]
 
 
+class HeadParams(C.Structure):
+    _fields_ = [("smoothing", C.c_int32), ("head_position", C.c_int32), ("edgecorrection", C.c_int32), ("pad_", C.c_int32),
+                ("alpha", C.c_double), ("fov_deg", C.c_double), ("camera_offset", C.c_double),
+                ("distance_to_screen", C.c_double)]
+
+
+class HeadEvent(C.Structure):
+    _fields_ = [("valid", C.c_int32), ("status", C.c_int32), ("x", C.c_double), ("y", C.c_double), ("z", C.c_double),
+                ("fx", C.c_double), ("fy", C.c_double), ("fwidth", C.c_double), ("fheight", C.c_double)]
+
+
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
                 ("max_frames", C.c_int32), ("max_raw_per_frame", C.c_int32), ("max_rects_per_frame", C.c_int32),
@@ -69,7 +80,7 @@ def build(force=False):
 _lib = None
 
 EXPORTS = ["ht_version", "ht_create", "ht_destroy", "ht_last_error", "ht_sync", "ht_max_rects", "ht_detect",
-           "ht_track_init", "ht_track_init_from_detect", "ht_track", "ht_detect_track", "ht_stream_reset", "ht_stream_step", "ht_backprojection", "ht_whitebalance",
+           "ht_track_init", "ht_track_init_from_detect", "ht_track", "ht_detect_track", "ht_stream_reset", "ht_stream_step", "ht_stream_head_config", "ht_stream_step_head", "ht_ingest", "ht_backprojection", "ht_whitebalance",
            "ht_plan_info", "ht_debug_plane", "ht_debug_raw", "ht_debug_model_hist", "ht_debug_track_stats", "ht_set_track_memo", "ht_debug_set_exactness", "ht_debug_track_trace", "ht_launch_count",
            "ht_profile", "ht_profile_read"]
 
@@ -103,6 +114,9 @@ def lib():
                                   vp, vp, vp, vp, vp]
     L.ht_stream_reset.argtypes = [vp, C.c_int, C.c_int]
     L.ht_stream_step.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.ht_stream_head_config.argtypes = [vp, vp]
+    L.ht_stream_step_head.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.ht_ingest.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int]
     L.ht_backprojection.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp]
     L.ht_whitebalance.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.ht_plan_info.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]

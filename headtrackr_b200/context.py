@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import HtError, Rect, StreamEvent, TrackObj, Window
+from ._lib import HeadEvent, HeadParams, HtError, Rect, StreamEvent, TrackObj, Window
 from .synth import load_cascade_blob
 
 
@@ -179,6 +179,30 @@ class Context:
         """Streams [first, first+n) start over in "VJ" (a new facetrackr.Tracker with whitebalancing off)."""
         self._check(self._L.ht_stream_reset(self._h, first, self.max_frames - first if n is None else n))
 
+    def stream_head_config(self, smoothing=True, fov=None, camera_offset=11.5, head_position=True, edgecorrection=True,
+                           alpha=0.35, distance_to_screen=60.0, enable=True):
+        """Head-position epilogue of stream_step (src/main.js:246-300): parameters of headtrackr.Tracker
+        ({smoothing, fov, cameraOffset, headPosition}); enable=False switches it off."""
+        if not enable:
+            self._check(self._L.ht_stream_head_config(self._h, None))
+            return
+        p = HeadParams(int(bool(smoothing)), int(bool(head_position)), int(bool(edgecorrection)), 0, alpha,
+                       float(fov) if fov is not None else 0.0, camera_offset, distance_to_screen)
+        self._check(self._L.ht_stream_head_config(self._h, C.addressof(p)))
+
+    def stream_step_head(self, frames, interval=5, min_neighbors=1, calc_angles=False):
+        """stream_step plus the head epilogue -> (events, heads); heads[k] = dict(valid, found, x, y, z, face=(x,y,w,h))."""
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        ev = (StreamEvent * n)()
+        he = (HeadEvent * n)()
+        self._check(self._L.ht_stream_step_head(self._h, ptr, n, W, H, interval, min_neighbors, int(bool(calc_angles)),
+                                                C.addressof(ev), C.addressof(he)))
+        events = [dict(detection=("", "VJ", "CS")[e.detection], x=e.x, y=e.y, width=e.width, height=e.height, angle=e.angle,
+                       confidence=e.confidence, found=bool(e.status & 1), lost=bool(e.status & 2)) for e in ev]
+        heads = [dict(valid=bool(h.valid), found=bool(h.status & 1), x=h.x, y=h.y, z=h.z,
+                      face=(h.fx, h.fy, h.fwidth, h.fheight)) for h in he]
+        return events, heads
+
     def stream_step(self, frames, interval=5, min_neighbors=1, calc_angles=False, out_events=None):
         """One frame per stream through ht_stream_step.  -> per stream, the TrackObj facetrackr.getTrackingObject()
         would return after track(): dict(detection="VJ"|"CS", x, y, width, height, angle, confidence, found, lost).
@@ -193,6 +217,17 @@ class Context:
                                            C.addressof(ev)))
         return [dict(detection=("", "VJ", "CS")[e.detection], x=e.x, y=e.y, width=e.width, height=e.height, angle=e.angle,
                      confidence=e.confidence, found=bool(e.status & 1), lost=bool(e.status & 2)) for e in ev]
+
+    def ingest(self, frames, width, height, out=None):
+        """drawImage(video, 0, 0, width, height) for a batch (src/main.js:170).  numpy in -> numpy (n, height, width, 4)
+        out; with a torch CUDA `out` tensor the result stays on the device."""
+        ptr, n, H, W, keep = _frames_ptr(frames)
+        if out is not None:
+            self._check(self._L.ht_ingest(self._h, ptr, n, W, H, out.data_ptr(), width, height))
+            return out
+        dst = np.zeros((n, height, width, 4), np.uint8)
+        self._check(self._L.ht_ingest(self._h, ptr, n, W, H, dst.ctypes.data, width, height))
+        return dst
 
     def backprojection(self, frame, slot=0):
         ptr, n, H, W, keep = _frames_ptr(frame)

@@ -71,6 +71,19 @@ struct Plan {
   DevPlan dplan{};
 };
 
+// floor(n / d) == (uint64(n) * M) >> k for all n <= 255 d + d / 2  (d = 4 dw dh): the exact-division constants of a
+// canvas-shim drawImage.  false when the numerators do not fit 32 bits.
+bool bilinear_division_constants(unsigned long long d, uint32_t &magic, uint32_t &shift) {
+  const unsigned __int128 nmax = (unsigned __int128)d * 255 + d / 2 + 1;
+  if (d == 0 || nmax >= ((unsigned __int128)1 << 32)) return false;
+  int k = 32;
+  while ((((unsigned __int128)1) << k) <= nmax * d) ++k;
+  const unsigned __int128 M = ((((unsigned __int128)1) << k) / d) + 1;
+  if (k > 63 || M >= ((unsigned __int128)1 << 32) || nmax * M >= ((unsigned __int128)1 << 64)) return false;
+  magic = (uint32_t)M; shift = (uint32_t)k;
+  return true;
+}
+
 int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std::string &err, bool upload = true) {
   P.w = W; P.h = H; P.interval = interval;
   const double scale = std::pow(2.0, 1.0 / (interval + 1.0));                      // ccv.js:110
@@ -164,15 +177,8 @@ int build_plan(Plan &P, int W, int H, int interval, int casc_w, int casc_h, std:
       while (P.taps.size() & 3) P.taps.push_back(TapEnt{0, 0, 0, 0}); // k_resample reads column taps four at a time
       j.row_off = make_taps(dh, js.sh, js.sy);
       const unsigned long long d = 4ull * dw * dh;
-      const unsigned __int128 nmax = (unsigned __int128)d * 255 + d / 2 + 1;
-      if (nmax >= ((unsigned __int128)1 << 32)) { err = "frame too large for 32-bit bilinear numerators"; return HT_ERR_SIZE; }
-      int k = 32;
-      while ((((unsigned __int128)1) << k) <= nmax * d) ++k;
-      const unsigned __int128 M = ((((unsigned __int128)1) << k) / d) + 1;
-      if (k > 63 || M >= ((unsigned __int128)1 << 32) || nmax * M >= ((unsigned __int128)1 << 64)) {
-        err = "frame too large for the exact-division constants"; return HT_ERR_SIZE;
-      }
-      j.magic = (uint32_t)M; j.shift = (uint32_t)k; j.half = (uint32_t)(d / 2);
+      if (!bilinear_division_constants(d, j.magic, j.shift)) { err = "frame too large for 32-bit bilinear numerators"; return HT_ERR_SIZE; }
+      j.half = (uint32_t)(d / 2);
     }
     const int job_id = (int)P.jobs.size();
     P.jobs.push_back(j);
@@ -521,6 +527,8 @@ struct ht_ctx {
   int track_nt = 256;                       // threads per k_track CTA (HT_TRACK_NT=128|256)
   bool track_lpt = true;                    // longest-chain-first launch order (HT_TRACK_LPT=0 disables)
   DevBuf d_stream_mode, d_stream_mask, d_stream_cs, d_stream_init, d_stream_events;   // ht_stream_step
+  DevBuf d_head_state, d_head_params, d_head_events;                                  // ht_stream_head_config
+  bool head_on = false;
   bool track_history = true;                // order by the cost of each stream's previous launch (HT_TRACK_HISTORY=0: by window area)
   DevBuf d_track_cost;                      // [max_frames][2] {passes, window pixels / 256} per slot
   int track_heavy_div = 64;                 // >0: the n/div costliest streams run on a cluster of
@@ -684,6 +692,15 @@ cudaError_t launch_track_nt(int c, cudaStream_t st, int n, const uint16_t *bins,
     case 1: return launch_track_c<1, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
     case 2: return launch_track_c<2, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
     case 4: return launch_track_c<4, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
+    case 16: {
+      static bool allowed = false;   // clusters of 16 are a non-portable size: opt in once per instantiation
+      if (!allowed) {
+        cudaError_t e = cudaFuncSetAttribute(k_track<16, NT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        allowed = true;
+      }
+      return launch_track_c<16, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
+    }
     default: return launch_track_c<8, NT>(st, n, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats, 0, calls_done, list, count, use_list, list_off, opt);
   }
 }
@@ -1102,7 +1119,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
     c->track_heavy_div = std::max(0, atoi(th));
     if (const char *comma = strchr(th, ',')) {
       const int hc = atoi(comma + 1);
-      if (hc == 1 || hc == 2 || hc == 4 || hc == 8) c->track_heavy_cluster = hc;
+      if (hc == 1 || hc == 2 || hc == 4 || hc == 8 || hc == 16) c->track_heavy_cluster = hc;
     }
   }
   if (const char *tli = getenv("HT_TRACK_LIGHT")) {
@@ -1158,7 +1175,7 @@ void ht_destroy(ht_ctx *ctx) {
   for (auto &kv : ctx->plans) kv.second->dev.release();
   DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
                     &ctx->labels, &ctx->seq2, &ctx->d_out_rects, &ctx->d_out_counts, &ctx->d_flags, &ctx->model_hist,
-                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_tmaps, &ctx->d_late_chunk0, &ctx->d_track_cost, &ctx->d_stream_mode, &ctx->d_stream_mask, &ctx->d_stream_cs, &ctx->d_stream_init, &ctx->d_stream_events, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
+                    &ctx->bins, &ctx->d_sched, &ctx->d_trace, &ctx->d_tmaps, &ctx->d_late_chunk0, &ctx->d_track_cost, &ctx->d_stream_mode, &ctx->d_stream_mask, &ctx->d_stream_cs, &ctx->d_stream_init, &ctx->d_stream_events, &ctx->d_head_state, &ctx->d_head_params, &ctx->d_head_events, &ctx->cur_hist, &ctx->track_state, &ctx->d_slots, &ctx->d_rects, &ctx->d_found, &ctx->d_objs,
                     &ctx->d_windows, &ctx->d_wb_sums, &ctx->d_wb_out, &ctx->d_scratch};
   for (DevBuf *b : bufs) b->release();
   for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -1434,6 +1451,44 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
 }
 
 static_assert(sizeof(ht_stream_event) == sizeof(StreamEvent) && sizeof(ht_stream_event) == 56, "ht_stream_event layout");
+static_assert(sizeof(ht_head_event) == sizeof(HeadEvent) && sizeof(ht_head_event) == 64, "ht_head_event layout");
+static_assert(sizeof(ht_head_params) == 48, "ht_head_params layout");
+
+__global__ void k_head_reset(HeadState *s, int first, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) head_new_state(s[first + k]);
+}
+
+static HeadParams make_head_params(const ht_head_params *p) {
+  HeadParams hp{};
+  hp.smoothing = p->smoothing; hp.head_position = p->head_position; hp.edgecorrection = p->edgecorrection;
+  hp.alpha = p->alpha; hp.fov_deg = p->fov_deg; hp.camera_offset = p->camera_offset; hp.distance_to_screen = p->distance_to_screen;
+  const double head_width_cm = 16, head_height_cm = 19;                       // src/headposition.js:53-63
+  const double hsa = std::atan(head_width_cm / head_height_cm);
+  hp.head_diag_cm = std::sqrt((head_width_cm * head_width_cm) + (head_height_cm * head_height_cm));
+  hp.sin_hsa = std::sin(hsa); hp.cos_hsa = std::cos(hsa); hp.tan_hsa = std::tan(hsa);
+  return hp;
+}
+
+int ht_stream_head_config(ht_ctx *ctx, const ht_head_params *params) {
+  if (!ctx) return HT_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (!params) { ctx->head_on = false; return HT_OK; }
+  if (!(params->alpha >= 0.0 && params->alpha <= 1.0) || !(params->distance_to_screen > 0.0)) return ctx->fail(HT_ERR_ARG, "bad head parameters");
+  const size_t mf = (size_t)ctx->cfg.max_frames;
+  if (!ctx->d_head_state.p) {
+    CK(ctx->d_head_state.reserve(mf * sizeof(HeadState)));
+    CK(ctx->d_head_params.reserve(sizeof(HeadParams)));
+    CK(ctx->d_head_events.reserve(mf * sizeof(HeadEvent)));
+    k_head_reset<<<(unsigned)((mf + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_head_state.as<HeadState>(), 0, (int)mf);
+  }
+  const HeadParams hp = make_head_params(params);
+  CK(cudaMemcpyAsync(ctx->d_head_params.p, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));    // `hp` is a local
+  ctx->head_on = true;
+  return HT_OK;
+}
+
 
 static int ensure_stream_buffers(ht_ctx *ctx) {
   const size_t mf = (size_t)ctx->cfg.max_frames;
@@ -1455,6 +1510,8 @@ int ht_stream_reset(ht_ctx *ctx, int first, int n) {
   int rc = ensure_stream_buffers(ctx);
   if (rc != HT_OK) return rc;
   CK(cudaMemsetAsync(ctx->d_stream_mode.as<int32_t>() + first, 0, (size_t)n * sizeof(int32_t), ctx->stream));
+  if (ctx->d_head_state.p)   // a new headtrackr.Tracker: smoother, head diagonals, fov estimate start over too
+    k_head_reset<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_head_state.as<HeadState>(), first, n);
   return HT_OK;
 }
 
@@ -1466,8 +1523,14 @@ int ht_stream_reset(ht_ctx *ctx, int first, int n) {
 // No host round trip between the kernels; the host only drains the event records.
 int ht_stream_step(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors, int calc_angles,
                    ht_stream_event *out_events) {
+  return ht_stream_step_head(ctx, rgba, n, w, h, interval, min_neighbors, calc_angles, out_events, nullptr);
+}
+
+int ht_stream_step_head(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors, int calc_angles,
+                        ht_stream_event *out_events, ht_head_event *out_head) {
   if (!ctx) return HT_ERR_ARG;
   if (!out_events) return ctx->fail(HT_ERR_ARG, "out_events is NULL");
+  if (out_head && !ctx->head_on) return ctx->fail(HT_ERR_STATE, "ht_stream_head_config has not been called");
   int rc = check_batch(ctx, n);
   if (rc != HT_OK) return rc;
   CK(cudaSetDevice(ctx->cfg.device));
@@ -1502,8 +1565,12 @@ int ht_stream_step(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int in
   ctx->prof_end();
   // events + transitions, then initTracker for the streams that just found their face
   StreamEvent *d_ev = is_device_ptr(out_events) ? reinterpret_cast<StreamEvent *>(out_events) : ctx->d_stream_events.as<StreamEvent>();
+  HeadEvent *d_he = nullptr;
+  if (ctx->head_on) d_he = (out_head && is_device_ptr(out_head)) ? reinterpret_cast<HeadEvent *>(out_head) : ctx->d_head_events.as<HeadEvent>();
   k_stream_update<<<(n + 127) / 128, 128, 0, st>>>(mode, n, ctx->d_out_rects.as<Rect>(), ctx->d_out_counts.as<int32_t>(), ctx->K,
-                                                   ctx->d_objs.as<int32_t>(), ctx->d_rects.as<int32_t>(), init_en, d_ev);
+                                                   ctx->d_objs.as<int32_t>(), ctx->d_rects.as<int32_t>(), init_en, d_ev,
+                                                   ctx->head_on ? ctx->d_head_state.as<HeadState>() : nullptr,
+                                                   ctx->d_head_params.as<HeadParams>(), d_he, w, h);
   ctx->prof_begin(HT_PROF_TRACK_INIT);
   k_track_init<<<n, 256, 0, st>>>(d_rgba, (size_t)w * h * 4, w, h, nullptr, ctx->d_rects.as<int32_t>(), calc_angles ? 1 : 0,
                                   ctx->model_hist.as<uint32_t>(), ctx->track_state.as<TrackState>(), nullptr, init_en);
@@ -1512,9 +1579,44 @@ int ht_stream_step(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int in
   CK(cudaGetLastError());
   ctx->last_plan = P;
   ctx->last_n = n;
-  if (!is_device_ptr(out_events)) {
-    CK(cudaMemcpyAsync(out_events, d_ev, sizeof(StreamEvent) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    return ht_sync(ctx);
+  bool any_host = false;
+  if (!is_device_ptr(out_events)) { CK(cudaMemcpyAsync(out_events, d_ev, sizeof(StreamEvent) * (size_t)n, cudaMemcpyDeviceToHost, st)); any_host = true; }
+  if (out_head && !is_device_ptr(out_head)) { CK(cudaMemcpyAsync(out_head, d_he, sizeof(HeadEvent) * (size_t)n, cudaMemcpyDeviceToHost, st)); any_host = true; }
+  if (any_host) return ht_sync(ctx);
+  return HT_OK;
+}
+
+// canvasContext.drawImage(video, 0, 0, canvas.width, canvas.height) for n frames (src/main.js:170)
+int ht_ingest(ht_ctx *ctx, const uint8_t *src_rgba, int n, int sw, int sh, uint8_t *dst_rgba, int dw, int dh) {
+  if (!ctx) return HT_ERR_ARG;
+  if (!src_rgba || !dst_rgba || n <= 0 || sw <= 0 || sh <= 0) return ctx->fail(HT_ERR_ARG, "bad argument");
+  if (dw <= 0 || dh <= 0) return ctx->fail(HT_ERR_SIZE, "0-sized canvas (a browser draws nothing; the detector then throws)");
+  if ((reinterpret_cast<uintptr_t>(src_rgba) & 3u) || (reinterpret_cast<uintptr_t>(dst_rgba) & 3u)) return ctx->fail(HT_ERR_ARG, "frames must be 4-byte aligned");
+  if (sw > 16384 || sh > 16384 || dw > 16384 || dh > 16384) return ctx->fail(HT_ERR_SIZE, "frame too large");
+  IngestGeom g{sw, sh, dw, dh, 0, 0, 0};
+  if (!bilinear_division_constants(4ull * dw * dh, g.magic, g.shift)) return ctx->fail(HT_ERR_SIZE, "canvas too large for 32-bit bilinear numerators");
+  g.half = (uint32_t)(2ull * dw * dh);
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t sbytes = (size_t)n * sw * sh * 4, dbytes = (size_t)n * dw * dh * 4;
+  const uint8_t *d_src = src_rgba;
+  if (!is_device_ptr(src_rgba)) {
+    CK(ctx->d_frames.reserve(sbytes));
+    CK(cudaMemcpyAsync(ctx->d_frames.p, src_rgba, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_src = ctx->d_frames.as<uint8_t>();
+  }
+  const bool out_dev = is_device_ptr(dst_rgba);
+  uint8_t *d_dst = dst_rgba;
+  if (!out_dev) { CK(ctx->d_scratch.reserve(dbytes)); d_dst = ctx->d_scratch.as<uint8_t>(); }
+  if (sw == dw && sh == dh) {   // a 1:1 draw is a copy (oracle/ht_oracle.h)
+    CK(cudaMemcpyAsync(d_dst, d_src, dbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    k_ingest<<<dim3((unsigned)(dw + 63) / 64, (unsigned)(dh + 3) / 4, (unsigned)n), 256, 0, ctx->stream>>>(d_src, d_dst, g);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+  }
+  if (!out_dev) {
+    CK(cudaMemcpyAsync(dst_rgba, d_dst, dbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
   }
   return HT_OK;
 }
@@ -1723,6 +1825,32 @@ extern "C" int ht_selftest_planes(int w, int h, int interval, int32_t *out, int 
     int32_t *o = out + 2 + 6 * i;
     o[0] = (int32_t)P.planes[i].off; o[1] = P.planes[i].pitch; o[2] = P.planes[i].w; o[3] = P.planes[i].h; o[4] = slot; o[5] = q;
   }
+  return 0;
+}
+
+// the head-position epilogue of k_stream_update (head_step) over a sequence of CS results of one stream
+extern "C" int ht_selftest_head(const ht_head_params *params, int n, const double *cs /* [n][5]: is_cs, x, y, w, h */, int camw,
+                                int camh, ht_head_event *out) {
+  const HeadParams hp = make_head_params(params);
+  HeadState s;
+  head_new_state(s);
+  for (int i = 0; i < n; ++i) {
+    const double *c = cs + 5 * i;
+    HeadEvent he;
+    head_step(s, hp, c[0] != 0.0, c[1], c[2], c[3], c[4], c[0] != 0.0 && (c[3] == 0.0 || c[4] == 0.0), (double)camw, (double)camh, he);
+    memcpy(out + i, &he, sizeof(he));
+  }
+  return 0;
+}
+
+// k_ingest's per-pixel code over a whole frame batch
+extern "C" int ht_selftest_ingest(const uint8_t *src, int n, int sw, int sh, uint8_t *dst, int dw, int dh) {
+  IngestGeom g{sw, sh, dw, dh, 0, 0, 0};
+  if (!bilinear_division_constants(4ull * dw * dh, g.magic, g.shift)) return -1;
+  g.half = (uint32_t)(2ull * dw * dh);
+  for (int f = 0; f < n; ++f)
+    for (int Y = 0; Y < dh; ++Y)
+      for (int X = 0; X < dw; ++X) ingest_pixel(src, dst, g, X, Y, f);
   return 0;
 }
 

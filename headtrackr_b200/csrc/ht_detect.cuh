@@ -175,6 +175,48 @@ __global__ void __launch_bounds__(256, 4) k_gray(const uint8_t *__restrict__ rgb
 }
 
 // ------------------------------------------------------------------------------------------------
+// K0  frame ingest — src/main.js:170: canvasContext.drawImage(videoElement, 0, 0, canvas.width, canvas.height): the
+// video frame scaled onto the working canvas, all four channels.  Same DEFINED resampler as the pyramid (exact
+// integer bilinear at pixel centres, taps clamped, round half up; oracle/ht_oracle.h), taps computed on the fly.
+// One thread per destination pixel: four 4-byte loads, one 4-byte store.  (The 1:1 canvas copy facetrackr makes
+// before detection, src/facetrackr.js:140-145, needs no kernel here: nothing on this path modifies its input.)
+struct IngestGeom {
+  int sw, sh, dw, dh;
+  uint32_t magic, shift, half;   // floor(n / (4 dw dh)) == (uint64(n) * magic) >> shift for n <= 255.5 * 4 dw dh
+};
+// one destination pixel (also run on the host by tests/test_ingest_host.py)
+__host__ __device__ __forceinline__ void ingest_pixel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const IngestGeom &g,
+                                                      int X, int Y, int frame) {
+  const uint32_t *s = reinterpret_cast<const uint32_t *>(src) + (size_t)frame * g.sw * g.sh;
+  // u = (X + 1/2) sw / dw - 1/2 = ((2X + 1) sw - dw) / (2 dw): floor and numerator of the fraction, exactly
+  const int un = (2 * X + 1) * g.sw - g.dw, vn = (2 * Y + 1) * g.sh - g.dh;
+  const int Dx = 2 * g.dw, Dy = 2 * g.dh;
+  int x0 = un / Dx, y0 = vn / Dy;
+  if (un < 0 && x0 * Dx != un) --x0;       // floor for negative numerators (the first column / row when upscaling)
+  if (vn < 0 && y0 * Dy != vn) --y0;
+  const uint32_t fx = (uint32_t)(un - x0 * Dx), fy = (uint32_t)(vn - y0 * Dy);
+  const int xa = x0 < 0 ? 0 : (x0 > g.sw - 1 ? g.sw - 1 : x0), xb = x0 + 1 < 0 ? 0 : (x0 + 1 > g.sw - 1 ? g.sw - 1 : x0 + 1);
+  const int ya = y0 < 0 ? 0 : (y0 > g.sh - 1 ? g.sh - 1 : y0), yb = y0 + 1 < 0 ? 0 : (y0 + 1 > g.sh - 1 ? g.sh - 1 : y0 + 1);
+  const uint32_t p00 = ld_ro(s + (size_t)ya * g.sw + xa), p01 = ld_ro(s + (size_t)ya * g.sw + xb);
+  const uint32_t p10 = ld_ro(s + (size_t)yb * g.sw + xa), p11 = ld_ro(s + (size_t)yb * g.sw + xb);
+  const uint32_t w00 = ((uint32_t)Dx - fx) * ((uint32_t)Dy - fy), w01 = fx * ((uint32_t)Dy - fy);
+  const uint32_t w10 = ((uint32_t)Dx - fx) * fy, w11 = fx * fy;
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t num = w00 * ((p00 >> (8 * c)) & 0xffu) + w01 * ((p01 >> (8 * c)) & 0xffu) +
+                         w10 * ((p10 >> (8 * c)) & 0xffu) + w11 * ((p11 >> (8 * c)) & 0xffu) + g.half;
+    out |= (uint32_t)(((uint64_t)num * g.magic) >> g.shift) << (8 * c);
+  }
+  reinterpret_cast<uint32_t *>(dst)[((size_t)frame * g.dh + Y) * g.dw + X] = out;
+}
+__global__ void __launch_bounds__(256) k_ingest(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, IngestGeom g) {
+  const int X = blockIdx.x * 64 + (threadIdx.x & 63), Y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (X >= g.dw || Y >= g.dh) return;
+  ingest_pixel(src, dst, g, X, Y, (int)blockIdx.z);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2  pyramid level = canvas-shim drawImage (exact integer bilinear, see oracle/ht_oracle.h and
 // src/ccv.js:121,128,135,140,145).  One launch per pyramid "generation" (levels whose sources are
 // complete).  Block = 32 x 32 pixels of one destination plane of one frame quad; thread = one column x 4 rows.

@@ -8,6 +8,8 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <limits>
+
 #include "ht_common.cuh"
 
 namespace ht {
@@ -182,7 +184,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // combine their partial moments through distributed shared memory.  Mean-shift is a serial chain
 // of passes per stream (up to 10 per track() call); spreading one pass over several SMs shortens
 // the chain of the streams with large windows, which otherwise set the kernel's duration.
-constexpr int TRACK_CLUSTER_MAX = 8;   // the cluster size is a launch-time choice (1, 2, 4 or 8 CTAs per stream)
+constexpr int TRACK_CLUSTER_MAX = 16;  // the cluster size is a launch-time choice (1, 2, 4, 8 or - non-portable - 16 CTAs per stream)
 
 // Longest-chain-first launch order.  A stream's mean-shift passes form a serial chain whose length grows with its
 // search window, and a launch holds only a few hundred streams at a time, so the streams with the largest windows
@@ -632,6 +634,162 @@ struct StreamEvent {       // == ht_stream_event (include/headtrackr_b200.h)
   double x, y, width, height, angle, confidence;
 };
 
+// ------------------------------------------------------------------------------------------------
+// What src/main.js does with a "CS" result after facetrackr: "found" status, Smoother (src/smoother.js:25-87),
+// the wait for a stable head diagonal (src/main.js:262-281) and headposition.Tracker (src/headposition.js:35-191),
+// as a per-stream epilogue of the state machine - one `headtrackingEvent {x, y, z}` record per stream and frame
+// (SURVEY.md 8f-3).  Scalar fp64 code, operation for operation as the JavaScript (the library is built with
+// -fmad=false); only atan / tan come from CUDA's libm instead of V8's (<= 2 ulp).
+struct HeadParams {            // == ht_head_params (include/headtrackr_b200.h)
+  int32_t smoothing;           // src/main.js:39   (default 1)
+  int32_t head_position;       // src/main.js:55   (default 1)
+  int32_t edgecorrection;      // src/headposition.js:44-48 (default 1)
+  int32_t pad_;
+  double alpha;                // Smoother(0.35, ...)            src/main.js:163
+  double fov_deg;              // params.fov; <= 0: estimate it  src/main.js:283-288
+  double camera_offset;        // params.cameraOffset (11.5)     src/main.js:53
+  double distance_to_screen;   // 60                             src/headposition.js:75-79
+  // constants of the 16 x 19 cm head model, filled by the library with the host's libm (src/headposition.js:53-63)
+  double sin_hsa, cos_hsa, tan_hsa, head_diag_cm;
+};
+struct HeadState {
+  int32_t face_found, sm_init, n_diag, hp_init, first_run, pad_;
+  double sp[5];                // Smoother state: x, y, z, width, height (sp2 IS sp: src/smoother.js:28)
+  double diag[6];              // headDiagonal
+  double fov_saved_deg;        // `fov` of src/main.js:59,288
+  double tan_fov_width, head_diag_cam;   // headposition.Tracker
+};
+struct HeadEvent {             // == ht_head_event
+  int32_t valid;               // 1: a headtrackingEvent was dispatched on this frame
+  int32_t status;              // bit 0: headtrackrStatus "found" on this frame (src/main.js:246-249)
+  double x, y, z;              // src/headposition.js:183-188
+  double fx, fy, fwidth, fheight;   // the (smoothed) face object the position was computed from
+};
+
+__host__ __device__ inline double js_nan() {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(0x7ff8000000000000ll);
+#else
+  return std::numeric_limits<double>::quiet_NaN();
+#endif
+}
+
+__host__ __device__ inline void head_new_state(HeadState &s) {
+  s.face_found = s.sm_init = s.n_diag = s.hp_init = 0;
+  s.first_run = 1; s.pad_ = 0;
+  for (int i = 0; i < 5; ++i) s.sp[i] = 0.0;
+  for (int i = 0; i < 6; ++i) s.diag[i] = 0.0;
+  s.fov_saved_deg = 0.0; s.tan_fov_width = 0.0; s.head_diag_cam = 0.0;
+}
+
+// one frame of one stream: (x, y, w, h) = the CS TrackObj, lost = width or height 0
+__host__ __device__ inline void head_step(HeadState &s, const HeadParams &p, bool is_cs, double x, double y, double w, double h,
+                                          bool lost, double camw, double camh, HeadEvent &out) {
+  const double PI = 3.141592653589793;
+  out.valid = 0; out.status = 0; out.x = out.y = out.z = 0.0; out.fx = out.fy = out.fwidth = out.fheight = 0.0;
+  if (!is_cs) return;
+  if (lost) {                                  // src/main.js:230-244: new facetrackr, faceFound = false, headposition = undefined
+    s.face_found = 0; s.hp_init = 0;
+    return;
+  }
+  if (!s.face_found) { out.status |= 1; s.face_found = 1; }          // :246-249
+  if (p.smoothing) {                                                  // :255-261
+    const double nan = js_nan();                 // faceObj.z is undefined (src/main.js:259) -> NaN
+    if (!s.sm_init) { s.sm_init = 1; s.sp[0] = x; s.sp[1] = y; s.sp[2] = nan; s.sp[3] = w; s.sp[4] = h; }
+    const double pos[5] = {x, y, nan, w, h};
+    const double a = p.alpha;
+    for (int i = 0; i < 5; ++i) {                                     // src/smoother.js:39-42 with sp2 === sp
+      s.sp[i] = a * pos[i] + (1 - a) * s.sp[i];
+      s.sp[i] = a * s.sp[i] + (1 - a) * s.sp[i];
+    }
+    // predict(0): step = 0, ratio = (alpha * 0) / (1 - alpha), a = 2 + ratio, b = 1 + ratio (src/smoother.js:77-84)
+    const double ratio = (a * 0.0) / (1 - a), A = 2 + ratio, B = 1 + ratio;
+    x = A * s.sp[0] - B * s.sp[0]; y = A * s.sp[1] - B * s.sp[1];
+    w = A * s.sp[3] - B * s.sp[3]; h = A * s.sp[4] - B * s.sp[4];
+  }
+  out.fx = x; out.fy = y; out.fwidth = w; out.fheight = h;
+  if (!p.head_position) return;
+  bool track_now = s.hp_init != 0;
+  if (!s.hp_init) {                                                   // src/main.js:264-294
+    bool stable = false;
+    const double headdiag = sqrt(w * w + h * h);
+    if (s.n_diag < 6) s.diag[s.n_diag++] = headdiag;
+    else {
+      for (int i = 0; i < 5; ++i) s.diag[i] = s.diag[i + 1];
+      s.diag[5] = headdiag;
+      double mx = s.diag[0], mn = s.diag[0];
+      bool any_nan = false;
+      for (int i = 0; i < 6; ++i) { any_nan = any_nan || (s.diag[i] != s.diag[i]); mx = s.diag[i] > mx ? s.diag[i] : mx; mn = s.diag[i] < mn ? s.diag[i] : mn; }
+      if (!any_nan && (mx - mn) < 5) stable = true;                   // Math.max/min are NaN if any element is
+    }
+    if (stable) {                                                     // new headposition.Tracker(faceObj, W, H, {...})
+      s.head_diag_cam = sqrt((w * w) + (h * h));                      // src/headposition.js:66-68
+      double fov_width;
+      if (s.first_run) {
+        if (!(p.fov_deg > 0.0)) {                                     // :69-84
+          const double head_width_cam = p.sin_hsa * s.head_diag_cam;
+          const double camwidth_at_default_face_cm = (camw / head_width_cam) * 16;
+          fov_width = atan((camwidth_at_default_face_cm / 2) / p.distance_to_screen) * 2;
+        } else {
+          fov_width = p.fov_deg * PI / 180;
+        }
+        s.fov_saved_deg = fov_width * 180 / PI;                       // getFOV(), src/main.js:288
+        s.first_run = 0;
+      } else {
+        fov_width = s.fov_saved_deg * PI / 180;                       // {fov : fov}, src/main.js:291
+      }
+      s.tan_fov_width = 2 * tan(fov_width / 2);                       // src/headposition.js:87
+      s.hp_init = 1;
+      track_now = true;
+    }
+  }
+  if (!track_now) return;
+  // headposition.Tracker.track — src/headposition.js:91-191
+  double fx = x, fy = y, hdc = s.head_diag_cam;
+  const double sin_hsa = p.sin_hsa, cos_hsa = p.cos_hsa, tan_hsa = p.tan_hsa;
+  if (p.edgecorrection) {
+    const double margin = 11;
+    const double leftDistance = fx - (w / 2), rightDistance = camw - (fx + (w / 2));
+    const double topDistance = fy - (h / 2), bottomDistance = camh - (fy + (h / 2));
+    const bool onVerticalEdge = (leftDistance < margin || rightDistance < margin);
+    const bool onHorizontalEdge = (topDistance < margin || bottomDistance < margin);
+    if (onHorizontalEdge) {
+      if (onVerticalEdge) {                                           // corner: keep the previous diagonal
+        if (leftDistance < margin) fx = w - (hdc * sin_hsa / 2); else fx = fx - (w / 2) + (hdc * sin_hsa / 2);
+        if (topDistance < margin) fy = h - (hdc * cos_hsa / 2); else fy = fy - (h / 2) + (hdc * cos_hsa / 2);
+      } else if (topDistance < margin) {
+        const double ow = topDistance / margin, ew = (margin - topDistance) / margin;
+        fy = h - (ow * (h / 2) + ew * ((w / tan_hsa) / 2));
+        hdc = ew * (w / sin_hsa) + ow * (sqrt((w * w) + (h * h)));
+      } else {
+        const double ow = bottomDistance / margin, ew = (margin - bottomDistance) / margin;
+        fy = fy - (h / 2) + (ow * (h / 2) + ew * ((w / tan_hsa) / 2));
+        hdc = ew * (w / sin_hsa) + ow * (sqrt((w * w) + (h * h)));
+      }
+    } else if (onVerticalEdge) {
+      if (leftDistance < margin) {
+        const double ow = leftDistance / margin, ew = (margin - leftDistance) / margin;
+        hdc = ew * (h / cos_hsa) + ow * (sqrt((w * w) + (h * h)));
+        fx = w - (ow * (w / 2) + (ew) * (h * tan_hsa / 2));
+      } else {
+        const double ow = rightDistance / margin, ew = (margin - rightDistance) / margin;
+        hdc = ew * (h / cos_hsa) + ow * (sqrt((w * w) + (h * h)));
+        fx = fx - (w / 2) + (ow * (w / 2) + ew * (h * tan_hsa / 2));
+      }
+    } else {
+      hdc = sqrt((w * w) + (h * h));
+    }
+  } else {
+    hdc = sqrt((w * w) + (h * h));
+  }
+  s.head_diag_cam = hdc;
+  const double z = (p.head_diag_cm * camw) / (s.tan_fov_width * hdc);              // :165
+  const double hx = -((fx / camw) - 0.5) * z * s.tan_fov_width;                    // :170
+  double hy = -((fy / camh) - 0.5) * z * s.tan_fov_width * (camh / camw);
+  hy = hy + p.camera_offset;                                                      // :175-180
+  out.valid = 1; out.x = hx; out.y = hy; out.z = z;
+}
+
 __global__ void k_stream_plan(const int32_t *__restrict__ mode, int n, uint8_t *__restrict__ vj_quad_mask,
                               uint8_t *__restrict__ cs_enable, uint8_t *__restrict__ init_enable) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -648,7 +806,11 @@ __global__ void k_stream_plan(const int32_t *__restrict__ mode, int n, uint8_t *
 __global__ void k_stream_update(int32_t *__restrict__ mode, int n, const Rect *__restrict__ det,
                                 const int32_t *__restrict__ counts, int K, const int32_t *__restrict__ objs,
                                 int32_t *__restrict__ rects, uint8_t *__restrict__ init_enable,
-                                StreamEvent *__restrict__ events) {
+                                StreamEvent *__restrict__ events,
+                                // optional head-position epilogue (ht_stream_head_config): per-stream state, parameters,
+                                // one HeadEvent per stream; camw / camh = the canvas size
+                                HeadState *__restrict__ head_state, const HeadParams *__restrict__ head_params,
+                                HeadEvent *__restrict__ head_events, int camw, int camh) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   StreamEvent e;
@@ -685,6 +847,13 @@ __global__ void k_stream_update(int32_t *__restrict__ mode, int n, const Rect *_
     }
   }
   events[k] = e;
+  if (head_state) {
+    HeadState hs = head_state[k];
+    HeadEvent he;
+    head_step(hs, *head_params, e.detection == 2, e.x, e.y, e.width, e.height, (e.status & 2) != 0, (double)camw, (double)camh, he);
+    head_state[k] = hs;
+    if (head_events) head_events[k] = he;
+  }
 }
 
 // getBackProjectionImg — src/camshift.js:177-196 (debug path)

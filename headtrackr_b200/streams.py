@@ -28,10 +28,20 @@ class StreamSet:
         """A new facetrackr.Tracker({whitebalancing: false}) for one stream (src/main.js:236)."""
         self.ctx.stream_reset(stream, 1)
 
+    def enable_head_position(self, **params):
+        """headtrackr.Tracker's smoothing + head position per stream (src/main.js:246-300) as a GPU epilogue: the
+        listeners then also receive `headtrackingEvent {x, y, z}` and `headtrackrStatus {status: "found"}` dicts."""
+        self.ctx.stream_head_config(**params)
+        self._head = True
+
     def track(self, frames):
         """frames: (n, H, W, 4) u8 (numpy or torch CUDA) - the current frame of every stream."""
         t0 = time.time()
-        events = self.ctx.stream_step(frames, self.interval, self.min_neighbors, self.calc_angles)
+        heads = None
+        if getattr(self, "_head", False):
+            events, heads = self.ctx.stream_step_head(frames, self.interval, self.min_neighbors, self.calc_angles)
+        else:
+            events = self.ctx.stream_step(frames, self.interval, self.min_neighbors, self.calc_angles)
         dt = int((time.time() - t0) * 1000)
         for k, e in enumerate(events):
             e["time"] = dt
@@ -41,6 +51,13 @@ class StreamSet:
                            y=e["y"], confidence=e["confidence"], detection="CS", time=dt)
                 for fn in self._listeners:
                     fn(k, evt)
+            if heads is not None:
+                if heads[k]["found"]:
+                    for fn in self._listeners:
+                        fn(k, dict(type="headtrackrStatus", status="found"))
+                if heads[k]["valid"]:
+                    for fn in self._listeners:
+                        fn(k, dict(type="headtrackingEvent", x=heads[k]["x"], y=heads[k]["y"], z=heads[k]["z"]))
         return events
 
     def getTrackingObject(self, stream):

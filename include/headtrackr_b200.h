@@ -150,10 +150,45 @@ typedef struct {
   int32_t status;      /* bit 0: face found on this frame (VJ -> CS); bit 1: face lost on this frame (CS -> VJ) */
   double x, y, width, height, angle, confidence;   /* VJ: top-left, fp64 as ccv returns; CS: centre, integers */
 } ht_stream_event;
+/* Head position per stream and frame as an epilogue of the state machine: what src/main.js does
+ * with a "CS" result - headtrackrStatus "found" (src/main.js:246-249), headtrackr.Smoother (src/smoother.js:25-87,
+ * including its quirks: sp2 aliases sp, z is NaN, predict() runs with step 0), the wait for six head diagonals within
+ * 5 px (src/main.js:262-281), headposition.Tracker with its field-of-view estimate and edge correction
+ * (src/headposition.js:35-191) - evaluated by the kernel that already writes the stream events.  One ht_head_event
+ * per stream and frame; `valid` marks the frames on which the reference dispatches `headtrackingEvent {x, y, z}`. */
+typedef struct {
+  int32_t smoothing;           /* params.smoothing      (src/main.js:39, default 1) */
+  int32_t head_position;       /* params.headPosition   (src/main.js:55, default 1) */
+  int32_t edgecorrection;      /* headposition params   (src/headposition.js:44-48, default 1) */
+  int32_t pad_;
+  double alpha;                /* Smoother alpha        (src/main.js:163: 0.35) */
+  double fov_deg;              /* params.fov in degrees; <= 0: estimate it from the first stable face (src/main.js:283-288) */
+  double camera_offset;        /* params.cameraOffset   (src/main.js:53: 11.5) */
+  double distance_to_screen;   /* 60 cm                 (src/headposition.js:75-79) */
+} ht_head_params;
+typedef struct {
+  int32_t valid;               /* 1: headtrackingEvent dispatched on this frame */
+  int32_t status;              /* bit 0: headtrackrStatus "found" on this frame */
+  double x, y, z;              /* head position in cm relative to the screen centre (src/headposition.js:165-188) */
+  double fx, fy, fwidth, fheight;   /* the (smoothed) face object it was computed from */
+} ht_head_event;
+/* params == NULL switches the epilogue off.  Changing parameters does not reset stream state; ht_stream_reset does. */
+int ht_stream_head_config(ht_ctx *ctx, const ht_head_params *params);
+/* ht_stream_step plus one ht_head_event per stream (out_head may be NULL) */
+int ht_stream_step_head(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors,
+                        int calc_angles, ht_stream_event *out_events, ht_head_event *out_head);
+
 /* put streams [first, first+n) back into "VJ" (new facetrackr.Tracker) */
 int ht_stream_reset(ht_ctx *ctx, int first, int n);
 int ht_stream_step(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int interval, int min_neighbors,
                    int calc_angles, ht_stream_event *out_events);
+
+/* Frame ingest: canvasContext.drawImage(videoElement, 0, 0, canvas.width, canvas.height)
+ * (src/main.js:170) for n frames - the video frame (sw x sh) scaled onto the working canvas (dw x dh), all four
+ * channels, with the canvas resampler this build defines.  src and dst may be host or device
+ * memory; a device dst can be passed straight to ht_detect / ht_track / ht_stream_step.  (The 1:1 copy facetrackr
+ * makes before detection, src/facetrackr.js:140-145, needs no call: no entry point modifies its input frames.) */
+int ht_ingest(ht_ctx *ctx, const uint8_t *src_rgba, int n, int sw, int sh, uint8_t *dst_rgba, int dw, int dh);
 
 /* getBackProjectionImg() of the last track() state for one slot: RGBA w*h*4, floor(255*weight) gray
  * (src/camshift.js:177-196).  Debug path of the reference (src/facetrackr.js:194-196). */

@@ -87,3 +87,39 @@ def test_stream_step_replays_main_js_lost_and_found():
         assert n_cs >= 10 and n_lost >= 1
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("case_name", ["default", "no_smoothing_fov"])
+def test_stream_step_head_replays_main_js_head_events(case_name):
+    """f3: every headtrackingEvent {x, y, z} and "found" status of the reference's src/main.js run, produced by the
+    head-position epilogue of ht_stream_step on the device (smoother + stable diagonal + headposition.Tracker)."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import make_goldens_main as mg
+    from test_host_main import GOLD_M
+    case = next(c for c in GOLD_M["cases"] if c["name"] == case_name)
+    p = case["params"] or {}
+    spec = [tuple(s["frame"]) for s in case["steps"]]
+    i0 = next(i for i, s in enumerate(case["steps"]) if s["status"] == "detecting")
+    W, H = GOLD_M["width"], GOLD_M["height"]
+    c = Context(max_width=W, max_height=H, max_frames=4)
+    try:
+        c.stream_head_config(smoothing=p.get("smoothing", True), fov=p.get("fov"), camera_offset=p.get("cameraOffset", 11.5),
+                             head_position=p.get("headPosition", True))
+        c.stream_reset(0, 3)
+        n_head = 0
+        for i in range(i0, len(spec)):
+            f = mg.make_frame(*spec[i])
+            ev, heads = c.stream_step_head(np.stack([f, f, f]), 5, 1, calc_angles=bool(p.get("calcAngles", False)))
+            want = [e for e in case["steps"][i]["events"] if e["type"] == "headtrackingEvent"]
+            for k in (0, 2):
+                assert heads[k]["valid"] == (len(want) == 1), (i, k)
+                if want:
+                    for key in ("x", "y", "z"):
+                        a, b = heads[k][key], want[0][key]
+                        assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (i, key, a, b)
+                found = any(e["type"] == "headtrackrStatus" and e["status"] == "found" for e in case["steps"][i]["events"])
+                assert heads[k]["found"] == found, (i, k)
+            n_head += len(want)
+        assert n_head >= 5
+    finally:
+        c.close()
