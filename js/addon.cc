@@ -15,6 +15,10 @@
 //   streamStep(handle, rgba /* n frames, one per stream */, n, w, h, interval, minNeighbors, calcAngles)
 //        -> Array<{detection:"VJ"|"CS", x,y,width,height,angle,confidence, found, lost}>   (ht_stream_step)
 //   streamReset(handle, first, n)
+//   streamHeadConfig(handle, {smoothing, fov, cameraOffset, headPosition} | null)     (ht_stream_head_config)
+//   streamStepHead(handle, rgba, n, w, h, interval, minNeighbors, calcAngles)
+//        -> {events: [...as streamStep...], heads: Array<{valid, found, x, y, z}>}    (ht_stream_step_head)
+//   ingest(handle, rgba /* n video frames */, n, sw, sh, dw, dh) -> Uint8ClampedArray (n canvases)   (ht_ingest)
 //   destroy(handle)
 #include <node_api.h>
 
@@ -201,6 +205,104 @@ static napi_value StreamStep(napi_env env, napi_callback_info info) {
   return out;
 }
 
+static bool GetBoolProp(napi_env env, napi_value obj, const char *k, bool dflt) {
+  bool has = false; napi_value v; bool out = dflt;
+  if (napi_has_named_property(env, obj, k, &has) == napi_ok && has && napi_get_named_property(env, obj, k, &v) == napi_ok) napi_get_value_bool(env, v, &out);
+  return out;
+}
+static double GetNumProp(napi_env env, napi_value obj, const char *k, double dflt) {
+  bool has = false; napi_value v; double out = dflt;
+  if (napi_has_named_property(env, obj, k, &has) == napi_ok && has && napi_get_named_property(env, obj, k, &v) == napi_ok) napi_get_value_double(env, v, &out);
+  return out;
+}
+
+// headtrackr.Tracker's {smoothing, fov, cameraOffset, headPosition} (src/main.js:35-56) for the GPU head epilogue
+static napi_value StreamHeadConfig(napi_env env, napi_callback_info info) {
+  size_t argc = 2;
+  napi_value argv[2];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  ht_ctx *ctx = Ctx(env, argv[0]);
+  napi_valuetype t;
+  napi_typeof(env, argv[1], &t);
+  int rc;
+  if (t != napi_object) rc = ht_stream_head_config(ctx, nullptr);
+  else {
+    ht_head_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.smoothing = GetBoolProp(env, argv[1], "smoothing", true);
+    p.head_position = GetBoolProp(env, argv[1], "headPosition", true);
+    p.edgecorrection = 1;
+    p.alpha = 0.35;                                              // src/main.js:163
+    p.fov_deg = GetNumProp(env, argv[1], "fov", 0.0);            // <= 0: estimate (src/main.js:283-288)
+    p.camera_offset = GetNumProp(env, argv[1], "cameraOffset", 11.5);
+    p.distance_to_screen = 60.0;
+    rc = ht_stream_head_config(ctx, &p);
+  }
+  if (rc < 0) return Throw(env, ctx, rc);
+  return nullptr;
+}
+
+static napi_value StreamStepHead(napi_env env, napi_callback_info info) {
+  size_t argc = 8;
+  napi_value argv[8];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  ht_ctx *ctx = Ctx(env, argv[0]);
+  uint8_t *rgba; size_t len;
+  int32_t n, w, h, interval, min_neighbors, calc;
+  if (!GetBytes(env, argv[1], &rgba, &len)) return Throw(env, ctx, HT_ERR_ARG);
+  napi_get_value_int32(env, argv[2], &n); napi_get_value_int32(env, argv[3], &w); napi_get_value_int32(env, argv[4], &h);
+  napi_get_value_int32(env, argv[5], &interval); napi_get_value_int32(env, argv[6], &min_neighbors);
+  napi_get_value_int32(env, argv[7], &calc);
+  if (n <= 0 || len < (size_t)n * w * h * 4) return Throw(env, ctx, HT_ERR_ARG);
+  std::vector<ht_stream_event> ev((size_t)n);
+  std::vector<ht_head_event> he((size_t)n);
+  int rc = ht_stream_step_head(ctx, rgba, n, w, h, interval, min_neighbors, calc, ev.data(), he.data());
+  if (rc < 0) return Throw(env, ctx, rc);
+  napi_value out, events, heads;
+  napi_create_object(env, &out);
+  napi_create_array_with_length(env, (size_t)n, &events);
+  napi_create_array_with_length(env, (size_t)n, &heads);
+  for (int k = 0; k < n; ++k) {
+    napi_value o, s, b;
+    napi_create_object(env, &o);
+    napi_create_string_utf8(env, ev[k].detection == 2 ? "CS" : "VJ", 2, &s);
+    napi_set_named_property(env, o, "detection", s);
+    SetNum(env, o, "x", ev[k].x); SetNum(env, o, "y", ev[k].y); SetNum(env, o, "width", ev[k].width);
+    SetNum(env, o, "height", ev[k].height); SetNum(env, o, "angle", ev[k].angle); SetNum(env, o, "confidence", ev[k].confidence);
+    napi_get_boolean(env, (ev[k].status & 2) != 0, &b); napi_set_named_property(env, o, "lost", b);
+    napi_set_element(env, events, (uint32_t)k, o);
+    napi_value hobj;
+    napi_create_object(env, &hobj);
+    napi_get_boolean(env, he[k].valid != 0, &b); napi_set_named_property(env, hobj, "valid", b);
+    napi_get_boolean(env, (he[k].status & 1) != 0, &b); napi_set_named_property(env, hobj, "found", b);
+    SetNum(env, hobj, "x", he[k].x); SetNum(env, hobj, "y", he[k].y); SetNum(env, hobj, "z", he[k].z);
+    napi_set_element(env, heads, (uint32_t)k, hobj);
+  }
+  napi_set_named_property(env, out, "events", events);
+  napi_set_named_property(env, out, "heads", heads);
+  return out;
+}
+
+// canvasContext.drawImage(video, 0, 0, dw, dh) for n frames (src/main.js:170)
+static napi_value Ingest(napi_env env, napi_callback_info info) {
+  size_t argc = 7;
+  napi_value argv[7];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  ht_ctx *ctx = Ctx(env, argv[0]);
+  uint8_t *rgba; size_t len;
+  int32_t n, sw, sh, dw, dh;
+  if (!GetBytes(env, argv[1], &rgba, &len)) return Throw(env, ctx, HT_ERR_ARG);
+  napi_get_value_int32(env, argv[2], &n); napi_get_value_int32(env, argv[3], &sw); napi_get_value_int32(env, argv[4], &sh);
+  napi_get_value_int32(env, argv[5], &dw); napi_get_value_int32(env, argv[6], &dh);
+  if (n <= 0 || len < (size_t)n * sw * sh * 4) return Throw(env, ctx, HT_ERR_ARG);
+  void *data; napi_value ab, ta;
+  NAPI_OK(napi_create_arraybuffer(env, (size_t)n * dw * dh * 4, &data, &ab));
+  int rc = ht_ingest(ctx, rgba, n, sw, sh, static_cast<uint8_t *>(data), dw, dh);
+  if (rc < 0) return Throw(env, ctx, rc);
+  NAPI_OK(napi_create_typedarray(env, napi_uint8_clamped_array, (size_t)n * dw * dh * 4, ab, 0, &ta));
+  return ta;
+}
+
 static napi_value StreamReset(napi_env env, napi_callback_info info) {
   size_t argc = 3;
   napi_value argv[3];
@@ -254,6 +356,9 @@ static napi_value Init(napi_env env, napi_value exports) {
       {"track", nullptr, Track, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"streamStep", nullptr, StreamStep, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"streamReset", nullptr, StreamReset, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"streamHeadConfig", nullptr, StreamHeadConfig, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"streamStepHead", nullptr, StreamStepHead, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"ingest", nullptr, Ingest, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"whitebalance", nullptr, Whitebalance, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"backprojection", nullptr, Backprojection, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
