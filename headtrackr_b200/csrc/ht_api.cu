@@ -401,7 +401,7 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
         return conflicts;
       };
       for (int lane = 0; lane < 32; ++lane) {
-        LateFeat lf{};
+        struct { uint16_t off[10]; int32_t a_int; } lf;   // scheduled in ConstCascade's 16-bit offsets, encoded at the end
         for (int q = 0; q < 10; ++q) lf.off[q] = 0xFFFF;
         lf.a_int = 0;
         if (!rem.empty()) {
@@ -420,7 +420,10 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
           lf.a_int = (int32_t)a_int[k];
           rem.erase(rem.begin() + (long)pick);
         }
-        hc.late.push_back(lf);
+        LateFeat rec{};
+        for (int q = 0; q < 10; ++q) rec.off[q] = late_encode(lf.off[q]);
+        rec.a_int = lf.a_int;
+        hc.late.push_back(rec);
       }
     }
   }
@@ -430,9 +433,9 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   hc.n_sched = hc.late.size();
   for (int k = 0; k < hc.n_features; ++k) {
     LateFeat lf{};
-    for (int q = 0; q < 10; ++q) lf.off[q] = 0xFFFF;
-    for (int q = 0; q < (cc.np_nn[k] & 15); ++q) lf.off[q] = cc.off[k][q];
-    for (int q = 0; q < (cc.np_nn[k] >> 4); ++q) lf.off[5 + q] = cc.off[k][5 + q];
+    for (int q = 0; q < 10; ++q) lf.off[q] = LATE_UNUSED;
+    for (int q = 0; q < (cc.np_nn[k] & 15); ++q) lf.off[q] = late_encode(cc.off[k][q]);
+    for (int q = 0; q < (cc.np_nn[k] >> 4); ++q) lf.off[5 + q] = late_encode(cc.off[k][5 + q]);
     lf.a_int = (int32_t)a_int[k];
     hc.late.push_back(lf);
   }
@@ -1983,8 +1986,8 @@ extern "C" int ht_selftest_cascade(const void *blob, size_t blob_len, int w, int
               const LateFeat &lf = hc.late[(size_t)ch * 32 + lane];
               unsigned pm = 255u, nm = 0u;
               for (int s = 0; s < 10; ++s) {
-                if (lf.off[s] == 0xFFFF) continue;
-                const unsigned v8 = px_at(tA, tB, lf.off[s]);
+                if (lf.off[s] == LATE_UNUSED) continue;
+                const unsigned v8 = px_at(tA, tB, late_decode(lf.off[s]));
                 if (s < 5) pm = std::min(pm, v8); else nm = std::max(nm, v8);
               }
               acc += (pm > nm) ? (long long)lf.a_int : -(long long)lf.a_int;
@@ -2040,7 +2043,7 @@ int main(int argc, char **argv) {
         for (int &v : bank_word) v = -1;
         bool any = false;
         for (int lane = 0; lane < 32; ++lane) {
-          const uint16_t o = hc.late[(size_t)ch * 32 + lane].off[s];
+          const uint16_t o = late_decode(hc.late[(size_t)ch * 32 + lane].off[s]);
           if (o == 0xFFFF) continue;
           any = true; ++used_slots;
           const int word = o & 0x7fff;
@@ -2052,8 +2055,8 @@ int main(int argc, char **argv) {
       for (int lane = 0; lane < 32; ++lane) {
         const LateFeat &lf = hc.late[(size_t)ch * 32 + lane];
         std::vector<uint16_t> p, n;
-        for (int s = 0; s < 5; ++s) if (lf.off[s] != 0xFFFF) p.push_back(lf.off[s]);
-        for (int s = 5; s < 10; ++s) if (lf.off[s] != 0xFFFF) n.push_back(lf.off[s]);
+        for (int s = 0; s < 5; ++s) if (lf.off[s] != LATE_UNUSED) p.push_back(late_decode(lf.off[s]));
+        for (int s = 5; s < 10; ++s) if (lf.off[s] != LATE_UNUSED) n.push_back(late_decode(lf.off[s]));
         if (p.empty() && n.empty()) { if (lf.a_int != 0) ++bad; continue; }
         std::sort(p.begin(), p.end()); std::sort(n.begin(), n.end());
         int match = -1;

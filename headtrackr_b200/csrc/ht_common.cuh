@@ -157,11 +157,23 @@ struct ConstCascade {
 // that within a chunk the 32 offsets of each load slot fall into different shared-memory banks (all lanes add the
 // same per-window base, so conflicts depend only on the offsets).  Unused slots hold 0xFFFF and cost no access.
 struct alignas(16) LateFeat {
-  uint16_t off[10];  // slots 0-4: p points, 5-9: n points (ConstCascade::off encoding); 0xFFFF = unused
+  // slots 0-4: p points, 5-9: n points.  An entry is the BYTE offset of the point (4 x point_word) with bit 31 set
+  // when it is relative to baseB, or 0xFFFFFFFF when the slot is unused: the kernel forms the address with one
+  // select and one add, `(int(o) < 0 ? sB - 2^31 : sA) + o` (round 2's first version unpacked 16-bit word offsets:
+  // 9 instructions per slot, 25 % of the kernel's instructions).
+  uint32_t off[10];
   int32_t a_int;     // alpha[2k+1] * 1e8 (0 for the padding records of a stage's last chunk)
-  uint32_t pad_[2];
+  uint32_t pad_;
 };
-static_assert(sizeof(LateFeat) == 32, "LateFeat is two 16-byte loads");
+static_assert(sizeof(LateFeat) == 48, "LateFeat is three 16-byte loads");
+constexpr uint32_t LATE_UNUSED = 0xFFFFFFFFu;
+// ConstCascade::off encoding (u16: word offset, bit 15 = baseB, 0xFFFF = unused) <-> LateFeat::off encoding
+__host__ __device__ constexpr uint32_t late_encode(uint16_t o) {
+  return o == 0xFFFF ? LATE_UNUSED : (uint32_t)(o & 0x7fffu) * 4u | ((o & 0x8000u) ? 0x80000000u : 0u);
+}
+__host__ __device__ constexpr uint16_t late_decode(uint32_t o) {
+  return o == LATE_UNUSED ? (uint16_t)0xFFFF : (uint16_t)(((o & 0x7fffffffu) >> 2) | ((o >> 31) ? 0x8000u : 0u));
+}
 static_assert(sizeof(ConstCascade) <= 65536 - 1024, "cascade must fit the constant bank");
 
 struct DevPlan {  // pointers into one device allocation

@@ -440,16 +440,15 @@ __device__ __forceinline__ unsigned lds_u8_if(unsigned saddr, bool p, unsigned d
   return v;
 }
 
-// One feature record (LateFeat) for one window, evaluated by one lane: min(p points) > max(n points).
-__device__ __forceinline__ bool feat_fires(unsigned sA, unsigned sB, const uint4 a, const uint4 b) {
-  // off[0..9] = a.x lo, a.x hi, a.y lo, a.y hi, a.z lo (p) | a.z hi, a.w lo, a.w hi, b.x lo, b.x hi (n)
-  const unsigned o[10] = {a.x & 0xffffu, a.x >> 16, a.y & 0xffffu, a.y >> 16, a.z & 0xffffu,
-                          a.z >> 16, a.w & 0xffffu, a.w >> 16, b.x & 0xffffu, b.x >> 16};
+// One feature record (LateFeat, three 16-byte loads) for one window, evaluated by one lane: min(p) > max(n).
+// sBm = sB - 2^31: an entry with bit 31 set (relative to baseB) then needs no masking.
+__device__ __forceinline__ bool feat_fires(unsigned sA, unsigned sBm, const uint4 a, const uint4 b, const uint4 c) {
+  const unsigned o[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
   unsigned vv[10];
 #pragma unroll
   for (int s = 0; s < 10; ++s) {
-    const unsigned addr = ((o[s] & 0x8000u) ? sB : sA) + 4u * (o[s] & 0x7fffu);
-    vv[s] = lds_u8_if(addr, o[s] != 0xffffu, s < 5 ? 255u : 0u);   // unused slots: neutral element, no bank traffic
+    const unsigned addr = ((int)o[s] < 0 ? sBm : sA) + o[s];
+    vv[s] = lds_u8_if(addr, o[s] != LATE_UNUSED, s < 5 ? 255u : 0u);   // unused slots: neutral element, no bank traffic
   }
   const unsigned pm = __vimin3_u32(__vimin3_u32(vv[0], vv[1], vv[2]), vv[3], vv[4]);
   const unsigned nm = __vimax3_u32(__vimax3_u32(vv[5], vv[6], vv[7]), vv[8], vv[9]);
@@ -461,7 +460,7 @@ __device__ __forceinline__ bool feat_fires(unsigned sA, unsigned sB, const uint4
 // lane then performs the same sequential chain of fp64 adds in feature order (uniform alpha reads).  Round 2's
 // first version ran stage_sum_ordered on every lane: 14 k instructions of dependent loads per detection, the
 // straggler that set the duration of every CTA with a face in it.
-__device__ __forceinline__ double stage_sum_ordered_warp(unsigned sA, unsigned sB, int j, const LateFeat *__restrict__ feat_orig,
+__device__ __forceinline__ double stage_sum_ordered_warp(unsigned sA, unsigned sBm, int j, const LateFeat *__restrict__ feat_orig,
                                                          int lane) {
   const int first = c_casc.stage[j].first, count = c_casc.stage[j].count;
   double sum = 0.0;
@@ -469,7 +468,7 @@ __device__ __forceinline__ double stage_sum_ordered_warp(unsigned sA, unsigned s
     bool fired = false;
     if (base + lane < count) {
       const uint4 *fp = reinterpret_cast<const uint4 *>(feat_orig + first + base + lane);
-      fired = feat_fires(sA, sB, __ldg(fp), __ldg(fp + 1));
+      fired = feat_fires(sA, sBm, __ldg(fp), __ldg(fp + 1), __ldg(fp + 2));
     }
     const unsigned mask = __ballot_sync(0xffffffffu, fired);
     const int n = min(32, count - base);
@@ -808,26 +807,26 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
       const int b = nth_set_bit(m_in, c, wdx - __shfl_sync(0xffffffffu, excl, c));
       const uint8_t *tA, *tB;
       bases(c, b, tA, tB);
-      const unsigned sA = (unsigned)__cvta_generic_to_shared(tA), sB = (unsigned)__cvta_generic_to_shared(tB);
+      const unsigned sA = (unsigned)__cvta_generic_to_shared(tA), sBm = (unsigned)__cvta_generic_to_shared(tB) - 0x80000000u;
       bool pass = true;
       for (int j = late_first; j < c_casc.n_stages && pass; ++j) {
         long long acc = 0;
         const int c0 = late_chunk0[j], c1 = late_chunk0[j + 1];
         for (int ch = c0; ch < c1; ++ch) {
           const uint4 *fp = reinterpret_cast<const uint4 *>(late + (size_t)ch * 32 + lane);
-          const uint4 a = __ldg(fp), bb = __ldg(fp + 1);
-          const int ai = (int)bb.y;                      // alpha_int (0 for padding records)
-          acc += feat_fires(sA, sB, a, bb) ? (long long)ai : -(long long)ai;
+          const uint4 a = __ldg(fp), bb = __ldg(fp + 1), cc = __ldg(fp + 2);
+          const int ai = (int)cc.z;                      // alpha_int (0 for padding records)
+          acc += feat_fires(sA, sBm, a, bb, cc) ? (long long)ai : -(long long)ai;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         const long long thr = c_casc.thr_int[j];
         if (acc == thr || (force_ties & 2))             // exact tie: the reference's ordered adds decide
-          pass = !(stage_sum_ordered_warp(sA, sB, j, feat_orig, lane) < c_casc.stage[j].threshold);
+          pass = !(stage_sum_ordered_warp(sA, sBm, j, feat_orig, lane) < c_casc.stage[j].threshold);
         else pass = acc > thr;
       }
       if (pass) {  // confidence = ordered fp64 sum of the last stage
-        const double s = stage_sum_ordered_warp(sA, sB, c_casc.n_stages - 1, feat_orig, lane);
+        const double s = stage_sum_ordered_warp(sA, sBm, c_casc.n_stages - 1, feat_orig, lane);
         if (lane == 0) emit(c, b, s);
       }
     }
