@@ -32,6 +32,7 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = Context(max_width=W, max_height=H, max_frames=n, device=0, stream=stream.cuda_stream)
+    ctx.set_track_memo(os.environ.get("TIMELINE_MEMO", "0") == "1")   # strict (bench headline) unless asked
     d = torch.from_numpy(batch).cuda()
     K = ctx.K
     outs = (torch.zeros(n * K * 12, dtype=torch.int32, device="cuda"), torch.zeros(n, dtype=torch.int32, device="cuda"),
