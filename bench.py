@@ -321,19 +321,24 @@ def run_ours(args, cfg):
     torch.cuda.set_stream(stream)
     ctx = Context(max_width=W, max_height=H, max_frames=B, device=local, stream=stream.cuda_stream)
     K = ctx.K
-    d_rects = torch.zeros((B, K, 6), dtype=torch.float64, device="cuda")      # ht_rect = 48 B
-    d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
-    d_found = torch.zeros((B,), dtype=torch.int32, device="cuda")
-    d_objs = torch.zeros((B, 6), dtype=torch.int32, device="cuda")            # ht_trackobj = 24 B
-    d_wins = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+    # Pipelined steps (ht_set_pipeline, default for the detect+track workload): the tracking of step s stays on the
+    # library's second stream and runs under the detection of step s+1.  Two output sets alternate so that the records of
+    # step s-1 can be gathered while step s is in flight; the last step is joined inside the timed region.
+    pipe = bool(args.pipeline) and workload == "detect_track30"
+    n_sets = 2 if pipe else 1
+    d_rects = [torch.zeros((B, K, 6), dtype=torch.float64, device="cuda") for _ in range(n_sets)]      # ht_rect = 48 B
+    d_counts = [torch.zeros((B,), dtype=torch.int32, device="cuda") for _ in range(n_sets)]
+    d_found = [torch.zeros((B,), dtype=torch.int32, device="cuda") for _ in range(n_sets)]
+    d_objs = [torch.zeros((B, 6), dtype=torch.int32, device="cuda") for _ in range(n_sets)]            # ht_trackobj = 24 B
+    d_wins = [torch.zeros((B, 4), dtype=torch.int32, device="cuda") for _ in range(n_sets)]
     d_events = torch.zeros((T, B, 56), dtype=torch.uint8, device="cuda")      # ht_stream_event = 56 B
     # the record every rank contributes to the result gather: one fixed-size row per frame (per stream and frame)
     if workload in ("detect", "detect720"):
-        rec_src, rec_shape, rec_dtype = d_counts, (B,), torch.int32
+        rec_srcs, rec_shape, rec_dtype = d_counts, (B,), torch.int32
     elif streams:
-        rec_src, rec_shape, rec_dtype = d_events, (T, B, 56), torch.uint8
+        rec_srcs, rec_shape, rec_dtype = [d_events], (T, B, 56), torch.uint8
     else:
-        rec_src, rec_shape, rec_dtype = d_objs, (B, 6), torch.int32
+        rec_srcs, rec_shape, rec_dtype = d_objs, (B, 6), torch.int32
     # The gather is double-buffered and runs on its own stream: the records of step s are copied aside and gathered
     # over NCCL while step s+1 is computing, so a slow rank no longer stalls the others on every step.
     gathered = [torch.zeros((world,) + rec_shape, dtype=rec_dtype, device="cuda") for _ in range(2)] if world > 1 else None
@@ -341,50 +346,70 @@ def run_ours(args, cfg):
     comm_stream = torch.cuda.Stream() if world > 1 else None
     gather_events = []
     step_no = [0]
+    gather_no = [0]
+    ungathered = [None]         # (pipelined) output set whose records have not been gathered yet
 
-    def compute():
+    def compute(o=0):
         if workload in ("detect", "detect720"):
-            ctx.detect_raw(dev, interval, 1, out_rects=d_rects, out_counts=d_counts)
+            ctx.detect_raw(dev, interval, 1, out_rects=d_rects[0], out_counts=d_counts[0])
         elif streams:
             for t in range(T):
                 ctx.stream_step(dev[t], interval, 1, calc_angles=False, out_events=d_events[t])
         else:
             ctx.detect_track(dev, interval, 1, calc_angles=False, n_calls=track_calls,
-                             outputs=(d_rects, d_counts, d_found, d_objs, d_wins))
+                             outputs=(d_rects[o], d_counts[o], d_found[o], d_objs[o], d_wins[o]))
 
     pending = [None, None]      # completion event of the gather that last used staging buffer b
 
-    def step(time_gather=False):
-        b = step_no[0] & 1
-        if world > 1 and pending[b] is not None:
+    def gather(src, time_gather=False):
+        # the only collective: fixed-size result records gathered over NCCL/NVLink
+        b = gather_no[0] & 1
+        gather_no[0] += 1
+        if pending[b] is not None:
             stream.wait_event(pending[b])        # staged[b] / gathered[b] are free again
-        compute()
-        if world > 1:   # the only collective: fixed-size result records gathered over NCCL/NVLink
-            staged[b].copy_(rec_src, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(stream)
-            comm_stream.wait_event(done)
-            with torch.cuda.stream(comm_stream):
-                if time_gather:
-                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    g0.record(comm_stream)
-                dist.all_gather_into_tensor(gathered[b], staged[b])
-                if time_gather:
-                    g1.record(comm_stream)
-                    gather_events.append((g0, g1))
-                fin = torch.cuda.Event()
-                fin.record(comm_stream)
-            pending[b] = fin
+        staged[b].copy_(src, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(stream)
+        comm_stream.wait_event(done)
+        with torch.cuda.stream(comm_stream):
+            if time_gather:
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(comm_stream)
+            dist.all_gather_into_tensor(gathered[b], staged[b])
+            if time_gather:
+                g1.record(comm_stream)
+                gather_events.append((g0, g1))
+            fin = torch.cuda.Event()
+            fin.record(comm_stream)
+        pending[b] = fin
+
+    def step(time_gather=False):
+        o = step_no[0] % n_sets
+        compute(o)
+        if world > 1:
+            if not pipe:
+                gather(rec_srcs[0], time_gather)
+            else:
+                # everything enqueued after compute() is ordered behind the tracking of the PREVIOUS step (the library
+                # makes k_group of this step wait for it): its records are complete, and this step writes the other set
+                if ungathered[0] is not None:
+                    gather(rec_srcs[ungathered[0]], time_gather)
+                ungathered[0] = o
         step_no[0] += 1
 
     def drain():
+        if pipe:
+            ctx.join()          # the context's stream waits for the last step's tracking (no host wait)
+            if world > 1 and ungathered[0] is not None:
+                gather(rec_srcs[ungathered[0]], True)
+                ungathered[0] = None
         for e in pending:
             if e is not None:
                 stream.wait_event(e)
 
     def barrier():
+        drain()
         if world > 1:
-            drain()
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -395,6 +420,7 @@ def run_ours(args, cfg):
     # (ht_set_track_memo) - identical results, far fewer passes when 30 calls hit one frame; that
     # mode is measured separately below and reported under "memo", never as the headline.
     ctx.set_track_memo(False)
+    ctx.set_pipeline(pipe)
     if streams:
         ctx.stream_reset(0, B)
     # nvidia-smi needs a few hundred ms before its first sample: start it before the warm-up so that it is sampling
@@ -438,7 +464,7 @@ def run_ours(args, cfg):
     #      rank r's frames - rank 0 regenerates the first frames of every other rank and runs them itself ----
     shard_check = None
     if world > 1 and not streams:
-        g = gathered[(step_no[0] - 1) & 1]
+        g = gathered[(gather_no[0] - 1) & 1]
         torch.cuda.synchronize()
         if rank == 0:
             n_chk, bad = 8, 0
@@ -565,7 +591,9 @@ def run_ours(args, cfg):
                                   if frames_per_step * W * H * 4 > 126e6 else "L2 flushed by the step itself: every step streams "
                                   f"{frames_per_step * W * H * 4 / 1e6:.0f} MB of frames and re-writes the pyramid arena",
                                unique_frames=N_UNIQUE if not streams else B * T,
-                               track_memo="off (strict: every pass re-summed)"),
+                               track_memo="off (strict: every pass re-summed)",
+                               pipeline=("on: the tracking of step s runs on the library's second stream under the detection of "
+                                         "step s+1 (ht_set_pipeline); the last step is joined inside the timed region") if pipe else "off"),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": args.steps},
                 "gpu_launches": int(launches),
@@ -625,6 +653,8 @@ def main():
     ap.add_argument("--interval", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=int(os.environ.get("HT_BENCH_PIPELINE", "1")),
+                    help="detect+track: 1 = pipelined steps (ht_set_pipeline), 0 = every step joins its own tracking")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload], workload=args.workload, stream_frames=args.stream_frames)
     for k, v in (("width", args.width), ("height", args.height), ("interval", args.interval),

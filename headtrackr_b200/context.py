@@ -272,6 +272,15 @@ class Context:
         """Re-use the moments of windows already summed in the same launch (default on; results are identical)."""
         self._check(self._L.ht_set_track_memo(self._h, int(bool(enable))))
 
+    def set_pipeline(self, enable=True):
+        """Pipelined batches: a detect_track call with device frames and device outputs leaves its tracking on a second
+        stream, where it runs under the next call's detection (identical results; read them after sync() / join())."""
+        self._check(self._L.ht_set_pipeline(self._h, int(bool(enable))))
+
+    def join(self):
+        """Stream-level join of a pipelined call's tracking (no host wait)."""
+        self._check(self._L.ht_join(self._h))
+
     def debug_set_exactness(self, flags):
         """Force the exactness fallbacks (bit 0: generated cascade stages, 1: late stages, 2: mean-shift moments)."""
         self._check(self._L.ht_debug_set_exactness(self._h, int(flags)))

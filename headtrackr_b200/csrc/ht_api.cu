@@ -496,6 +496,16 @@ struct ht_ctx {
   cudaStream_t aux_stream = nullptr;        // tracking of part p overlaps the detection of part p+1 (ht_detect_track)
   cudaEvent_t aux_done = nullptr, part_events[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned part_seq = 0;
+  // ht_set_pipeline: ht_detect_track on device-resident frames with device outputs leaves the tracking of call s on
+  // the aux stream and returns; it runs under the detection of call s+1 (k_track is a latency chain that leaves
+  // most issue slots idle, the detection kernels are throughput-bound).  What the two touch in common is double
+  // buffered by call parity (bin planes, current-frame histograms) or ordered by an event (the caller's rectangle
+  // arrays: k_group of call s+1 waits for the tracking of call s).  Every other entry point joins first.
+  int pipeline = 0;
+  bool aux_pending = false;                 // work on aux_stream that the context's stream has not waited for yet
+  cudaEvent_t pipe_detect_done = nullptr;
+  int pipe_parity = 0;
+  size_t bins_off = 0, hist_off = 0;        // element offsets of the active bin-plane / histogram buffer (parity)
   // Tracking of part p on a second stream while part p+1 is uploaded / detected (ht_detect_track).  Default (-1):
   // only for HOST frames, where the batch arrives at PCIe speed and the GPU has idle time to fill - measured e2e
   // 37.6k vs 33.0k frames/s with 4 parts (8 parts 36.8k, 16 parts 28.6k).  For device-resident frames it was
@@ -539,8 +549,9 @@ struct ht_ctx {
   int track_mid_div = 16, track_mid_cluster = 4;  // HT_TRACK_MID=div[,cluster]: the next n/16 costliest streams on clusters of 4
                                                   // (measured 4.12 -> 3.40 ms per 1024 x 30 calls; div 8: 3.55)
   int track_light_div = 0, track_light_nt = 256;  // HT_TRACK_LIGHT=div[,threads]: the cheapest n/div streams on single CTAs
-  cudaStream_t tier_stream[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t tier_done[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t tier_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // heavy, mid, light, rest (side 3: when tiers are on)
+  cudaEvent_t tier_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  int track_prio = 1;                       // HT_TRACK_PRIO=0: tier streams without priorities, the default tier on the context's stream
   cudaStream_t sched_stream = nullptr;
   cudaEvent_t sched_ready = nullptr, sched_done = nullptr;
   int track_bail_area = 0;                  // >0: two-phase k_track; phase A hands streams with a larger window (px) to phase B
@@ -568,6 +579,17 @@ bool is_device_ptr(const void *p) {
   cudaPointerAttributes a{};
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// (ht_set_pipeline) order everything still running on the aux stream before later work on the context's stream, and go
+// back to the first bin-plane / histogram buffer.  Called by every entry point except the pipelined ht_detect_track.
+int join_aux(ht_ctx *ctx) {
+  if (ctx->aux_pending) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_done, 0));
+    ctx->aux_pending = false;
+  }
+  ctx->bins_off = 0; ctx->hist_off = 0; ctx->pipe_parity = 0;
+  return HT_OK;
 }
 
 int get_plan(ht_ctx *ctx, int w, int h, int interval, Plan **out) {
@@ -599,8 +621,11 @@ int device_frames(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, const u
   return HT_OK;
 }
 
-int check_batch(ht_ctx *ctx, int n) {
+// argument check of every batched entry point; it also joins a pipelined call's tracking (ht_set_pipeline) unless the
+// caller is the pipelined path itself
+int check_batch(ht_ctx *ctx, int n, bool join = true) {
   if (n <= 0 || n > ctx->cfg.max_frames) return ctx->fail(HT_ERR_ARG, "n=%d outside [1,%d]", n, ctx->cfg.max_frames);
+  if (join) return join_aux(ctx);
   return HT_OK;
 }
 
@@ -625,7 +650,7 @@ int ensure_tracker_buffers(ht_ctx *ctx) {
   const size_t mf = (size_t)ctx->cfg.max_frames;
   if (!ctx->model_hist.p) {
     CK(ctx->model_hist.reserve(mf * 4096 * sizeof(uint32_t)));
-    CK(ctx->cur_hist.reserve(mf * 4096 * sizeof(uint32_t)));
+    CK(ctx->cur_hist.reserve(2 * mf * 4096 * sizeof(uint32_t)));   // two parities (ht_set_pipeline)
     CK(ctx->track_state.reserve(mf * sizeof(TrackState)));
     CK(cudaMemsetAsync(ctx->track_state.p, 0, mf * sizeof(TrackState), ctx->stream));
     CK(ctx->d_rects.reserve(mf * 4 * sizeof(int32_t)));
@@ -772,12 +797,22 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
       take(ctx->track_heavy_div, ctx->track_heavy_cluster, 256, 0);
       take(ctx->track_mid_div, ctx->track_mid_cluster, 256, 1);
       const int n_light = (ctx->track_light_div > 0) ? std::min(left, n / ctx->track_light_div) : 0;
-      if (left - n_light > 0) tiers[n_tiers++] = Tier{left - n_light, c, nt, -1};
+      // Round 2, call 8 timeline: with the default tier on the context's own stream (no event wait) its 1,888 CTAs
+      // reached the GPU first and filled every slot with ITS costliest streams; the heavy and middle tiers - the
+      // longest chains of the launch - started 1.4 ms late and the launch ended at 1.4 + 2.3 ms.  Now every tier sits
+      // on a side stream behind the same event, submitted costliest tier first, and the side streams carry
+      // descending priorities (heavy > mid > rest > light), so a free slot always goes to the longest pending chain.
+      const bool rest_side = ctx->track_prio != 0 && (ctx->track_heavy_div > 0 || ctx->track_mid_div > 0);
+      if (left - n_light > 0) tiers[n_tiers++] = Tier{left - n_light, c, nt, rest_side ? 3 : -1};
       if (n_light > 0) tiers[n_tiers++] = Tier{n_light, 1, ctx->track_light_nt, 2};
       if (n_tiers > 1) {
-        for (int t = 0; t < 3; ++t)
+        int prio_least = 0, prio_greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));   // numerically lower = more urgent
+        for (int t = 0; t < 4; ++t)
           if (!ctx->tier_stream[t]) {
-            CK(cudaStreamCreateWithFlags(&ctx->tier_stream[t], cudaStreamNonBlocking));
+            const int rank = (t == 0) ? 0 : (t == 1 ? 1 : (t == 3 ? 2 : 3));   // heavy, mid, rest, light
+            const int prio = ctx->track_prio ? std::min(prio_least, prio_greatest + rank) : prio_least;
+            CK(cudaStreamCreateWithPriority(&ctx->tier_stream[t], cudaStreamNonBlocking, prio));
             CK(cudaEventCreateWithFlags(&ctx->tier_done[t], cudaEventDisableTiming));
           }
         if (!ctx->sched_ready) CK(cudaEventCreateWithFlags(&ctx->sched_ready, cudaEventDisableTiming));
@@ -899,7 +934,8 @@ struct HistOut {
 // ctx->detect_pipe the gray + pyramid kernels of wave w+1 run on a second stream (and a second arena) under the
 // cascade of wave w.
 int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n, int min_neighbors, Rect *d_rects_batch,
-               int32_t *d_counts_batch, HistOut ho = HistOut{nullptr, nullptr}, const uint8_t *quad_mask = nullptr) {
+               int32_t *d_counts_batch, HistOut ho = HistOut{nullptr, nullptr}, const uint8_t *quad_mask = nullptr,
+               cudaEvent_t before_group = nullptr) {
   cudaStream_t st = ctx->stream;
   const int w = P->w, h = P->h;
   const size_t frame_bytes = (size_t)w * h * 4;
@@ -996,6 +1032,7 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
     ctx->last_wave_arena = arena;
   }
   // K4 sort + group
+  if (before_group) CK(cudaStreamWaitEvent(st, before_group, 0));   // (pipelined calls) the previous call's tracking still reads the rectangle arrays
   ctx->prof_begin(HT_PROF_GROUP);
   k_group<<<(n + 3) / 4, 128, 0, st>>>(P->dplan, n, ctx->raw_keys.as<uint32_t>() + (size_t)f0 * ctx->raw_cap,
                                        ctx->raw_conf.as<double>() + (size_t)f0 * ctx->raw_cap,
@@ -1027,10 +1064,10 @@ int run_track_from_detect(ht_ctx *ctx, const uint8_t *d_rgba_batch, int w, int h
   ctx->launches += 2;
   if (n_calls > 0) {
     // the current-frame histograms and the bin plane were produced by the gray pass of run_detect (one frame read)
-    uint16_t *bins = ctx->bins.as<uint16_t>() + (size_t)f0 * w * h;
+    uint16_t *bins = ctx->bins.as<uint16_t>() + ctx->bins_off + (size_t)f0 * w * h;
     ctx->prof_begin(HT_PROF_TRACK);
     int rc = launch_track(ctx, n, f0, bins, w, h, nullptr, ctx->model_hist.as<uint32_t>() + (size_t)f0 * 4096,
-                      ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096, ctx->track_state.as<TrackState>() + f0, n_calls,
+                      ctx->cur_hist.as<uint32_t>() + ctx->hist_off + (size_t)f0 * 4096, ctx->track_state.as<TrackState>() + f0, n_calls,
                       d_objs + 6 * (size_t)f0, d_win ? d_win + 4 * (size_t)f0 : nullptr, ctx->d_flags.as<int32_t>() + 2);
     if (rc != HT_OK) return rc;
     ctx->prof_end();
@@ -1144,6 +1181,8 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
   if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
   if (const char *ov = getenv("HT_OVERLAP")) { c->overlap_track = atoi(ov) != 0 ? 1 : 0; c->overlap_parts = atoi(ov); }
   if (const char *hc2 = getenv("HT_H2D_CHUNK")) c->h2d_chunk = std::max(1, atoi(hc2));
+  if (const char *pl = getenv("HT_PIPELINE")) c->pipeline = atoi(pl) != 0 ? 1 : 0;
+  if (const char *tp = getenv("HT_TRACK_PRIO")) c->track_prio = atoi(tp) != 0 ? 1 : 0;
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
   // the cascade image is copied into __constant__ memory lazily by run_detect; the late-stage table lives in HBM
   if (c->d_casc.reserve(c->hc.late.size() * sizeof(LateFeat)) != cudaSuccess ||
@@ -1174,6 +1213,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
 void ht_destroy(ht_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->plans) kv.second->dev.release();
   DevBuf *bufs[] = {&ctx->d_casc, &ctx->arena, &ctx->d_frames, &ctx->raw_keys, &ctx->raw_conf, &ctx->raw_count, &ctx->sorted,
@@ -1190,7 +1230,7 @@ void ht_destroy(ht_ctx *ctx) {
   if (ctx->pipe_start) cudaEventDestroy(ctx->pipe_start);
   for (cudaEvent_t e : ctx->pipe_events) if (e) cudaEventDestroy(e);
   if (ctx->sched_stream) cudaStreamDestroy(ctx->sched_stream);
-  for (int t = 0; t < 3; ++t) {
+  for (int t = 0; t < 4; ++t) {
     if (ctx->tier_stream[t]) cudaStreamDestroy(ctx->tier_stream[t]);
     if (ctx->tier_done[t]) cudaEventDestroy(ctx->tier_done[t]);
   }
@@ -1198,6 +1238,7 @@ void ht_destroy(ht_ctx *ctx) {
   if (ctx->sched_done) cudaEventDestroy(ctx->sched_done);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->aux_done) cudaEventDestroy(ctx->aux_done);
+  if (ctx->pipe_detect_done) cudaEventDestroy(ctx->pipe_detect_done);
   for (cudaEvent_t e : ctx->part_events) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1205,6 +1246,7 @@ void ht_destroy(ht_ctx *ctx) {
 
 int ht_sync(ht_ctx *ctx) {
   if (!ctx) return HT_ERR_ARG;
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
   CK(cudaStreamSynchronize(ctx->stream));
   int32_t flags[2] = {0, 0};
   CK(cudaMemcpy(flags, ctx->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost));
@@ -1353,7 +1395,14 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   if (!ctx) return HT_ERR_ARG;
   if (!out_rects || !out_counts || !out_objs) return ctx->fail(HT_ERR_ARG, "output pointers are NULL");
   if (n_calls < 0) return ctx->fail(HT_ERR_ARG, "n_calls must be >= 0");
-  int rc = check_batch(ctx, n);
+  const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
+  const bool found_dev = out_found && is_device_ptr(out_found), objs_dev = is_device_ptr(out_objs);
+  const bool win_dev = out_windows && is_device_ptr(out_windows);
+  // pipelined call (ht_set_pipeline): everything stays on the device, so nothing forces this call to wait for its own
+  // tracking - it is left on the aux stream and runs under the next call's detection
+  const bool deferred = ctx->pipeline > 0 && n_calls > 0 && rgba && is_device_ptr(rgba) && rects_dev && counts_dev && objs_dev &&
+                        (!out_found || found_dev) && (!out_windows || win_dev);
+  int rc = check_batch(ctx, n, !deferred);
   if (rc != HT_OK) return rc;
   CK(cudaSetDevice(ctx->cfg.device));
   Plan *P = nullptr;
@@ -1361,11 +1410,44 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   if (rc != HT_OK) return rc;
   rc = ensure_tracker_buffers(ctx);
   if (rc != HT_OK) return rc;
-  if (n_calls > 0) CK(ctx->bins.reserve((size_t)n * w * h * sizeof(uint16_t)));
   cudaStream_t st = ctx->stream;
-  const bool rects_dev = is_device_ptr(out_rects), counts_dev = is_device_ptr(out_counts);
-  const bool found_dev = out_found && is_device_ptr(out_found), objs_dev = is_device_ptr(out_objs);
-  const bool win_dev = out_windows && is_device_ptr(out_windows);
+  if (deferred) {
+    const size_t plane_elems = (size_t)ctx->cfg.max_frames * w * h;     // one parity's bin planes
+    if (ctx->bins.cap < 2 * plane_elems * sizeof(uint16_t)) {
+      if (ctx->aux_stream) CK(cudaStreamSynchronize(ctx->aux_stream));   // the buffer about to be replaced may still be read
+      CK(cudaStreamSynchronize(st));
+      CK(ctx->bins.reserve(2 * plane_elems * sizeof(uint16_t)));
+    }
+    if (!ctx->aux_stream) {
+      int prio_least = 0, prio_greatest = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+      CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_greatest));
+      CK(cudaEventCreateWithFlags(&ctx->aux_done, cudaEventDisableTiming));
+      for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->part_events[i], cudaEventDisableTiming));
+    }
+    if (!ctx->pipe_detect_done) CK(cudaEventCreateWithFlags(&ctx->pipe_detect_done, cudaEventDisableTiming));
+    ctx->pipe_parity ^= 1;
+    ctx->bins_off = (size_t)ctx->pipe_parity * plane_elems;
+    ctx->hist_off = (size_t)ctx->pipe_parity * (size_t)ctx->cfg.max_frames * 4096;
+    Rect *dr = reinterpret_cast<Rect *>(out_rects);
+    rc = run_detect(ctx, P, rgba, 0, n, min_neighbors, dr, out_counts,
+                    HistOut{ctx->cur_hist.as<uint32_t>() + ctx->hist_off, ctx->bins.as<uint16_t>() + ctx->bins_off}, nullptr,
+                    ctx->aux_pending ? ctx->aux_done : nullptr);
+    if (rc != HT_OK) return rc;
+    CK(cudaEventRecord(ctx->pipe_detect_done, st));
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->pipe_detect_done, 0));
+    ctx->stream = ctx->aux_stream;
+    rc = run_track_from_detect(ctx, rgba, w, h, 0, n, dr, out_counts, calc_angles, n_calls, out_found,
+                               reinterpret_cast<int32_t *>(out_objs), reinterpret_cast<int32_t *>(out_windows));
+    ctx->stream = st;
+    if (rc != HT_OK) return rc;
+    CK(cudaEventRecord(ctx->aux_done, ctx->aux_stream));
+    ctx->aux_pending = true;
+    ctx->last_plan = P;
+    ctx->last_n = n;
+    return HT_OK;
+  }
+  if (n_calls > 0) CK(ctx->bins.reserve((size_t)n * w * h * sizeof(uint16_t)));
   Rect *d_rects = rects_dev ? reinterpret_cast<Rect *>(out_rects) : ctx->d_out_rects.as<Rect>();
   int32_t *d_counts = counts_dev ? out_counts : ctx->d_out_counts.as<int32_t>();
   int32_t *d_found = out_found ? (found_dev ? out_found : ctx->d_found.as<int32_t>()) : nullptr;
@@ -1385,7 +1467,8 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
   if (use_aux && ctx->overlap_parts > 1) parts = std::min(ctx->overlap_parts, std::max(1, n / 32));
   auto part_begin = [&](int p) { return (int)(((long long)n * p) / parts); };
   auto hist_out = [&](int f0) {
-    return n_calls > 0 ? HistOut{ctx->cur_hist.as<uint32_t>() + (size_t)f0 * 4096, ctx->bins.as<uint16_t>() + (size_t)f0 * w * h}
+    return n_calls > 0 ? HistOut{ctx->cur_hist.as<uint32_t>() + ctx->hist_off + (size_t)f0 * 4096,
+                                 ctx->bins.as<uint16_t>() + ctx->bins_off + (size_t)f0 * w * h}
                        : HistOut{nullptr, nullptr};
   };
   if (use_aux && parts > 1 && !ctx->aux_stream) {
@@ -1508,6 +1591,7 @@ static int ensure_stream_buffers(ht_ctx *ctx) {
 
 int ht_stream_reset(ht_ctx *ctx, int first, int n) {
   if (!ctx) return HT_ERR_ARG;
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
   if (first < 0 || n <= 0 || first + n > ctx->cfg.max_frames) return ctx->fail(HT_ERR_ARG, "stream range outside [0,%d)", ctx->cfg.max_frames);
   CK(cudaSetDevice(ctx->cfg.device));
   int rc = ensure_stream_buffers(ctx);
@@ -1626,6 +1710,7 @@ int ht_ingest(ht_ctx *ctx, const uint8_t *src_rgba, int n, int sw, int sh, uint8
 
 int ht_backprojection(ht_ctx *ctx, int slot, const uint8_t *rgba, int w, int h, uint8_t *out_rgba) {
   if (!ctx) return HT_ERR_ARG;
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
   if (!out_rgba || slot < 0 || slot >= ctx->cfg.max_frames || w <= 0 || h <= 0) return ctx->fail(HT_ERR_ARG, "bad argument");
   CK(cudaSetDevice(ctx->cfg.device));
   int rc = ensure_tracker_buffers(ctx);
@@ -1687,6 +1772,7 @@ int ht_profile(ht_ctx *ctx, int enable) {
 int ht_profile_read(ht_ctx *ctx, double *ms, uint64_t *launches, int reset) {
   if (!ctx) return HT_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
   CK(cudaStreamSynchronize(ctx->stream));
   for (auto &sp : ctx->prof_spans) {
     float t = 0.f;
@@ -1726,6 +1812,7 @@ int ht_plan_info(ht_ctx *ctx, int w, int h, int interval, int32_t *n_slots, int3
 
 int ht_debug_plane(ht_ctx *ctx, int frame, int slot, int q, uint8_t *out, int cap_bytes, int32_t *w, int32_t *h) {
   if (!ctx) return HT_ERR_ARG;
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
   Plan *P = ctx->last_plan;
   if (!P) return ctx->fail(HT_ERR_STATE, "no ht_detect call yet");
   if (frame < 0 || frame >= ctx->last_n || slot < 0 || slot >= P->n_slots || q < 0 || q > 3) return ctx->fail(HT_ERR_ARG, "bad frame/slot/q");
@@ -1752,6 +1839,7 @@ int ht_debug_plane(ht_ctx *ctx, int frame, int slot, int q, uint8_t *out, int ca
 
 int ht_debug_raw(ht_ctx *ctx, int frame, ht_rect *out, int cap, int32_t *count) {
   if (!ctx) return HT_ERR_ARG;
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
   if (!ctx->last_plan || frame < 0 || frame >= ctx->last_n || !count) return ctx->fail(HT_ERR_ARG, "bad frame");
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1776,6 +1864,18 @@ int ht_set_track_memo(ht_ctx *ctx, int enable) {
   return HT_OK;
 }
 
+int ht_set_pipeline(ht_ctx *ctx, int enable) {
+  if (!ctx) return HT_ERR_ARG;
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
+  ctx->pipeline = enable ? 1 : 0;
+  return HT_OK;
+}
+
+int ht_join(ht_ctx *ctx) {
+  if (!ctx) return HT_ERR_ARG;
+  return join_aux(ctx);
+}
+
 int ht_debug_track_stats(ht_ctx *ctx, uint64_t *out5, int reset) {
   if (!ctx || !out5) return HT_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));
@@ -1797,6 +1897,9 @@ int ht_debug_track_trace(ht_ctx *ctx, uint64_t *out, int n) {
 
 int ht_debug_model_hist(ht_ctx *ctx, int slot, uint32_t *out4096) {
   if (!ctx) return HT_ERR_ARG;
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
   if (!out4096 || slot < 0 || slot >= ctx->cfg.max_frames || !ctx->model_hist.p) return ctx->fail(HT_ERR_ARG, "bad slot");
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));

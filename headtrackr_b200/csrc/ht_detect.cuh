@@ -490,13 +490,24 @@ __device__ __forceinline__ void cp_async4(unsigned saddr, const void *g, bool va
 #ifndef HT_CASC_MINB
 #define HT_CASC_MINB (TH <= 8 ? 4 : (TH <= 12 ? 3 : 2))
 #endif
+// position of the r-th (0-based) set bit of w, r < popc(w): five popcount halvings, ~25 instructions (__fns is a
+// software loop; round 2, call 8: 7 % of k_cascade's samples sat in it and its caller)
+__device__ __forceinline__ int nth_bit32(uint32_t w, int r) {
+  int pos = 0, t;
+  t = __popc(w & 0xffffu); if (r >= t) { r -= t; pos += 16; w >>= 16; }
+  t = __popc(w & 0xffu);   if (r >= t) { r -= t; pos += 8;  w >>= 8; }
+  t = __popc(w & 0xfu);    if (r >= t) { r -= t; pos += 4;  w >>= 4; }
+  t = __popc(w & 0x3u);    if (r >= t) { r -= t; pos += 2;  w >>= 2; }
+  t = (int)(w & 1u);       if (r >= t) pos += 1;
+  return pos;
+}
 // r-th (0-based) set bit of the MASK_WORDS-word mask of class c, or -1.  All reads are shared-memory loads.
 __device__ __forceinline__ int nth_set_bit(const uint32_t *__restrict__ masks, int c, int r) {
 #pragma unroll
   for (int j = 0; j < MASK_WORDS; ++j) {
     const uint32_t w = masks[j * 32 + c];
     const int pc = __popc(w);
-    if (r < pc) return j * 32 + (int)__fns(w, 0u, r + 1);
+    if (r < pc) return j * 32 + nth_bit32(w, r);
     r -= pc;
   }
   return -1;

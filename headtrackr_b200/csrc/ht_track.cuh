@@ -258,7 +258,10 @@ __device__ __forceinline__ void row_partial(const uint16_t *__restrict__ row, co
 }
 
 template <int TRACK_CLUSTER, int NT>
-__global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : (NT >= 512 ? 2 : (NT >= 256 ? 3 : 6)))
+#ifndef HT_TRACK_MINB
+#define HT_TRACK_MINB 3   // resident 256-thread CTAs per SM the register allocation aims at (3: 80 registers, 4: 64)
+#endif
+__global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : (NT >= 512 ? 2 : (NT >= 256 ? HT_TRACK_MINB : 6)))
 k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restrict__ slots,
         const uint32_t *__restrict__ model_hist, const uint32_t *__restrict__ cur_hist, TrackState *__restrict__ state,
         int n_calls, int32_t *__restrict__ out_objs /* 6 x i32 per frame */, int32_t *__restrict__ out_windows,

@@ -226,6 +226,18 @@ int ht_debug_set_exactness(ht_ctx *ctx, int flags);
  * to one of them (a converged stream; a stream oscillating between two windows - src/camshift.js:283-306 would
  * re-sum them).  Results are identical either way; enable = 0 re-sums every pass like the reference. */
 int ht_set_track_memo(ht_ctx *ctx, int enable);
+/* Pipelined batches (default off; HT_PIPELINE=1 in the environment turns it on at ht_create).  With enable != 0 an
+ * ht_detect_track call whose frames AND outputs are all device pointers returns as soon as its detection is enqueued
+ * and leaves its tracking (hand-off + n_calls x track(), src/facetrackr.js:97-108,190) on a second, higher-priority
+ * stream, where it runs under the detection kernels of the NEXT ht_detect_track call: CAMShift is a latency chain per
+ * stream that leaves most of the GPU idle, the detector is throughput-bound.  Results are identical to the
+ * unpipelined call.  The caller's side of the contract: out_found / out_objs / out_windows of call s are complete
+ * after ht_sync or ht_join (or any other entry point of the context, which all join first) - NOT merely after the
+ * next ht_detect_track; out_rects / out_counts may be reused by the next call (the library orders the accesses);
+ * the frames of call s must stay unchanged until then as well. */
+int ht_set_pipeline(ht_ctx *ctx, int enable);
+/* Stream-level join: later work on the context's stream waits for a pipelined call's tracking.  No host wait. */
+int ht_join(ht_ctx *ctx);
 /* per-stream timeline of the last ht_track / ht_detect_track launch, 4 x u64 per stream: {globaltimer ns at start,
  * at end, SM id of the leading CTA, moment passes}.  Only for contexts created with HT_TRACK_TRACE=1 in the
  * environment (tools/track_timeline.py); HT_ERR_ARG otherwise. */
