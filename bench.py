@@ -317,7 +317,9 @@ def run_ours(args, cfg):
         for j in range(B):
             hv[j] = np.roll(base[j % N_UNIQUE], (j // N_UNIQUE) * 16, axis=1)
     dev = host.cuda(non_blocking=False)
-    stream = torch.cuda.Stream()          # a real (non-NULL) stream: the context launches on it, the events time it
+    # a real (non-NULL) stream: the context launches on it, the events time it.  HT_BENCH_STREAM_PRIO: CUDA priority of
+    # that stream (torch clamps it to the device's range); the library's background tracking runs below it (HT_PIPE_BG)
+    stream = torch.cuda.Stream(priority=int(os.environ.get("HT_BENCH_STREAM_PRIO", "0")))
     torch.cuda.set_stream(stream)
     ctx = Context(max_width=W, max_height=H, max_frames=B, device=local, stream=stream.cuda_stream)
     K = ctx.K

@@ -290,7 +290,7 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   auto point_off = [&](int z, int x, int y, bool &ok) -> uint16_t {
     const int lim = (24 >> z) - 1;
     if (z < 0 || z > 2 || x < 0 || y < 0 || x > lim || y > lim) { ok = false; return 0; }
-    return (uint16_t)(point_word(z, x, y) | (z > 0 ? 0x8000 : 0));   // bit 15: relative to baseB
+    return (uint16_t)(point_word(z, x, y) | ((z > 0 && !HT_UNIBASE) ? 0x8000 : 0));   // bit 15: relative to baseB (two-base layout)
   };
   for (int k = 0; k < hc.n_features; ++k) {
     const uint8_t *r = pf + (size_t)k * 32;
@@ -502,9 +502,12 @@ struct ht_ctx {
   // buffered by call parity (bin planes, current-frame histograms) or ordered by an event (the caller's rectangle
   // arrays: k_group of call s+1 waits for the tracking of call s).  Every other entry point joins first.
   int pipeline = 0;
+  int pipe_bg = 0;                          // HT_PIPE_BG=1: pipelined tracking runs BELOW the priority of the context's stream,
+                                            // and k_cascade leaves room for one k_track CTA per SM while it is in flight
   bool aux_pending = false;                 // work on aux_stream that the context's stream has not waited for yet
   cudaEvent_t pipe_detect_done = nullptr;
   int pipe_parity = 0;
+  cudaStream_t main_stream = nullptr;       // the context's stream while ctx->stream is temporarily the aux stream
   size_t bins_off = 0, hist_off = 0;        // element offsets of the active bin-plane / histogram buffer (parity)
   // Tracking of part p on a second stream while part p+1 is uploaded / detected (ht_detect_track).  Default (-1):
   // only for HOST frames, where the batch arrives at PCIe speed and the GPU has idle time to fill - measured e2e
@@ -697,6 +700,15 @@ cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, 
                            const uint32_t *mh, const uint32_t *ch, TrackState *state, int n_calls, int32_t *d_objs,
                            int32_t *d_win, int32_t *flag, unsigned long long *stats, int bail_area, int32_t *calls_done,
                            int32_t *bail_list, int32_t *bail_count, int use_list, int list_off, TrackOpts opt) {
+  // Same shared-memory carve-out as k_cascade (the maximum): an SM only changes its L1 / shared split when it is idle,
+  // so CTAs of kernels that ask for different splits do not mix on one SM - and k_track is meant to run beside the
+  // detection kernels of the next call (ht_set_pipeline).
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    cudaError_t ce = cudaFuncSetAttribute(k_track<C, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ce != cudaSuccess) return ce;
+    carveout_set = true;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)n * C);
   cfg.blockDim = dim3(NT);
@@ -808,10 +820,16 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
       if (n_tiers > 1) {
         int prio_least = 0, prio_greatest = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));   // numerically lower = more urgent
+        int prio_top = prio_greatest;
+        if (ctx->pipeline && ctx->pipe_bg) {   // background mode: every tier below the context's own stream
+          int pm = 0;
+          CK(cudaStreamGetPriority(ctx->main_stream ? ctx->main_stream : ctx->stream, &pm));
+          prio_top = std::min(prio_least, pm + 1);
+        }
         for (int t = 0; t < 4; ++t)
           if (!ctx->tier_stream[t]) {
             const int rank = (t == 0) ? 0 : (t == 1 ? 1 : (t == 3 ? 2 : 3));   // heavy, mid, rest, light
-            const int prio = ctx->track_prio ? std::min(prio_least, prio_greatest + rank) : prio_least;
+            const int prio = ctx->track_prio ? std::min(prio_least, prio_top + rank) : prio_least;
             CK(cudaStreamCreateWithPriority(&ctx->tier_stream[t], cudaStreamNonBlocking, prio));
             CK(cudaEventCreateWithFlags(&ctx->tier_done[t], cudaEventDisableTiming));
           }
@@ -859,10 +877,14 @@ int track_init_common(ht_ctx *ctx, const int32_t *slots, int n, const uint8_t *d
 // Shared memory of one k_cascade CTA: the staged tile and three sets of per-class survivor bit masks.
 constexpr size_t CASC_SMEM = (size_t)TILE_WORDS * 4 + 3 * (size_t)MASK_WORDS * 32 * sizeof(uint32_t);
 constexpr size_t GRAY_HIST_SMEM = 2 * 4096 * sizeof(uint32_t);   // two frames per word, 16-bit counters
+// (ht_set_pipeline, background mode) dynamic shared memory that lets exactly THREE k_cascade CTAs share an SM and leaves
+// room for one k_track CTA (35.5 KB static): 4 x (57,600 + 1 KB reserved) > 228 KB, 3 x 58,624 + 36,480 <= 233,472
+constexpr size_t CASC_SMEM_BG = 57600;
+static_assert(CASC_SMEM <= CASC_SMEM_BG || HT_TILE_TH > 8, "background padding assumes the 32x8 tile");
 
 int set_kernel_attributes(ht_ctx *ctx) {
-  CK(cudaFuncSetAttribute(k_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CASC_SMEM));
-  CK(cudaFuncSetAttribute(k_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CASC_SMEM));
+  CK(cudaFuncSetAttribute(k_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(CASC_SMEM, CASC_SMEM_BG)));
+  CK(cudaFuncSetAttribute(k_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(CASC_SMEM, CASC_SMEM_BG)));
   CK(cudaFuncSetAttribute(k_cascade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(k_cascade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(k_gray<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAY_HIST_SMEM));
@@ -1017,7 +1039,9 @@ int run_detect(ht_ctx *ctx, Plan *P, const uint8_t *d_rgba_batch, int f0, int n,
     if (!P->casc_tiles.empty()) {
       ctx->prof_begin(HT_PROF_CASCADE);
       auto kern = ctx->hc.fast ? k_cascade<true> : k_cascade<false>;
-      kern<<<dim3((unsigned)P->casc_tiles.size(), quads), CASCADE_THREADS, CASC_SMEM, st>>>(
+      // background mode: while the previous call's tracking is in flight, three cascade CTAs per SM instead of four
+      const size_t casc_smem = (before_group && ctx->pipe_bg) ? std::max(CASC_SMEM, CASC_SMEM_BG) : CASC_SMEM;
+      kern<<<dim3((unsigned)P->casc_tiles.size(), quads), CASCADE_THREADS, casc_smem, st>>>(
           P->dplan, ctx->d_casc.as<LateFeat>(), ctx->d_casc.as<LateFeat>() + ctx->hc.n_sched, ctx->d_late_chunk0.as<int32_t>(),
           (ctx->use_tma && ctx->d_tmaps.p) ? ctx->d_tmaps.as<uint8_t>() + (piped ? (size_t)(wi & 1) : 0) * P->scales.size() * 128 : nullptr, 0,
           arena, P->arena_stride, nw,
@@ -1179,9 +1203,11 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
   if (const char *wv = getenv("HT_WAVE")) c->wave_frames = std::max(4, atoi(wv));
   if (const char *wm = getenv("HT_WAVE_MB")) c->wave_mb = std::max(1, atoi(wm));
   if (const char *tm = getenv("HT_TMA")) c->use_tma = atoi(tm) != 0;
+  if (HT_UNIBASE) c->use_tma = false;       // super-row tiles: a dense TMA box cannot be written into them
   if (const char *ov = getenv("HT_OVERLAP")) { c->overlap_track = atoi(ov) != 0 ? 1 : 0; c->overlap_parts = atoi(ov); }
   if (const char *hc2 = getenv("HT_H2D_CHUNK")) c->h2d_chunk = std::max(1, atoi(hc2));
   if (const char *pl = getenv("HT_PIPELINE")) c->pipeline = atoi(pl) != 0 ? 1 : 0;
+  if (const char *bg = getenv("HT_PIPE_BG")) c->pipe_bg = atoi(bg) != 0 ? 1 : 0;
   if (const char *tp = getenv("HT_TRACK_PRIO")) c->track_prio = atoi(tp) != 0 ? 1 : 0;
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
   // the cascade image is copied into __constant__ memory lazily by run_detect; the late-stage table lives in HBM
@@ -1419,9 +1445,11 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
       CK(ctx->bins.reserve(2 * plane_elems * sizeof(uint16_t)));
     }
     if (!ctx->aux_stream) {
-      int prio_least = 0, prio_greatest = 0;
+      int prio_least = 0, prio_greatest = 0, aux_prio = 0;
       CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-      CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_greatest));
+      aux_prio = prio_greatest;
+      if (ctx->pipe_bg) { int pm = 0; CK(cudaStreamGetPriority(st, &pm)); aux_prio = std::min(prio_least, pm + 1); }
+      CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, aux_prio));
       CK(cudaEventCreateWithFlags(&ctx->aux_done, cudaEventDisableTiming));
       for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->part_events[i], cudaEventDisableTiming));
     }
@@ -1436,10 +1464,12 @@ int ht_detect_track(ht_ctx *ctx, const uint8_t *rgba, int n, int w, int h, int i
     if (rc != HT_OK) return rc;
     CK(cudaEventRecord(ctx->pipe_detect_done, st));
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->pipe_detect_done, 0));
+    ctx->main_stream = st;
     ctx->stream = ctx->aux_stream;
     rc = run_track_from_detect(ctx, rgba, w, h, 0, n, dr, out_counts, calc_angles, n_calls, out_found,
                                reinterpret_cast<int32_t *>(out_objs), reinterpret_cast<int32_t *>(out_windows));
     ctx->stream = st;
+    ctx->main_stream = nullptr;
     if (rc != HT_OK) return rc;
     CK(cudaEventRecord(ctx->aux_done, ctx->aux_stream));
     ctx->aux_pending = true;
@@ -2003,48 +2033,48 @@ extern "C" int ht_selftest_cascade(const void *blob, size_t blob_len, int w, int
   for (const DevCascTile &tl : P.casc_tiles) {
     const DevScale &sc = P.scales[tl.scale];
     const int x0 = tl.tx * TW, y0 = tl.ty * TH;
-    // staging: the kernel's loops, word for word
+    // staging: what the kernel's loops write, through the same layout functions (tile_l0 / tile_l1 / tile_l2)
+    std::fill(tile.begin(), tile.end(), 0u);
     {
       const DevPlane pl = P.planes[sc.p0];
       const uint32_t *src = arena + pl.off;
       const int X0 = 4 * x0, Y0 = 4 * y0;
-      for (int i = 0; i < L0_ROWS * P0; ++i) {
-        const int r = i / P0, c = i - r * P0;
-        const int X = (c < H0) ? 2 * c : 2 * (c - H0) + 1;
-        const bool ok = (Y0 + r < pl.h) && (X0 + X < pl.pitch);
-        tile[(size_t)i] = ok ? src[(size_t)(Y0 + r) * pl.pitch + X0 + X] : 0u;
-      }
+      for (int r = 0; r < L0_ROWS; ++r)
+        for (int X = 0; X < L0_COLS; ++X) {
+          const bool ok = (Y0 + r < pl.h) && (X0 + X < pl.pitch);
+          tile[(size_t)tile_l0(r, X)] = ok ? src[(size_t)(Y0 + r) * pl.pitch + X0 + X] : 0u;
+        }
     }
     {
       const DevPlane pl = P.planes[sc.p1];
       const uint32_t *src = arena + pl.off;
       const int X0 = 2 * x0, Y0 = 2 * y0;
-      for (int i = 0; i < L1_ROWS * P1; ++i) {
-        const int r = i / P1, c = i - r * P1;
-        const bool ok = (Y0 + r < pl.h) && (X0 + c < pl.pitch);
-        tile[(size_t)(W1 + i)] = ok ? src[(size_t)(Y0 + r) * pl.pitch + X0 + c] : 0u;
+      for (int r = 0; r < L1_ROWS; ++r)
+        for (int c = 0; c < P1; ++c) {
+          const bool ok = (Y0 + r < pl.h) && (X0 + c < pl.pitch);
+          tile[(size_t)tile_l1(r, c)] = ok ? src[(size_t)(Y0 + r) * pl.pitch + X0 + c] : 0u;
+        }
+    }
+    for (int rr = 0; rr < 2 * L2_ROWS; ++rr)
+      for (int c2 = 0; c2 < P2; ++c2) {
+        const int q = (c2 & 1) | ((rr & 1) << 1), r = rr >> 1, c = c2 >> 1;
+        const DevPlane pl = P.planes[sc.p2[q]];
+        const uint32_t *src = arena + pl.off;
+        const bool ok = (y0 + r < pl.h) && (x0 + c < pl.pitch);
+        tile[(size_t)tile_l2(rr, c2)] = ok ? src[(size_t)(y0 + r) * pl.pitch + x0 + c] : 0u;
       }
-    }
-    for (int i = 0; i < 2 * L2_ROWS * P2; ++i) {
-      const int rr = i / P2, c2 = i - rr * P2;
-      const int q = (c2 & 1) | ((rr & 1) << 1), r = rr >> 1, c = c2 >> 1;
-      const DevPlane pl = P.planes[sc.p2[q]];
-      const uint32_t *src = arena + pl.off;
-      const bool ok = (y0 + r < pl.h) && (x0 + c < pl.pitch);
-      tile[(size_t)(W2 + i)] = ok ? src[(size_t)(y0 + r) * pl.pitch + x0 + c] : 0u;
-    }
     const uint8_t *tile_b = reinterpret_cast<const uint8_t *>(tile.data());
     auto bases = [&](int e, const uint8_t *&tA, const uint8_t *&tB) {
       const int u = e & 63, v = (e >> 6) & 31, f = e >> 11;
-      tA = tile_b + 4 * (v * (2 * P0) + u) + f;
-      tB = tile_b + 4 * (v * P1 + u) + f;
+      tA = tile_b + 4 * (v * VA + u) + f;
+      tB = tile_b + 4 * (v * VB + u) + f;
     };
     // dense group (quad form)
     std::vector<int> list[32];
     for (int v = 0; v < 2 * TH; ++v)
       for (int u = 0; u < 2 * TW; ++u) {
         const int lx = u >> 1, ly = v >> 1;
-        const uint32_t *tA = tile.data() + v * (2 * P0) + u, *tB = tile.data() + v * P1 + u;
+        const uint32_t *tA = tile.data() + v * VA + u, *tB = tile.data() + v * VB + u;
         uint32_t a_lo = 0, a_hi = 0;
         if (x0 + lx < sc.qw && y0 + ly < sc.qh) {
           a_lo = ((fmask & 1u) ? 0x8000u : 0u) | ((fmask & 4u) ? 0x80000000u : 0u);

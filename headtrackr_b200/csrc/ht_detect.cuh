@@ -447,7 +447,11 @@ __device__ __forceinline__ bool feat_fires(unsigned sA, unsigned sBm, const uint
   unsigned vv[10];
 #pragma unroll
   for (int s = 0; s < 10; ++s) {
+#if HT_UNIBASE
+    const unsigned addr = sA + o[s];                                  // one base for all three levels
+#else
     const unsigned addr = ((int)o[s] < 0 ? sBm : sA) + o[s];
+#endif
     vv[s] = lds_u8_if(addr, o[s] != LATE_UNUSED, s < 5 ? 255u : 0u);   // unused slots: neutral element, no bank traffic
   }
   const unsigned pm = __vimin3_u32(__vimin3_u32(vv[0], vv[1], vv[2]), vv[3], vv[4]);
@@ -490,6 +494,24 @@ __device__ __forceinline__ void cp_async4(unsigned saddr, const void *g, bool va
 #ifndef HT_CASC_MINB
 #define HT_CASC_MINB (TH <= 8 ? 4 : (TH <= 12 ? 3 : 2))
 #endif
+#ifndef HT_CT_GROUPS
+#define HT_CT_GROUPS 1   // 1: the survivor groups of the generated cascade as four unrolled copies with constant stage bounds
+#endif
+// a compile-time int that converts to int in device code (std::integral_constant's conversion is a host function)
+template <int V>
+struct IntC {
+  __host__ __device__ constexpr operator int() const { return V; }
+};
+// warp-wide reductions in one REDUX instruction each (sm_80+), instead of five shuffle + op rounds
+__device__ __forceinline__ int warp_max_i32(int v) { return (int)__reduce_max_sync(0xffffffffu, (unsigned)v); }   // v >= 0
+// sum of 32 signed 64-bit values with |v| < 2^46 (late-stage integer sums: <= 66 chunks x |alpha_int| < 2^31 per lane):
+// offset to positive, two 24/23-bit halves summed separately (each total < 2^29), recombined
+__device__ __forceinline__ long long warp_sum_i64(long long v) {
+  const unsigned long long u = (unsigned long long)(v + (1ll << 46));
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(u & 0xffffffull));
+  const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(u >> 24));
+  return (long long)(((unsigned long long)hi << 24) + lo) - (32ll << 46);
+}
 // position of the r-th (0-based) set bit of w, r < popc(w): five popcount halvings, ~25 instructions (__fns is a
 // software loop; round 2, call 8: 7 % of k_cascade's samples sat in it and its caller)
 __device__ __forceinline__ int nth_bit32(uint32_t w, int r) {
@@ -543,7 +565,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
   // Level 1 is a plain 2-D box of its plane (L1_ROWS x P1 words): when tensor maps are given it is staged by the
   // TMA engine - one elected thread issues cp.async.bulk.tensor (3-D map: column, row, frame quad; elements outside
   // the plane are zero-filled) completing on an mbarrier - while all threads scatter levels 0 and 2.
-  const bool use_tma = tmaps != nullptr;
+  const bool use_tma = !HT_UNIBASE && tmaps != nullptr;   // a TMA box is dense: it cannot write into super-rows
   if (use_tma) {
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
     if (tid == 0) {
@@ -553,7 +575,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
     __syncthreads();   // nobody may poll the barrier before it is initialised
     if (tid == 0) {
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(L1_ROWS * P1 * 4)) : "memory");
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + W1);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + W1);   // (separate-block layout only)
       const unsigned long long map = (unsigned long long)(reinterpret_cast<const uint8_t *>(tmaps) + 128 * (size_t)tl.scale);
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -582,7 +604,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
         for (int k = 0; k < 4; ++k) {
           const int i = i0 + k * CASCADE_THREADS, r = i / G0, X = (i - r * G0) * 4;
           if (i >= L0_ROWS * G0) break;
-          uint32_t *row = tile + r * P0 + (X >> 1);
+          uint32_t *row = tile + tile_l0(r, X);   // (X % 4 == 0: the even half; the odd half is H0 words further)
           if (X + 2 < L0_COLS) *reinterpret_cast<uint2 *>(row) = make_uint2(v[k].x, v[k].z);   // even columns X, X+2
           else row[0] = v[k].x;                            // last group of a row: X+2 is outside the tile
           if (X + 1 < L0_COLS) row[H0] = v[k].y;           // odd columns X+1, X+3
@@ -598,7 +620,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
       for (int i = tid; i < L1_ROWS * G1; i += CASCADE_THREADS) {
         const int r = i / G1, c = (i - r * G1) * 4;
         const bool ok = (Y0 + r < pl.h) && (X0 + c < pl.pitch);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + W1 + r * P1 + c);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + tile_l1(r, c));
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src + (size_t)(Y0 + r) * pl.pitch + X0 + c : src),
                      "r"(ok ? 16u : 0u) : "memory");
       }
@@ -617,7 +639,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
           const DevPlane pl = plan.planes[plan.scales[tl.scale].p2[2 * dy + 1]];
           if (y0 + r < pl.h && x0 + c < pl.pitch) v1 = __ldg(reinterpret_cast<const uint4 *>(qa + pl.off + (size_t)(y0 + r) * pl.pitch + x0 + c));
         }
-        uint32_t *row = tile + W2 + (2 * r + dy) * P2 + 2 * c;
+        uint32_t *row = tile + tile_l2(2 * r + dy, 2 * c);
         *reinterpret_cast<uint4 *>(row) = make_uint4(v0.x, v1.x, v0.y, v1.y);
         if (2 * c + 8 <= P2) *reinterpret_cast<uint4 *>(row + 4) = make_uint4(v0.z, v1.z, v0.w, v1.w);   // (P2 = 76 = 9 * 8 + 4)
       }
@@ -652,8 +674,8 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
   };
   auto bases = [&](int c, int b, const uint8_t *&tA, const uint8_t *&tB) {
     const int v = b >> 3, uh = (b >> 2) & 1, f = b & 3, u = class_u(c, v, uh);
-    tA = tile_b + 4 * (v * (2 * P0) + u) + f;
-    tB = tile_b + 4 * (v * P1 + u) + f;
+    tA = tile_b + 4 * (v * VA + u) + f;
+    tB = tile_b + 4 * (v * VB + u) + f;
   };
   const int late_first = c_casc.group_first[c_casc.n_groups];
   const bool has_late = late_first < c_casc.n_stages;
@@ -674,7 +696,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
         uint32_t m = 0;
         if (FAST) {
           // quad form (cascade_face_gen.inc): 4 frames per lane
-          const uint32_t *tA = tile + v * (2 * P0) + u, *tB = tile + v * P1 + u;
+          const uint32_t *tA = tile + v * VA + u, *tB = tile + v * VB + u;
           uint32_t a_lo = 0, a_hi = 0;   // alive bits: frame 0 -> lo bit 15, 2 -> lo bit 31, 1 -> hi bit 15, 3 -> hi bit 31
           if (x0 + lx < sc.qw && y0 + ly < sc.qh) {
             a_lo = ((fmask & 1u) ? 0x8000u : 0u) | ((fmask & 4u) ? 0x80000000u : 0u);
@@ -708,7 +730,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
           // table-driven: ordered fp64 sums, one frame at a time
           for (int f = 0; f < 4; ++f) {
             bool alive = (x0 + lx < sc.qw) && (y0 + ly < sc.qh) && ((fmask >> f) & 1u);
-            const uint8_t *tA = tile_b + 4 * (v * (2 * P0) + u) + f, *tB = tile_b + 4 * (v * P1 + u) + f;
+            const uint8_t *tA = tile_b + 4 * (v * VA + u) + f, *tB = tile_b + 4 * (v * VB + u) + f;
             for (int j = c_casc.group_first[0]; j < c_casc.group_first[1]; ++j) {
               if (!__any_sync(0xffffffffu, alive)) break;
               alive = alive && stage_pass_ordered(tA, tB, j);
@@ -725,25 +747,22 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
   __syncthreads();
 
   // ---- survivor masks: lane L walks the set bits of class L; warp w takes the entries of rank w, w + NW, ... ----
-  for (; g < c_casc.n_groups; ++g) {
-    const int jb = c_casc.group_first[g], je = c_casc.group_first[g + 1];
-    const bool emit_here = (g == c_casc.n_groups - 1) && !has_late;
+  // One group = stages [jb, je).  For the generated cascade the bounds are compile-time constants (integral_constant
+  // arguments): the stage loop unrolls and gen_stage's switch folds away (round 2, call 8: 3.4 % of the samples sat in
+  // that dispatch).  Returns true when the CTA is finished.
+  auto run_group = [&](auto JB, auto JE, const bool emit_here) __attribute__((always_inline)) -> bool {
+    const int jb = JB, je = JE;
     int n = 0;
 #pragma unroll
     for (int j = 0; j < MASK_WORDS; ++j) n += __popc(m_in[j * 32 + lane]);
-    int maxn = n;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
-    if (maxn == 0) return;   // uniform over the CTA
+    if (warp_max_i32(n) == 0) return true;   // uniform over the CTA
     for (int i = tid; i < MASK_WORDS * 32; i += CASCADE_THREADS) m_clr[i] = 0u;   // the mask of the group after next
     // warp w takes the entries of rank [w n / NW, (w+1) n / NW) of every class: one nth_set_bit per lane and group,
     // then a walk over consecutive set bits (round-2 call 3: rank-strided entries spent 16 % of the kernel's
     // instructions in __fns)
     const int r_beg = (warp * n) / CASCADE_WARPS, r_end = ((warp + 1) * n) / CASCADE_WARPS;
     const int my_iters = r_end - r_beg;
-    int iters = my_iters;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) iters = max(iters, __shfl_xor_sync(0xffffffffu, iters, o));
+    const int iters = warp_max_i32(my_iters);
     int bpos = my_iters > 0 ? nth_set_bit(m_in, lane, r_beg) : 0;       // bit index of the current entry
     uint32_t cur = my_iters > 0 ? (m_in[(bpos >> 5) * 32 + lane] & (0xffffffffu << (bpos & 31))) : 0u;   // its word, lower bits cleared
     for (int it = 0; it < iters; ++it) {
@@ -758,6 +777,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
       const uint8_t *tA, *tB;
       bases(lane, b, tA, tB);
       double sum = 0.0;
+#pragma unroll
       for (int j = jb; j < je; ++j) {
         if (!__any_sync(0xffffffffu, alive)) break;
         if (FAST && j < HT_GEN_STAGES) {
@@ -779,9 +799,26 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
         }
       }
     }
-    if (emit_here) return;
+    if (emit_here) return true;
     __syncthreads();
     uint32_t *t = m_in; m_in = m_out; m_out = m_clr; m_clr = t;
+    return false;
+  };
+  if (FAST) {
+    // the generated groups {2} {3} {4,5} {6,7} (parse_cascade's cuts_fast; the dense group covered {0,1} or {0,1,2})
+    static_assert(HT_GEN_STAGES == 8, "compile-time groups assume 8 generated stages");
+#if HT_CT_GROUPS
+    if (g < 2 && run_group(IntC<2>{}, IntC<3>{}, false)) return;
+    if (run_group(IntC<3>{}, IntC<4>{}, false)) return;
+    if (run_group(IntC<4>{}, IntC<6>{}, false)) return;
+    if (run_group(IntC<6>{}, IntC<8>{}, !has_late)) return;
+#else   // one rolled copy of the group code (62 registers, no spills) - measured slower: 6.55 vs 6.28 ms per 1024 frames
+    for (; g < c_casc.n_groups; ++g)
+      if (run_group(c_casc.group_first[g], c_casc.group_first[g + 1], (g == c_casc.n_groups - 1) && !has_late)) return;
+#endif
+  } else {
+    for (; g < c_casc.n_groups; ++g)
+      if (run_group(c_casc.group_first[g], c_casc.group_first[g + 1], (g == c_casc.n_groups - 1) && !has_late)) return;
   }
   if (!has_late) {
     if (c_casc.n_groups == 1) {   // a cascade that ends with the dense group: emit its survivors
@@ -829,8 +866,7 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
           const int ai = (int)cc.z;                      // alpha_int (0 for padding records)
           acc += feat_fires(sA, sBm, a, bb, cc) ? (long long)ai : -(long long)ai;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = warp_sum_i64(acc);
         const long long thr = c_casc.thr_int[j];
         if (acc == thr || (force_ties & 2))             // exact tie: the reference's ordered adds decide
           pass = !(stage_sum_ordered_warp(sA, sBm, j, feat_orig, lane) < c_casc.stage[j].threshold);
