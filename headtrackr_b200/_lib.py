@@ -81,7 +81,7 @@ _lib = None
 
 EXPORTS = ["ht_version", "ht_create", "ht_destroy", "ht_last_error", "ht_sync", "ht_max_rects", "ht_detect",
            "ht_track_init", "ht_track_init_from_detect", "ht_track", "ht_detect_track", "ht_stream_reset", "ht_stream_step", "ht_stream_head_config", "ht_stream_step_head", "ht_ingest", "ht_backprojection", "ht_whitebalance",
-           "ht_plan_info", "ht_debug_plane", "ht_debug_raw", "ht_debug_model_hist", "ht_debug_track_stats", "ht_set_track_memo", "ht_set_pipeline", "ht_join", "ht_debug_set_exactness", "ht_debug_track_trace", "ht_launch_count",
+           "ht_plan_info", "ht_debug_plane", "ht_debug_raw", "ht_debug_model_hist", "ht_debug_track_stats", "ht_set_track_memo", "ht_set_pipeline", "ht_join", "ht_debug_set_exactness", "ht_debug_track_trace", "ht_debug_track_phases", "ht_launch_count",
            "ht_profile", "ht_profile_read"]
 
 PROF_CLASSES = ["gray", "pyramid", "cascade", "group", "hist", "track_init", "track"]
@@ -125,6 +125,7 @@ def lib():
     L.ht_debug_model_hist.argtypes = [vp, C.c_int, vp]
     L.ht_debug_track_stats.argtypes = [vp, vp, C.c_int]
     L.ht_debug_track_trace.argtypes = [vp, vp, C.c_int]
+    L.ht_debug_track_phases.argtypes = [vp, vp, C.c_int]
     L.ht_set_track_memo.argtypes = [vp, C.c_int]
     L.ht_set_pipeline.argtypes = [vp, C.c_int]
     L.ht_join.argtypes = [vp]

@@ -291,6 +291,12 @@ class Context:
         self._check(self._L.ht_debug_track_trace(self._h, out.ctypes.data, n))
         return out
 
+    def debug_track_phases(self, n):
+        """(n, 8) uint64 phase totals in SM cycles (profiling builds with -DHT_TRACK_PASSTRACE=1; zeros otherwise)."""
+        out = np.zeros((n, 8), np.uint64)
+        self._check(self._L.ht_debug_track_phases(self._h, out.ctypes.data, n))
+        return out
+
     def debug_model_hist(self, slot):
         out = np.zeros(4096, np.uint32)
         self._check(self._L.ht_debug_model_hist(self._h, slot, out.ctypes.data))

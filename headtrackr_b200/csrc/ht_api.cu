@@ -547,13 +547,16 @@ struct ht_ctx {
   bool head_on = false;
   bool track_history = true;                // order by the cost of each stream's previous launch (HT_TRACK_HISTORY=0: by window area)
   DevBuf d_track_cost;                      // [max_frames][2] {passes, window pixels / 256} per slot
-  int track_heavy_div = 64;                 // >0: the n/div costliest streams run on a cluster of
+  int track_heavy_div = 128;                // >0: the n/div costliest streams run on a cluster of
   int track_heavy_cluster = 8;              //     track_heavy_cluster CTAs on sched_stream (HT_TRACK_HEAVY=div[,cluster])
-  int track_mid_div = 16, track_mid_cluster = 4;  // HT_TRACK_MID=div[,cluster]: the next n/16 costliest streams on clusters of 4
-                                                  // (measured 4.12 -> 3.40 ms per 1024 x 30 calls; div 8: 3.55)
+  int track_mid_div = 32, track_mid_cluster = 4;  // HT_TRACK_MID=div[,cluster]: the next n/32 costliest streams on clusters of 4
+                                                  // (call 4: 4.12 -> 3.40 ms per 1024 x 30 calls with n/16; call 17, with
+                                                  // prioritised tier streams: n/64 + n/16 3.17, n/128 + n/32 2.97, n/64 + n/48 3.00)
   int track_light_div = 0, track_light_nt = 256;  // HT_TRACK_LIGHT=div[,threads]: the cheapest n/div streams on single CTAs
   cudaStream_t tier_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // heavy, mid, light, rest (side 3: when tiers are on)
   cudaEvent_t tier_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  int track_mask_frames = 4;                // >0: mask only streams whose last launch swept more than this many frames' worth of pixels
+  int track_mask_min = 4;                   // HT_TRACK_MASK=<min n_calls> (0: off): zero-weight marking of the bin plane before k_track
   int track_prio = 1;                       // HT_TRACK_PRIO=0: tier streams without priorities, the default tier on the context's stream
   cudaStream_t sched_stream = nullptr;
   cudaEvent_t sched_ready = nullptr, sched_done = nullptr;
@@ -663,7 +666,10 @@ int ensure_tracker_buffers(ht_ctx *ctx) {
     CK(ctx->d_sched.reserve((2 * mf + 64) * sizeof(int32_t)));
     CK(ctx->d_track_cost.reserve(2 * mf * sizeof(int32_t)));
     CK(cudaMemsetAsync(ctx->d_track_cost.p, 0, 2 * mf * sizeof(int32_t), ctx->stream));
-    if (ctx->track_trace) CK(ctx->d_trace.reserve(4 * mf * sizeof(unsigned long long)));
+    if (ctx->track_trace) {   // [mf x 4] per-stream records, then [mf x 8] phase totals (HT_TRACK_PASSTRACE builds)
+      CK(ctx->d_trace.reserve(12 * mf * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(ctx->d_trace.p, 0, 12 * mf * sizeof(unsigned long long), ctx->stream));
+    }
   }
   return HT_OK;
 }
@@ -689,6 +695,7 @@ int launch_hist(ht_ctx *ctx, const uint8_t *d_rgba, int n, int w, int h, uint32_
 // per-launch options of k_track that do not depend on the batch
 struct TrackOpts {
   unsigned long long *trace;   // HT_TRACK_TRACE=1: per-stream timeline buffer (else NULL)
+  size_t trace_stride;         // u64 entries between a stream's record and its phase totals
   int memo;                    // ht_ctx::track_memo
   int force_serial;            // ht_ctx::force_ties & 4
   int32_t *cost;               // per slot {passes, window pixels / 256} of the last launch (scheduling history)
@@ -719,7 +726,7 @@ cudaError_t launch_track_c(cudaStream_t st, int n, const uint16_t *bins, int w, 
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_track<C, NT>, bins, w, h, d_slots, mh, ch, state, n_calls, d_objs, d_win, flag, stats,
-                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, opt.trace, opt.memo, opt.force_serial, opt.cost, opt.enable);
+                            bail_area, calls_done, bail_list, bail_count, use_list, list_off, opt.trace, opt.trace_stride, opt.memo, opt.force_serial, opt.cost, opt.enable);
 }
 
 // cluster size x CTA size chosen at run time
@@ -760,7 +767,20 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
                  const uint8_t *enable = nullptr) {
   unsigned long long *stats = ctx->d_flags.as<unsigned long long>() + 8;
   cudaStream_t st = ctx->stream;
+  // several track() calls on this frame: mark the plane entries whose weight is +0.0 first (k_bins_mask), k_track then
+  // skips whole row segments of them.  (One call per frame - ht_stream_step - does not repay the extra pass.)
+  if (ctx->track_mask_min > 0 && n_calls >= ctx->track_mask_min) {
+    const int chunks = std::max(1, std::min(64, 1184 / std::max(1, n)));
+    // selective (default): only streams whose previous launch visited more than track_mask_frames whole frames' worth
+    // of pixels (history of the slot; first launch: nobody) - 1/10 of the bench mix, and nearly all of its pixel visits
+    const int min_px256 = (int)std::min<long long>(((long long)ctx->track_mask_frames * w * h) >> 8, 0x7fffffff);
+    k_bins_mask<<<dim3((unsigned)chunks, (unsigned)n), 256, 0, st>>>(const_cast<uint16_t *>(bins), w * h, mh, d_slots, state, chunks, enable,
+                                                                     ctx->track_mask_frames > 0 ? ctx->d_track_cost.as<int32_t>() : nullptr, min_px256);
+    ++ctx->launches;
+  }
   const TrackOpts opt{ctx->track_trace ? ctx->d_trace.as<unsigned long long>() + 4 * (size_t)f0 : nullptr,
+                      // (the kernel indexes both areas with the stream number relative to f0)
+                      4 * (size_t)ctx->cfg.max_frames - 4 * (size_t)f0 + 8 * (size_t)f0,
                       ctx->track_memo ? 1 : 0, (ctx->force_ties & 4) ? 1 : 0, ctx->d_track_cost.as<int32_t>(), enable};
   // per-chunk scheduling scratch: [calls_done | area n][bail_list | order n][bail_count 1]
   int32_t *calls_done = ctx->d_sched.as<int32_t>() + (size_t)f0;
@@ -1209,6 +1229,10 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
   if (const char *pl = getenv("HT_PIPELINE")) c->pipeline = atoi(pl) != 0 ? 1 : 0;
   if (const char *bg = getenv("HT_PIPE_BG")) c->pipe_bg = atoi(bg) != 0 ? 1 : 0;
   if (const char *tp = getenv("HT_TRACK_PRIO")) c->track_prio = atoi(tp) != 0 ? 1 : 0;
+  if (const char *tk = getenv("HT_TRACK_MASK")) {   // HT_TRACK_MASK=<min n_calls>[,<min frames swept>]  (0: off / 0: every stream)
+    c->track_mask_min = std::max(0, atoi(tk));
+    if (const char *comma = strchr(tk, ',')) c->track_mask_frames = std::max(0, atoi(comma + 1));
+  }
   if (cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming) != cudaSuccess) { g_create_error = "ht_create: event"; return HT_ERR_CUDA; }
   // the cascade image is copied into __constant__ memory lazily by run_detect; the late-stage table lives in HBM
   if (c->d_casc.reserve(c->hc.late.size() * sizeof(LateFeat)) != cudaSuccess ||
@@ -1922,6 +1946,17 @@ int ht_debug_track_trace(ht_ctx *ctx, uint64_t *out, int n) {
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(out, ctx->d_trace.p, 4 * sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  return HT_OK;
+}
+
+int ht_debug_track_phases(ht_ctx *ctx, uint64_t *out, int n) {
+  if (!ctx) return HT_ERR_ARG;
+  { const int jr = join_aux(ctx); if (jr != HT_OK) return jr; }
+  if (!ctx->track_trace || !ctx->d_trace.p || n < 0 || n > ctx->cfg.max_frames)
+    return ctx->fail(HT_ERR_ARG, "no track trace (create the context with HT_TRACK_TRACE=1)");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, ctx->d_trace.as<unsigned long long>() + 4 * (size_t)ctx->cfg.max_frames, 8 * sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
   return HT_OK;
 }
 

@@ -136,6 +136,61 @@ __global__ void k_pick_face(const Rect *__restrict__ det, const int32_t *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Zero-weight marking of the bin plane.  getWeights (src/camshift.js:314-330) gives a pixel the weight
+// min(model[bin] / current[bin], 1): it is exactly +0.0 for every colour bin that does not occur in the model
+// histogram, i.e. in the face rectangle of initTracker - the vast majority of a frame's pixels (85-99 % on the bench
+// frames; a face has a few dozen to a few hundred of the 4096 bins).  Adding +0.0 to a moment sum never changes it,
+// so those pixels can be skipped.  This pass rewrites their plane entries to ZERO (0x8000 = 8 * 4096, the table's
+// extra +0.0 entry): k_track then skips every 128-pixel row segment whose entries are all ZERO with one warp vote.
+// One read + one write of the u16 plane per frame, worth it when several track() calls follow on the same frame.
+constexpr uint32_t BIN_ZERO = 8u * 4096u;          // byte offset of wsm[4096]
+constexpr uint32_t BIN_ZERO2 = BIN_ZERO | (BIN_ZERO << 16);
+__global__ void __launch_bounds__(256) k_bins_mask(uint16_t *__restrict__ bins, int n_px, const uint32_t *__restrict__ model_hist,
+                                                   const int32_t *__restrict__ slots, const TrackState *__restrict__ state,
+                                                   int chunks, const uint8_t *__restrict__ enable,
+                                                   // cost != NULL: only the streams whose previous launch visited more than
+                                                   // min_px256 * 256 pixels (k_track's scheduling history) - the pass over
+                                                   // the plane is repaid by streams that sweep large windows many times
+                                                   const int32_t *__restrict__ cost, int min_px256) {
+  __shared__ uint32_t bm[128];                     // bit b set: model histogram bin b is non-zero
+  const int k = blockIdx.y;
+  if (enable && !enable[k]) return;
+  const int slot = slots ? slots[k] : k;
+  if (!state[slot].initialised) return;            // k_track refuses such a slot anyway
+  if (cost && cost[2 * slot + 1] < min_px256) return;
+  const uint32_t *mh = model_hist + (size_t)slot * 4096;
+  if (threadIdx.x < 128) {
+    uint32_t w = 0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) w |= (__ldg(mh + 32 * threadIdx.x + i) != 0u ? 1u : 0u) << i;
+    bm[threadIdx.x] = w;
+  }
+  __syncthreads();
+  uint16_t *pl = bins + (size_t)k * n_px;
+  auto mask2 = [&](uint32_t v) {                   // two u16 entries (8 * bin each)
+    const uint32_t b0 = (v & 0xffffu) >> 3, b1 = v >> 19;
+    uint32_t o = v;
+    if (b0 < 4096u && !((bm[b0 >> 5] >> (b0 & 31u)) & 1u)) o = (o & 0xffff0000u) | BIN_ZERO;
+    if (b1 < 4096u && !((bm[b1 >> 5] >> (b1 & 31u)) & 1u)) o = (o & 0x0000ffffu) | (BIN_ZERO << 16);
+    return o;
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(pl) & 15u) == 0);
+  const int n_grp = vec ? n_px / 8 : 0;            // groups of 8 entries (16 bytes)
+  const int per = (n_grp + chunks - 1) / chunks;
+  const int beg = blockIdx.x * per, end = min(n_grp, beg + per);
+  for (int g = beg + threadIdx.x; g < end; g += 256) {
+    uint4 v = *reinterpret_cast<const uint4 *>(pl + 8 * (size_t)g);
+    const uint4 o = make_uint4(mask2(v.x), mask2(v.y), mask2(v.z), mask2(v.w));
+    if (o.x != v.x || o.y != v.y || o.z != v.z || o.w != v.w) *reinterpret_cast<uint4 *>(pl + 8 * (size_t)g) = o;
+  }
+  if (blockIdx.x == 0)                             // tail (and unaligned planes): entry by entry
+    for (int p = 8 * n_grp + threadIdx.x; p < n_px; p += 256) {
+      const uint32_t b = pl[p] >> 3;
+      if (b < 4096u && !((bm[b >> 5] >> (b & 31u)) & 1u)) pl[p] = (uint16_t)BIN_ZERO;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // track() — src/camshift.js:213-312.  One CTA per slot runs getWeights, the <=10 mean-shift
 // iterations and the camShift epilogue for n_calls successive track() calls on the same frame.
 
@@ -174,6 +229,14 @@ __device__ __noinline__ Mom moments_serial(const uint16_t *__restrict__ px, int 
   return m;
 }
 
+#ifndef HT_TRACK_MBAR
+#define HT_TRACK_MBAR 0   // 1: partial moments travel with st.async + mbarrier (no cluster barrier, one CTA barrier per pass); measured 3.20 vs 3.15 ms - no gain, left off
+#endif
+__device__ __forceinline__ double warp_sum_all(double v) {   // every lane gets the total (same tree in every warp)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -273,7 +336,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         // use_list == 2: the k-th cluster runs stream bail_list[list_off + k] (k_track_rank's order)
         int list_off,
         // optional timeline (HT_TRACK_TRACE=1): per stream {globaltimer at start, at end, SM id, passes}
-        unsigned long long *__restrict__ trace,
+        unsigned long long *__restrict__ trace, size_t trace_stride,
         // memo != 0: moments are a pure function of (frame, weights, window) and all three are fixed for the calls of
         // one launch, so the leader keeps the moments of the last windows it has seen and re-uses them when
         // mean-shift returns to one of them (a converged stream, or one oscillating between two windows)
@@ -295,6 +358,13 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   // next window, barrier).  cpart is double-buffered by pass parity: a CTA that is already exchanging pass p+1
   // cannot overwrite what a slower CTA still reads for pass p.
   __shared__ double cpart[2][TRACK_CLUSTER_MAX][6];  // partial moments of every CTA of the cluster (written remotely)
+  // HT_TRACK_MBAR: every WARP of every CTA of the cluster sends its six partial sums straight into every CTA's wpart
+  // (st.async through distributed shared memory, completing bytes on the receiver's mbarrier); warp 0 of each CTA waits
+  // for 48 * C * NW bytes and adds them up in a fixed order.  Replaces red[] + __syncthreads + the cross-warp sum +
+  // cluster.sync (arrive.release / wait.acquire: 11 % of the kernel's samples plus 3.5 % for the CTA barrier).
+  constexpr bool MBAR = HT_TRACK_MBAR && TRACK_CLUSTER > 1 && TRACK_CLUSTER * NW <= 128;   // (12 KB of slots at most)
+  __shared__ double wpart[MBAR ? 2 : 1][MBAR ? TRACK_CLUSTER * NW : 1][6];
+  __shared__ __align__(8) unsigned long long mbar[2];
   __shared__ int win[4];                          // wadx, wady, wadw, wadh of the next pass
   __shared__ int ctrl;                            // 0 = run another pass over win[], 1 = this stream is finished
   constexpr int MEMO_N = 8;
@@ -377,13 +447,38 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
     it = 0; prevx = s.sx; prevy = s.sy;                            // :280-281
     return false;
   };
-  if (TRACK_CLUSTER > 1) cluster.sync();  // every CTA is resident before the first remote shared-memory access
+  if (MBAR && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&mbar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&mbar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (TRACK_CLUSTER > 1) cluster.sync();  // every CTA is resident (and its mbarriers initialised) before the first remote access
   if (stepper) publish(start_call() ? 1 : 0);
   __syncthreads();
 
+#ifndef HT_TRACK_LOOP2
+#define HT_TRACK_LOOP2 1   // 1: leaner pixel loop (column blocks outer, x factors per block, edge selects only where needed)
+#endif
+#ifndef HT_TRACK_PASSTRACE
+#define HT_TRACK_PASSTRACE 0   // 1 (profiling build): the leader thread accumulates the clock cycles of each phase of a pass
+#endif
+#if HT_TRACK_PASSTRACE
+  long long pt_acc[5] = {0, 0, 0, 0, 0};
+  long long pt_t = 0;
+#define HT_PT_MARK(i) do { if (trace && leader) { const long long now_ = clock64(); pt_acc[i] += now_ - pt_t; pt_t = now_; } } while (0)
+#else
+#define HT_PT_MARK(i) do { } while (0)
+#endif
   constexpr int ROW_STRIDE = NW * TRACK_CLUSTER;
+  unsigned pass_no = 0;        // passes of this stream so far (uniform over the cluster): mbarrier / buffer parity
   while (!ctrl) {
     const int wx = win[0], wy = win[1], ww = win[2] - win[0], wh = win[3] - win[1];
+#if HT_TRACK_PASSTRACE
+    if (trace && leader) pt_t = clock64();
+#endif
+    if (MBAR && tid == 0)      // arm this pass's mbarrier: one arrival (this one) + the bytes all warps of all CTAs will send
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&mbar[parity])),
+                   "r"((unsigned)(48 * TRACK_CLUSTER * NW)) : "memory");
     // Each lane reads 4 adjacent pixels (one 8 B load of 4 colour bins) of 4 rows per step.  Rows are assigned by
     // ABSOLUTE frame row (a CTA keeps hitting its own L1 lines when the window shifts between passes).  The steps of
     // a pass (row group x 128-pixel column block) are software-pipelined: the four loads of step t+1 are issued
@@ -394,6 +489,87 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
     const int xbeg = wx & ~3, xend = wx + ww;
     const int mine = crank * NW + warp;                          // rows with (wy+yy) % ROW_STRIDE == mine
     const int yy0 = (mine - (wy % ROW_STRIDE) + ROW_STRIDE) % ROW_STRIDE;
+#if HT_TRACK_LOOP2
+    if (vec4) {
+      // Round 2, call 16: under load a pass is bound by the instructions its warps issue (6 warps per scheduler), and a
+      // 16-pixel step cost ~330 of them - 50 for the four loads' address / predicate arithmetic, 16 selects for the window
+      // edge, the x factors (4 I2F.F64 + 4 DMUL) recomputed in every step.  Here: column blocks are the OUTER loop (x
+      // factors once per block, kept across its row groups), 32-bit row offsets, selects only in blocks that contain a
+      // window edge (warp-uniform), the row coordinate advanced by additions.
+      const int n_x = (xend - xbeg + 127) >> 7;
+      const int n_rg = (yy0 < wh) ? (wh - yy0 + 4 * ROW_STRIDE - 1) / (4 * ROW_STRIDE) : 0;
+      const int total = n_rg * n_x;
+      const uint16_t *col = px + (size_t)wy * W + xbeg + 4 * lane;
+      const uint32_t wsm_base = (uint32_t)__cvta_generic_to_shared(wsm);
+      const uint32_t rs = (uint32_t)ROW_STRIDE * (uint32_t)W;          // elements between two consecutive rows of this warp
+      auto issue = [&](int rg, int xi, uint2 (&v)[4]) {
+        const bool col_ok = xbeg + 4 * lane + 128 * xi < xend;
+        const int y0 = yy0 + 4 * rg * ROW_STRIDE;
+        const uint16_t *q = col + ((uint32_t)y0 * (uint32_t)W + 128u * (uint32_t)xi);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = (col_ok && y0 + j * ROW_STRIDE < wh) ? __ldg(reinterpret_cast<const uint2 *>(q + (uint32_t)j * rs))
+                                                    : make_uint2(BIN_ZERO2, BIN_ZERO2);
+      };
+      double vx[4] = {0, 0, 0, 0}, vx2[4] = {0, 0, 0, 0};
+      unsigned in_mask = 0;
+      bool edge_any = true;
+      int cur_xi = -1;
+      auto consume = [&](int rg, int xi, const uint2 (&v)[4]) {
+        if (xi != cur_xi) {                                            // uniform over the warp
+          cur_xi = xi;
+          const int x4 = xbeg + 4 * lane + 128 * xi;
+          const double vx0 = (double)(x4 - wx);
+          in_mask = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            vx[i] = vx0 + (double)i;
+            vx2[i] = vx[i] * vx[i];
+            if (x4 + i >= wx && x4 + i < xend) in_mask |= 1u << i;
+          }
+          edge_any = __any_sync(0xffffffffu, in_mask != 15u);          // some lane of this block has pixels outside the window
+        }
+        const double vy0 = (double)(yy0 + 4 * rg * ROW_STRIDE);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // a 128-pixel row segment whose entries are all ZERO (k_bins_mask: colours absent from the model; rows below
+          // the window) adds +0.0 to every sum: skip it with one vote (uniform over the warp)
+          if (!__any_sync(0xffffffffu, v[j].x != BIN_ZERO2 || v[j].y != BIN_ZERO2)) continue;
+          uint32_t b[4] = {v[j].x & 0xffffu, v[j].x >> 16, v[j].y & 0xffffu, v[j].y >> 16};   // table offsets (8 * bin)
+          if (edge_any) {   // pixels outside the window read the extra table entry wsm[4096] == +0.0
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = ((in_mask >> i) & 1u) ? b[i] : BIN_ZERO;
+          }
+          double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double val = lds_f64(wsm_base + b[i]);
+            r0 += val;
+            r1 = fma(vx[i], val, r1);     // fused: this fast path is validated by trunc_ambiguous, the strict
+            r2 = fma(vx2[i], val, r2);    // reference order (separate multiply and add) is moments_serial
+          }
+          const double vy = vy0 + (double)(j * ROW_STRIDE);
+          a00 += r0; a10 += r1; a20 += r2;
+          a01 = fma(vy, r0, a01); a11 = fma(vy, r1, a11); a02 = fma(vy * vy, r0, a02);
+        }
+      };
+      // software pipeline over the steps (row group fastest inside a column block): the loads of step t+1 are in flight
+      // during the arithmetic of step t
+      uint2 va[4], vb[4];
+      int rg = 0, xi = 0;
+      if (total > 0) issue(0, 0, va);
+      for (int t = 0; t < total; t += 2) {
+        int rg1 = rg + 1, xi1 = xi;
+        if (rg1 == n_rg) { rg1 = 0; ++xi1; }
+        if (t + 1 < total) issue(rg1, xi1, vb);
+        consume(rg, xi, va);
+        int rg2 = rg1 + 1, xi2 = xi1;
+        if (rg2 == n_rg) { rg2 = 0; ++xi2; }
+        if (t + 2 < total) issue(rg2, xi2, va);
+        if (t + 1 < total) consume(rg1, xi1, vb);
+        rg = rg2; xi = xi2;
+      }
+#else
     if (vec4) {
       const int n_x = (xend - xbeg + 127) >> 7;
       const int n_rg = (yy0 < wh) ? (wh - yy0 + 4 * ROW_STRIDE - 1) / (4 * ROW_STRIDE) : 0;
@@ -423,6 +599,9 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          // a 128-pixel row segment whose entries are all ZERO (k_bins_mask: colours absent from the model; rows below
+          // the window) adds +0.0 to every sum: skip it with one vote (uniform over the warp)
+          if (!__any_sync(0xffffffffu, v[j].x != BIN_ZERO2 || v[j].y != BIN_ZERO2)) continue;
           const int y = yy0 + (4 * rg + j) * ROW_STRIDE;
           // table offsets (the plane holds 8 * bin); rows below the window were "loaded" as ZERO_W by issue()
           const uint32_t b[4] = {v[j].x & 0xffffu, v[j].x >> 16, v[j].y & 0xffffu, v[j].y >> 16};
@@ -454,6 +633,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         if (t + 1 < total) consume(rg1, xi1, vb);
         rg = rg2; xi = xi2;
       }
+#endif
     } else {
       for (int yy = yy0; yy < wh; yy += 4 * ROW_STRIDE) {
         double r[4][3];
@@ -472,6 +652,44 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         }
       }
     }
+    HT_PT_MARK(0);                     // pixel loop of this thread (loads, lookups, FMAs)
+    Mom msum = {0, 0, 0, 0, 0, 0};   // (MBAR) the window's moments, valid in thread 0
+    if (MBAR) {
+      a00 = warp_sum_all(a00); a10 = warp_sum_all(a10); a01 = warp_sum_all(a01);
+      a11 = warp_sum_all(a11); a20 = warp_sum_all(a20); a02 = warp_sum_all(a02);
+      const unsigned l_slot = (unsigned)__cvta_generic_to_shared(&wpart[MBAR ? parity : 0][MBAR ? crank * NW + warp : 0][0]);
+      const unsigned l_bar = (unsigned)__cvta_generic_to_shared(&mbar[parity]);
+      for (int idx = lane; idx < 6 * TRACK_CLUSTER; idx += 32) {   // lane -> (quantity q, destination CTA r)
+        const int q = idx % 6, r = idx / 6;
+        const double val = q == 0 ? a00 : q == 1 ? a10 : q == 2 ? a01 : q == 3 ? a11 : q == 4 ? a20 : a02;
+        unsigned r_slot, r_bar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_slot) : "r"(l_slot + 8u * (unsigned)q), "r"(r));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_bar) : "r"(l_bar), "r"(r));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                     ::"r"(r_slot), "l"(__double_as_longlong(val)), "r"(r_bar) : "memory");
+      }
+      if (warp == 0) {
+        // wait for this pass's phase of the mbarrier (it is used every second pass: phase bit = bit 1 of pass_no)
+        const unsigned phase = (pass_no >> 1) & 1u;
+        unsigned done = 0;
+        for (int spin = 0; !done && spin < (1 << 26); ++spin)   // bounded: a protocol error must not hang the device
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(l_bar), "r"(phase) : "memory");
+        if (!done) __trap();
+        // fixed-order sum of the C * NW slots: lane = (quantity q, residue g5 of the slot index mod 5), then the five
+        // partial sums of each quantity in ascending order - the same code on the same data in every CTA of the cluster
+        const int q = lane % 6, g5 = lane / 6;
+        double acc = 0.0;
+        if (g5 < 5)
+          for (int e = g5; e < TRACK_CLUSTER * NW; e += 5) acc += wpart[MBAR ? parity : 0][MBAR ? e : 0][q];
+        double t = acc;
+#pragma unroll
+        for (int j = 1; j < 5; ++j) t += __shfl_sync(0xffffffffu, acc, (q + 6 * j) & 31);
+        msum.m00 = __shfl_sync(0xffffffffu, t, 0); msum.m10 = __shfl_sync(0xffffffffu, t, 1);
+        msum.m01 = __shfl_sync(0xffffffffu, t, 2); msum.m11 = __shfl_sync(0xffffffffu, t, 3);
+        msum.m20 = __shfl_sync(0xffffffffu, t, 4); msum.m02 = __shfl_sync(0xffffffffu, t, 5);
+      }
+    } else {
     a00 = warp_sum(a00); a10 = warp_sum(a10); a01 = warp_sum(a01);
     a11 = warp_sum(a11); a20 = warp_sum(a20); a02 = warp_sum(a02);
     if (lane == 0) {
@@ -479,6 +697,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
       red[warp][3] = a11; red[warp][4] = a20; red[warp][5] = a02;
     }
     __syncthreads();
+    HT_PT_MARK(1);                     // warp sums + wait for the CTA's slowest warp
     if (tid < 6 * TRACK_CLUSTER) {   // fixed-order sums (run-to-run deterministic), one copy into every CTA
       const int q = tid % 6, r = tid / 6;
       double t = 0;
@@ -486,12 +705,15 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
       cluster.map_shared_rank(&cpart[0][0][0], r)[(parity * TRACK_CLUSTER_MAX + crank) * 6 + q] = t;
     }
     if (TRACK_CLUSTER > 1) cluster.sync(); else __syncthreads();
+    }
+    HT_PT_MARK(2);                     // cross-warp sum, remote stores, cluster barrier (wait for the slowest CTA)
     if (stepper) {
-      Mom m = {0, 0, 0, 0, 0, 0};
-      for (int r = 0; r < TRACK_CLUSTER; ++r) {
-        m.m00 += cpart[parity][r][0]; m.m10 += cpart[parity][r][1]; m.m01 += cpart[parity][r][2];
-        m.m11 += cpart[parity][r][3]; m.m20 += cpart[parity][r][4]; m.m02 += cpart[parity][r][5];
-      }
+      Mom m = msum;
+      if (!MBAR)
+        for (int r = 0; r < TRACK_CLUSTER; ++r) {
+          m.m00 += cpart[parity][r][0]; m.m10 += cpart[parity][r][1]; m.m01 += cpart[parity][r][2];
+          m.m11 += cpart[parity][r][3]; m.m20 += cpart[parity][r][4]; m.m02 += cpart[parity][r][5];
+        }
       bool exact = false;          // m is in the reference's strict summation order (moments_serial)
       bool fresh = true;           // m was computed by this pass (false: taken from the memo)
       int cw0 = win[0], cw1 = win[1], cw2 = win[2], cw3 = win[3];   // the window m belongs to
@@ -589,8 +811,11 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         break;
       }
     }
+    HT_PT_MARK(3);                     // scalar mean-shift step
     parity ^= 1;
+    ++pass_no;
     __syncthreads();
+    HT_PT_MARK(4);                     // CTA barrier that publishes the next window
   }
   if (leader) {
     if (cost) {
@@ -607,6 +832,10 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       trace[4 * (size_t)k + 1] = t; trace[4 * (size_t)k + 3] = st_pass;
+#if HT_TRACK_PASSTRACE
+      // phase totals (SM clock cycles) behind the per-stream records: [max_frames x 4][max_frames x 8]
+      for (int i = 0; i < 5; ++i) trace[trace_stride + 8 * (size_t)k + i] = (unsigned long long)pt_acc[i];
+#endif
     }
     if (bailed) {   // phase B continues this stream from call `call`
       calls_done[k] = call;

@@ -242,6 +242,10 @@ int ht_join(ht_ctx *ctx);
  * at end, SM id of the leading CTA, moment passes}.  Only for contexts created with HT_TRACK_TRACE=1 in the
  * environment (tools/track_timeline.py); HT_ERR_ARG otherwise. */
 int ht_debug_track_trace(ht_ctx *ctx, uint64_t *out, int n_streams);
+/* profiling builds (-DHT_TRACK_PASSTRACE=1) only, zeros otherwise: 8 x u64 per stream, the SM clock cycles the leading
+ * thread spent in each phase of its passes {pixel loop, warp sums + CTA barrier, exchange + cluster barrier, scalar
+ * mean-shift step, publishing barrier, 0, 0, 0}, summed over the launch. */
+int ht_debug_track_phases(ht_ctx *ctx, uint64_t *out, int n_streams);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ht_launch_count(const ht_ctx *ctx);
 

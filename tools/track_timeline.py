@@ -79,6 +79,27 @@ def main():
     for i in late:
         print(f"  last finishers: stream {i} (frame {i % 64}) start {start[i]:.0f} end {end[i]:.0f} passes {passes[i]} sm {tr[i, 2]}")
 
+    phases(ctx, n, tr)
+
+
+
+
+def phases(ctx, n, tr):
+    """Per-phase cycles of a pass (profiling builds, HT_LIB=...libht_ptrace.so): where does a pass spend its time?"""
+    ph = ctx.debug_track_phases(n).astype(np.float64)
+    if ph.sum() == 0:
+        return
+    passes = np.maximum(tr[:, 3].astype(np.float64), 1)
+    names = ["pixel loop", "warp sums + CTA barrier", "exchange + cluster barrier", "mean-shift step", "publish barrier"]
+    order = np.argsort(-passes * 1e6 - (tr[:, 1] - tr[:, 0]))
+    groups = {"16 longest chains": order[:16], "next 64": order[16:80], "median 128": order[len(order) // 2 - 64: len(order) // 2 + 64],
+              "all": order}
+    print("cycles per pass (leader thread, SM clock) by phase:")
+    for gname, idx in groups.items():
+        per = ph[idx, :5].sum(axis=0) / passes[idx].sum()
+        tot = per.sum()
+        print(f"  {gname:18s} total {tot:8.0f}  " + "  ".join(f"{nm}: {v:7.0f} ({100 * v / tot:4.1f}%)" for nm, v in zip(names, per)))
+
 
 if __name__ == "__main__":
     main()
