@@ -526,6 +526,34 @@ def run_ours(args, cfg):
     e2e_s = timed_e2e()
     e2e_value = world * frames_per_step * args.steps / e2e_s
 
+    # ---- the same steps without pipelining (every step joins its own tracking), reported beside the headline ----
+    unpipelined = None
+    if pipe:
+        ctx.set_pipeline(False)
+        step_guarded()
+        barrier()
+        ctx.profile(True)
+        ctx.profile_read(reset=True)
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record(stream)
+        for _ in range(args.steps):
+            step_guarded()
+        drain()
+        u1.record(stream)
+        barrier()
+        u_ms = u0.elapsed_time(u1)
+        u_prof = ctx.profile_read(reset=True)
+        ctx.profile(False)
+        if world > 1:
+            t = torch.tensor([u_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            u_ms = float(t.item())
+        unpipelined = {"value": world * frames_per_step * args.steps / (u_ms / 1e3), "ms_per_step": u_ms / args.steps,
+                       "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in u_prof.items()},
+                       "note": "ht_set_pipeline off: the tracking of a step completes before the next step's detection starts "
+                               "(per-kernel times without the waits that pipelining shows in kernel_ms_per_step)"}
+        ctx.set_pipeline(True)
+
     # ---- library default (window memo on): same steps, device-resident and e2e ----
     memo = None
     if workload == "detect_track30":
@@ -624,6 +652,8 @@ def run_ours(args, cfg):
                                "faces_found": int((ev[..., 1] & 1).sum()), "faces_lost": int(((ev[..., 1] >> 1) & 1).sum())}
         if shard_check is not None:
             line["shard_check"] = shard_check
+        if unpipelined is not None:
+            line["unpipelined"] = unpipelined
         if memo is not None:
             line["memo"] = memo
         if world == 1 and not args.no_cpu_baseline:

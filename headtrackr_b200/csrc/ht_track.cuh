@@ -457,7 +457,7 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   __syncthreads();
 
 #ifndef HT_TRACK_LOOP2
-#define HT_TRACK_LOOP2 1   // 1: leaner pixel loop (column blocks outer, x factors per block, edge selects only where needed)
+#define HT_TRACK_LOOP2 0   // 1: column blocks outer, x factors per block, edge selects only where needed - measured 3.01 vs 2.97 ms: no gain, left off
 #endif
 #ifndef HT_TRACK_PASSTRACE
 #define HT_TRACK_PASSTRACE 0   // 1 (profiling build): the leader thread accumulates the clock cycles of each phase of a pass
@@ -735,44 +735,42 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
         const bool conv = (s.sx == prevx && s.sy == prevy);         // :299
         bool done = false;
         if (conv || it == 9) {
-          // final moments (second == true) are those of this window; make the <<2 truncations safe
-          if (!exact) {
-            const double xc = m.m10 * inv, yc = m.m01 * inv;
-            const double a = (m.m20 - m.m10 * xc) * inv, c = (m.m02 - m.m01 * yc) * inv;
-            bool amb;
+          // final moments (second == true) are those of this window.  camShift epilogue - src/camshift.js:230-258 -
+          // computed once; when the moments are in the parallel order and a `<< 2` truncation (or, with angles, the sign
+          // of b) is not safe, the strict moments replace them and the epilogue is recomputed from those.
+          s.sx = max(0, min(s.sx, W));                                   // :308-309
+          s.sy = max(0, min(s.sy, H));
+          for (;;) {
+            const double invM00 = 1.0 / m.m00;
+            const double xc = m.m10 * invM00, yc = m.m01 * invM00;
+            const double mu20 = m.m20 - m.m10 * xc, mu02 = m.m02 - m.m01 * yc, mu11 = m.m11 - m.m01 * xc;
+            const double a = mu20 * invM00, c = mu02 * invM00;
+            double l1, l2, ang = 3.141592653589793 / 2;
+            bool amb = false;
             if (s.calc_angles) {
-              const double b = (m.m11 - m.m01 * xc) * inv, d = a + c;
+              const double b = mu11 * invM00;
+              const double d = a + c;
               const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
-              amb = trunc_ambiguous(sqrt((d - e) * 0.5)) || trunc_ambiguous(sqrt((d + e) * 0.5));
+              l1 = sqrt((d - e) * 0.5); l2 = sqrt((d + e) * 0.5);
               // `if (ang < 0) ang += PI` (src/camshift.js:244) follows the SIGN of b = mu11 / m00: for a symmetric blob
               // b is rounding residue and the parallel summation order may flip it (angle off by PI, far outside
               // the 1e-4 tolerance) - take the strict order whenever b is not clearly away from 0
-              amb = amb || fabs(b) <= 1e-9 * (fabs(a) + fabs(c) + 1.0);
+              amb = fabs(b) <= 1e-9 * (fabs(a) + fabs(c) + 1.0);
+              if (exact || !(amb || trunc_ambiguous(l1) || trunc_ambiguous(l2))) {
+                ang = atan2(2 * b, a - c + e);
+                if (ang < 0) ang = ang + 3.141592653589793;
+              }
             } else {
-              amb = trunc_ambiguous(sqrt(a)) || trunc_ambiguous(sqrt(c));
+              l1 = sqrt(a); l2 = sqrt(c);
             }
-            if (amb) { m = moments_serial(px, W, cw0, cw1, cw2, cw3, wsm); exact = true; ++st_serial; }
-          }
-          s.sx = max(0, min(s.sx, W));                                   // :308-309
-          s.sy = max(0, min(s.sy, H));
-          // camShift epilogue — src/camshift.js:230-258
-          const double invM00 = 1.0 / m.m00;
-          const double xc = m.m10 * invM00, yc = m.m01 * invM00;
-          const double mu20 = m.m20 - m.m10 * xc, mu02 = m.m02 - m.m01 * yc, mu11 = m.m11 - m.m01 * xc;
-          const double a = mu20 * invM00, c = mu02 * invM00;
-          if (s.calc_angles) {
-            const double b = mu11 * invM00;
-            const double d = a + c;
-            const double e = sqrt((4 * b * b) + ((a - c) * (a - c)));
-            s.tw = (int32_t)((uint32_t)js_to_int32(sqrt((d - e) * 0.5)) << 2);
-            s.th = (int32_t)((uint32_t)js_to_int32(sqrt((d + e) * 0.5)) << 2);
-            double ang = atan2(2 * b, a - c + e);
-            if (ang < 0) ang = ang + 3.141592653589793;
+            if (!exact && (amb || trunc_ambiguous(l1) || trunc_ambiguous(l2))) {
+              m = moments_serial(px, W, cw0, cw1, cw2, cw3, wsm); exact = true; ++st_serial;
+              continue;
+            }
+            s.tw = (int32_t)((uint32_t)js_to_int32(l1) << 2);
+            s.th = (int32_t)((uint32_t)js_to_int32(l2) << 2);
             s.angle = ang;
-          } else {
-            s.tw = (int32_t)((uint32_t)js_to_int32(sqrt(a)) << 2);
-            s.th = (int32_t)((uint32_t)js_to_int32(sqrt(c)) << 2);
-            s.angle = 3.141592653589793 / 2;
+            break;
           }
           s.tx = (int32_t)floor(fmax(0.0, fmin(s.sx + s.sw / 2.0, (double)W)));   // :253-254
           s.ty = (int32_t)floor(fmax(0.0, fmin(s.sy + s.sh / 2.0, (double)H)));
