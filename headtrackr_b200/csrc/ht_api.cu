@@ -340,7 +340,13 @@ int parse_cascade(const void *blob, size_t len, HostCascade &hc, std::string &er
   // numbers are not 8-digit decimals, lane-per-window groups to the end.
   {
     int g = 0;
-    const int cuts_fast[] = {0, 2, 3, 4, 6};      // {0,1} {2} {3} {4,5} {6,7}: the generated stages
+#if HT_GROUP_SPLIT >= 2
+    const int cuts_fast[] = {0, 2, 3, 4, 5, 6, 7};   // {0,1} {2} {3} {4} {5} {6} {7}
+#elif HT_GROUP_SPLIT == 1
+    const int cuts_fast[] = {0, 2, 3, 4, 5, 6};      // {0,1} {2} {3} {4} {5} {6,7}
+#else
+    const int cuts_fast[] = {0, 2, 3, 4, 6};         // {0,1} {2} {3} {4,5} {6,7}: the generated stages
+#endif
     const int cuts_int[] = {0, 2, 4, 6};
     const int cuts_fp[] = {0, 2, 4, 6, 9};
     static_assert(HT_GEN_STAGES == 8, "cuts_fast assumes 8 generated stages");

@@ -94,6 +94,12 @@ __host__ __device__ constexpr int bank_class(int u, int v) { return (u + BANK_K 
 // the window of class c at (v, uh)
 __host__ __device__ constexpr int class_u(int c, int v, int uh) { return ((c - BANK_K * v) & 31) + 32 * uh; }
 
+// survivor groups of the generated cascade after the dense group {0,1}: 0: {2} {3} {4,5} {6,7}; 1: {2} {3} {4} {5} {6,7};
+// 2: {2} {3} {4} {5} {6} {7}.  A split costs a CTA barrier and repacks the survivors (tools/early_exit_model.py: 9 live
+// lanes per warp iteration in stage 5 and 6 in stage 7 with the groups of 0).
+#ifndef HT_GROUP_SPLIT
+#define HT_GROUP_SPLIT 0
+#endif
 constexpr int MAX_STAGES = 64;
 constexpr int MAX_GROUPS = 16;
 

@@ -222,6 +222,14 @@ __global__ void __launch_bounds__(256) k_ingest(const uint8_t *__restrict__ src,
 // complete).  Block = 32 x 32 pixels of one destination plane of one frame quad; thread = one column x 4 rows.
 // Every load and store is a whole word (4 frames): the tap positions, weights and addresses - most of round 1's
 // 43 instructions per output pixel - are computed once for four frames.
+// byte f (= frame f of the quad) of a pyramid word, zero-extended
+__host__ __device__ __forceinline__ uint32_t quad_byte(uint32_t w, int f) {
+#ifdef __CUDA_ARCH__
+  return __byte_perm(w, 0u, 0x4440u + (unsigned)f);
+#else
+  return (w >> (8 * f)) & 0xffu;
+#endif
+}
 __host__ __device__ __forceinline__ void resample_thread(const DevPlan &plan, int tile0, uint32_t *__restrict__ arena,
                                                          size_t quad_stride, int bx, int by, int tid) {
   // per-block metadata: one 8 B tile record and one 64 B job record, fetched with vector loads
@@ -280,8 +288,9 @@ __host__ __device__ __forceinline__ void resample_thread(const DevPlan &plan, in
       const uint32_t w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1[r], w11 = wx1 * wy1[r];   // sum = 4 dw dh
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
-        const uint32_t a = (p[r][0] >> (8 * f)) & 0xffu, b = (p[r][1] >> (8 * f)) & 0xffu;
-        const uint32_t c = (p[r][2] >> (8 * f)) & 0xffu, d = (p[r][3] >> (8 * f)) & 0xffu;
+        // byte f of the four tap words: one PRMT each (shift + mask compiled to SHF + LOP3: 6 instructions per word)
+        const uint32_t a = quad_byte(p[r][0], f), b = quad_byte(p[r][1], f);
+        const uint32_t c = quad_byte(p[r][2], f), d = quad_byte(p[r][3], f);
         // == (wx0 a + wx1 b) wy0 + (wx0 c + wx1 d) wy1 + half  <= 255.5 * 4 dw dh < 2^32 (checked by the planner)
         const uint32_t num = w00 * a + w01 * b + w10 * c + w11 * d + half;
         out |= (uint32_t)(((uint64_t)num * magic) >> shift) << (8 * f);
@@ -810,8 +819,18 @@ __global__ void __launch_bounds__(CASCADE_THREADS, HT_CASC_MINB) k_cascade(DevPl
 #if HT_CT_GROUPS
     if (g < 2 && run_group(IntC<2>{}, IntC<3>{}, false)) return;
     if (run_group(IntC<3>{}, IntC<4>{}, false)) return;
+#if HT_GROUP_SPLIT >= 1     // {4} {5}: one more barrier, survivors repacked between the two stages
+    if (run_group(IntC<4>{}, IntC<5>{}, false)) return;
+    if (run_group(IntC<5>{}, IntC<6>{}, false)) return;
+#else
     if (run_group(IntC<4>{}, IntC<6>{}, false)) return;
+#endif
+#if HT_GROUP_SPLIT >= 2     // {6} {7}
+    if (run_group(IntC<6>{}, IntC<7>{}, false)) return;
+    if (run_group(IntC<7>{}, IntC<8>{}, !has_late)) return;
+#else
     if (run_group(IntC<6>{}, IntC<8>{}, !has_late)) return;
+#endif
 #else   // one rolled copy of the group code (62 registers, no spills) - measured slower: 6.55 vs 6.28 ms per 1024 frames
     for (; g < c_casc.n_groups; ++g)
       if (run_group(c_casc.group_first[g], c_casc.group_first[g + 1], (g == c_casc.n_groups - 1) && !has_late)) return;

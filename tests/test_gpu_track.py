@@ -232,3 +232,35 @@ def test_window_memo_does_not_change_results(ctx, blob):
         if fnd:
             o = runs[True][1][i]
             assert (o["x"], o["y"], o["width"], o["height"]) == (obj["x"], obj["y"], obj["width"], obj["height"])
+
+
+@pytest.mark.parametrize("W,H", [(320, 240), (333, 251)])
+def test_zero_weight_marking_changes_nothing(blob, W, H, monkeypatch):
+    """k_bins_mask rewrites the plane entries of colours absent from the model histogram to the table's +0.0 entry and
+    k_track skips all-zero row segments (src/camshift.js:314-330: such pixels have weight exactly 0): every output equals
+    the unmarked run's and the oracle's - also for odd frame sizes (unaligned planes take the scalar path)."""
+    import os
+    from headtrackr_b200.context import Context
+    frames = synth.batch(3, W, H, start=2)
+    rects = [face_rect(blob, frames[i]) for i in range(3)]
+    results = {}
+    for tag, env in (("marked", "1,0"), ("unmarked", "0")):
+        monkeypatch.setenv("HT_TRACK_MASK", env)
+        c = Context(max_width=W, max_height=H, max_frames=3, max_raw_per_frame=4096)
+        try:
+            c.set_track_memo(False)
+            c.track_init(frames, rects, calc_angles=True)
+            results[tag] = c.track(frames, n_calls=12)
+        finally:
+            c.close()
+    assert results["marked"] == results["unmarked"]
+    objs, wins = results["marked"]
+    for i in range(3):
+        ot = oracle.CamshiftTracker(calc_angles=True)
+        ot.init_tracker(frames[i], *rects[i])
+        for _ in range(12):
+            ot.track(frames[i])
+        w = ot.track_obj()
+        assert (objs[i]["x"], objs[i]["y"], objs[i]["width"], objs[i]["height"]) == (w["x"], w["y"], w["width"], w["height"])
+        assert abs(objs[i]["angle"] - w["angle"]) <= 1e-4
+        assert wins[i] == ot.search_window()
