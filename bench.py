@@ -185,19 +185,22 @@ def cpu_stream(frames, blob, interval):
     return len(frames)
 
 
-def cpu_step(cfg, frames, blob, threads):
+def cpu_step(cfg, frames, blob, threads, keep=None):
     import oracle
 
     def one(i):   # one C call per frame (the GIL is released for its whole duration)
         if cfg["workload"] == "streams":
             return cpu_stream(frames[i], blob, cfg["interval"])
         if cfg["track_calls"] > 0:
-            return oracle.detect_track(frames[i], blob, cfg["interval"], 1, False, cfg["track_calls"])[0]
-        return len(oracle.detect(frames[i], blob, cfg["interval"], 1))
+            n, found, obj = oracle.detect_track(frames[i], blob, cfg["interval"], 1, False, cfg["track_calls"])
+            return (n, found, obj["x"], obj["y"], obj["width"], obj["height"])
+        return (len(oracle.detect(frames[i], blob, cfg["interval"], 1)),)
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:   # ctypes releases the GIL inside the C oracle
-        list(ex.map(one, range(len(frames))))
+        results = list(ex.map(one, range(len(frames))))
+    if keep is not None:
+        keep[:] = results       # what the oracle computed for these frames (the GPU arm checks its own batch against it)
     return time.perf_counter() - t0
 
 
@@ -234,7 +237,7 @@ def cpu_sample_frames(cfg, n_sample):
     return make_base_frames(W, H, 0, n_sample), n_sample
 
 
-def cpu_baseline(cfg, n_sample, blob, steps=1, warmup=0, frames=None):
+def cpu_baseline(cfg, n_sample, blob, steps=1, warmup=0, frames=None, keep=None):
     import oracle
     oracle.lib()
     threads = usable_cores()
@@ -244,7 +247,7 @@ def cpu_baseline(cfg, n_sample, blob, steps=1, warmup=0, frames=None):
         units = len(frames)
     for _ in range(warmup):
         cpu_step(cfg, frames, blob, threads)
-    times = [cpu_step(cfg, frames, blob, threads) for _ in range(steps)]
+    times = [cpu_step(cfg, frames, blob, threads, keep) for _ in range(steps)]
     total = sum(times)
     what = (f"{len(frames)} synthetic streams x {units // max(len(frames), 1)} frames per step" if cfg["workload"] == "streams"
             else f"{units} of the bench's synthetic frames per step")
@@ -398,6 +401,10 @@ def run_ours(args, cfg):
                     gather(rec_srcs[ungathered[0]], time_gather)
                 ungathered[0] = o
         step_no[0] += 1
+
+    def last_outputs():
+        o = (step_no[0] - 1) % n_sets
+        return d_rects[o], d_counts[o], d_found[o], d_objs[o], d_wins[o]
 
     def drain():
         if pipe:
@@ -662,7 +669,29 @@ def run_ours(args, cfg):
                 cb, _ = cpu_baseline(cfg, min(args.cpu_sample, 16), blob)
             else:
                 sample = base if args.cpu_sample <= N_UNIQUE else make_base_frames(W, H, 0, args.cpu_sample)
-                cb, _ = cpu_baseline(cfg, args.cpu_sample, blob, frames=sample[: args.cpu_sample])
+                oracle_results = []
+                cb, _ = cpu_baseline(cfg, args.cpu_sample, blob, frames=sample[: args.cpu_sample], keep=oracle_results)
+                # parity of the TIMED batch: frames 0..N_UNIQUE-1 of the batch are the sample frames (roll 0) - what the
+                # last timed step left on the device for them must equal what the CPU restatement just computed
+                n_chk = min(len(oracle_results), N_UNIQUE, B)
+                if workload == "detect_track30" and n_chk:
+                    o = last_outputs()
+                    got_counts, got_found, got_objs = o[1].cpu().numpy(), o[2].cpu().numpy(), o[3].cpu().numpy()
+                    bad = sum(1 for i in range(n_chk)
+                              if (int(got_counts[i]), int(got_found[i])) != tuple(oracle_results[i][:2]) or
+                              (oracle_results[i][1] and tuple(int(v) for v in got_objs[i, :4]) != tuple(oracle_results[i][2:6])))
+                    line["batch_parity"] = {"frames_checked": n_chk, "mismatches": bad,
+                                            "what": "detection count, face found, track object x/y/width/height of the last "
+                                                    "timed step vs the CPU restatement of the reference on the same frames"}
+                    if bad:
+                        raise SystemExit(f"bench.py: the timed batch differs from the oracle on {bad} of {n_chk} frames")
+                elif workload in ("detect", "detect720") and n_chk:
+                    got_counts = d_counts[0].cpu().numpy()
+                    bad = sum(1 for i in range(n_chk) if int(got_counts[i]) != oracle_results[i][0])
+                    line["batch_parity"] = {"frames_checked": n_chk, "mismatches": bad,
+                                            "what": "grouped detection count of the last timed step vs the CPU restatement"}
+                    if bad:
+                        raise SystemExit(f"bench.py: the timed batch differs from the oracle on {bad} of {n_chk} frames")
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     ctx.close()

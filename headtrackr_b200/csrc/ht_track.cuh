@@ -420,9 +420,10 @@ k_track(const uint16_t *__restrict__ bins, int W, int H, const int32_t *__restri
   {
     const uint32_t *mh = model_hist + (size_t)slot * 4096, *ch = cur_hist + (size_t)k * 4096;
     for (int i = tid; i < 4096; i += NT) {
-      const uint32_t c = ch[i];
+      const uint32_t c = ch[i], m = mh[i];
       double p = 0.0;
-      if (c != 0) p = fmin((double)mh[i] / (double)c, 1.0);
+      // (a bin absent from the model gives 0 / c = +0.0: no division for it - that is nearly all of the 4096 bins)
+      if (c != 0 && m != 0) p = fmin((double)m / (double)c, 1.0);
       wsm[i] = p;
     }
     if (tid == 0) wsm[4096] = 0.0;
