@@ -303,7 +303,10 @@ def run_ours(args, cfg):
     numa = bind_to_gpu_numa_node(local) if world > 1 else {"node": None, "why": "single rank"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a collective that never completes (a rank that died, mismatched calls) aborts the job after 3 minutes instead of
+        # hanging it: every collective of this script finishes in milliseconds
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     W, H, B, interval, track_calls = cfg["width"], cfg["height"], cfg["batch"], cfg["interval"], cfg["track_calls"]
     workload = cfg["workload"]
     streams = workload == "streams"
@@ -440,7 +443,15 @@ def run_ours(args, cfg):
     for _ in range(args.warmup):
         step_guarded()
     barrier()
-    while time.perf_counter() - t_w < 0.6:      # (the extra warm-up steps are not timed)
+    # (extra warm-up steps until nvidia-smi is sampling; not timed.)  The decision to run another one is COLLECTIVE:
+    # every rank reads its own clock, and a rank that left this loop one iteration before the others would pair its next
+    # all_gather with their barrier - a mismatch on the communicator, i.e. a hang.  Rank 0 decides for everybody.
+    while True:
+        more = torch.tensor([1 if time.perf_counter() - t_w < 0.6 else 0], dtype=torch.int32, device="cuda")
+        if world > 1:
+            dist.broadcast(more, src=0)
+        if int(more.item()) == 0:
+            break
         step_guarded()
         barrier()
     l0 = ctx.launch_count

@@ -558,7 +558,7 @@ struct ht_ctx {
   int track_mid_div = 32, track_mid_cluster = 4;  // HT_TRACK_MID=div[,cluster]: the next n/32 costliest streams on clusters of 4
                                                   // (call 4: 4.12 -> 3.40 ms per 1024 x 30 calls with n/16; call 17, with
                                                   // prioritised tier streams: n/64 + n/16 3.17, n/128 + n/32 2.97, n/64 + n/48 3.00)
-  int track_light_div = 0, track_light_nt = 256;  // HT_TRACK_LIGHT=div[,threads]: the cheapest n/div streams on single CTAs
+  double track_light_div = 0; int track_light_nt = 256;  // HT_TRACK_LIGHT=div[,threads]: the cheapest n/div streams (div may be fractional) on single CTAs
   cudaStream_t tier_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // heavy, mid, light, rest (side 3: when tiers are on)
   cudaEvent_t tier_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int track_mask_frames = 4;                // >0: mask only streams whose last launch swept more than this many frames' worth of pixels
@@ -834,7 +834,7 @@ int launch_track(ht_ctx *ctx, int n, int f0, const uint16_t *bins, int w, int h,
       };
       take(ctx->track_heavy_div, ctx->track_heavy_cluster, 256, 0);
       take(ctx->track_mid_div, ctx->track_mid_cluster, 256, 1);
-      const int n_light = (ctx->track_light_div > 0) ? std::min(left, n / ctx->track_light_div) : 0;
+      const int n_light = (ctx->track_light_div > 0) ? std::min(left, (int)((double)n / ctx->track_light_div)) : 0;
       // Round 2, call 8 timeline: with the default tier on the context's own stream (no event wait) its 1,888 CTAs
       // reached the GPU first and filled every slot with ITS costliest streams; the heavy and middle tiers - the
       // longest chains of the launch - started 1.4 ms late and the launch ended at 1.4 + 2.3 ms.  Now every tier sits
@@ -1213,7 +1213,7 @@ int ht_create(ht_ctx **out, const ht_config *cfg, const void *cascade_blob, size
     }
   }
   if (const char *tli = getenv("HT_TRACK_LIGHT")) {
-    c->track_light_div = std::max(0, atoi(tli));
+    c->track_light_div = std::max(0.0, atof(tli));
     if (const char *comma = strchr(tli, ',')) {
       const int ln = atoi(comma + 1);
       if (ln == 128 || ln == 256 || ln == 512) c->track_light_nt = ln;
