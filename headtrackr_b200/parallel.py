@@ -21,3 +21,17 @@ def gather_records(local, world_counts, group=None):
     out = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return torch.cat([out[r][: world_counts[r]] for r in range(world)], dim=0)
+
+
+def agreed(flag, device="cpu", group=None):
+    """Rank 0's `flag` on every rank (one broadcast).  For loops whose exit depends on something rank-local (a clock,
+    a host-side measurement): if each rank decided for itself, a rank leaving one iteration early would pair its next
+    collective with the others' - mismatched operations on one communicator hang.  Without an initialised process group
+    (single process) it is the flag itself."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.broadcast(t, src=0, group=group)
+    return bool(int(t.item()))
