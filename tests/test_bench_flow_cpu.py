@@ -219,3 +219,12 @@ def test_two_ranks_same_collectives_and_right_records(pipeline, workload):
     assert line["n_gpus"] == 2 and line["value"] > 0
     assert line["shard_check"] == {"ranks_checked": 1, "frames_per_rank": 8, "mismatches": 0}
     assert len(line["per_rank"]) == 2 and line["gather"]["overlapped"] is True
+
+
+def test_two_ranks_streams_workload():
+    """config 5's loop (one ht_stream_step per video frame, T frames per step) on two skewed ranks."""
+    argv = ["--width", "64", "--height", "48", "--streams", "2", "--stream-frames", "4", "--steps", "2", "--warmup", "3",
+            "--no-cpu-baseline", "--gpus", "2", "--workload", "streams"]
+    outs = launch(2, argv, skew=0.15)
+    line = json.loads(outs[0].strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["value"] > 0 and "streams" in line
